@@ -1,0 +1,713 @@
+"""
+oracle/neutfem_oracle.py -- TEST INFRASTRUCTURE ONLY. Never imported by the product package.
+
+CPU restatement of the reference k-effective hot path (jujuC31/NeutFEM), numpy/scipy on top of the C
+restatement of the FEM layer (oracle/fem_ref.c):
+
+  * XS storage, defaults, tolerances          reference src/NeutFEM.cpp:113-300, 322-354
+  * BuildMatrices (triplets -> CSC)           reference src/NeutFEM.cpp:402-457, 1036-1302, 1328-1529
+  * diagonal RT0-P0 path                      reference src/NeutFEM.cpp:483-634
+  * BuildFissionRHS / SolveKeff outer loop    reference src/NeutFEM.cpp:1539-1561, 1627-1815
+  * SolveAdjoint                              reference src/NeutFEM.cpp:1877-2082
+  * SolveGroupInternal                        reference src/NeutFEM.cpp:2084-2105
+  * SolveCoarse                               reference src/NeutFEM.cpp:2380-2611
+  * SchurSolver (SetMatrices / Solve / SchurProduct / implicit CG / explicit S)
+                                              reference src/solvers.cpp:67-240, 259-314, 535-636
+  * ChebyshevAccel                            reference src/solvers.cpp:664-756
+
+Third-party boundary: the reference's linear algebra is Eigen ("3.4+", unpinned, not vendored, absent from
+this image). `Eigen::SparseLU` is restated with `scipy.sparse.linalg.splu` (SuperLU, the code SparseLU was
+ported from; COLAMD ordering in both); `setFromTriplets` with scipy COO->CSC (both sum duplicates). Where the
+reference hands a *formed* Schur matrix to an Eigen Krylov class (n_phi < 200 or DIRECT_*; solvers.cpp:328-509)
+the oracle solves it directly with splu -- the Krylov classes only approximate that solution to `tol`.
+
+PARITY UNPINNED at operator level: the reference has no assertions, golden vectors or CI and cannot
+be built here (no Eigen, undefined symbols). What pins this oracle: (i) internal identities checked in
+tests/test_oracle.py (implicit SchurProduct == explicitly formed S; A, S symmetric positive definite; closed
+forms of SURVEY Appendix A); (ii) the reference's published k-eff table README.md:289-292 (tests/golden/).
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+import os
+import subprocess
+import time
+from dataclasses import dataclass, field
+
+import numpy as np
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "liboracle_fem.so")
+
+# enum values as bound by the reference (NeutFEM.hpp:51-57, solvers.hpp:176-190)
+DIRICHLET, NEUMANN, MIRROR, ROBIN, PERIODIC = range(5)
+(DIRECT_LU, DIRECT_LDLT, DIRECT_LLT, CG, CG_DIAG, CG_ICHOL, BICGSTAB, BICGSTAB_DIAG, BICGSTAB_ILU, LCG) = range(10)
+
+
+def build_lib(force: bool = False) -> str:
+    """Compile oracle/fem_ref.c (gcc) into oracle/_build/liboracle_fem.so."""
+    src = os.path.join(_HERE, "fem_ref.c")
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+        os.makedirs(os.path.dirname(_LIB_PATH), exist_ok=True)
+        subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-fvisibility=hidden", "-o", _LIB_PATH, src, "-lm"])
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def _load():
+    global _lib
+    if _lib is None:
+        build_lib()
+        L = ctypes.CDLL(_LIB_PATH)
+        dp = ctypes.POINTER(ctypes.c_double)
+        ip = ctypes.POINTER(ctypes.c_int)
+        lp = ctypes.POINTER(ctypes.c_int64)
+        L.oracle_space_create.restype = ctypes.c_void_p
+        L.oracle_space_create.argtypes = [ctypes.c_int, dp, ctypes.c_int, dp, ctypes.c_int, dp, ctypes.c_int, ctypes.c_int]
+        L.oracle_space_destroy.argtypes = [ctypes.c_void_p]
+        L.oracle_space_info.argtypes = [ctypes.c_void_p, ip, lp]
+        L.oracle_local.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_double, ctypes.c_double, dp, dp, dp]
+        L.oracle_global_indices.argtypes = [ctypes.c_void_p, ctypes.c_int64, lp, lp]
+        L.oracle_assemble.restype = ctypes.c_int64
+        L.oracle_assemble.argtypes = [ctypes.c_void_p, ctypes.c_int, dp, ctypes.c_int, ctypes.c_int, lp, lp, dp, ctypes.c_int64]
+        L.oracle_boundary_attribute.restype = ctypes.c_int
+        L.oracle_boundary_attribute.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        L.oracle_dirichlet_terms.restype = ctypes.c_int64
+        L.oracle_dirichlet_terms.argtypes = [ctypes.c_void_p, dp, ip, lp, dp]
+        _lib = L
+    return _lib
+
+
+def _dptr(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+
+
+def _lptr(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_int64))
+
+
+class FESpaceOracle:
+    """Mesh + RT_k/P_m space (reference src/FEM.cpp:23-334)."""
+
+    def __init__(self, rt_order, p_order, x_breaks, y_breaks, z_breaks):
+        L = _load()
+        self.xb = np.ascontiguousarray(x_breaks, dtype=np.float64).ravel()
+        self.yb = np.ascontiguousarray(y_breaks, dtype=np.float64).ravel()
+        self.zb = np.ascontiguousarray(z_breaks, dtype=np.float64).ravel()
+        self.h = L.oracle_space_create(len(self.xb), _dptr(self.xb), len(self.yb), _dptr(self.yb),
+                                       len(self.zb), _dptr(self.zb), int(rt_order), int(p_order))
+        info = (ctypes.c_int * 10)()
+        info64 = (ctypes.c_int64 * 6)()
+        L.oracle_space_info(self.h, info, info64)
+        (self.dim, self.nx, self.ny, self.nz, self.nf, self.ni, self.nphi_loc, self.nJ_loc, self.nq, _) = list(info)
+        (self.nJx, self.nJy, self.nJz, self.n_J, self.n_Phi, self.ne) = [int(v) for v in info64]
+        self.k, self.m = int(rt_order), int(p_order)
+        self.hx = np.diff(self.xb)
+        self.hy = np.diff(self.yb) if self.dim >= 2 else np.ones(1)
+        self.hz = np.diff(self.zb) if self.dim == 3 else np.ones(1)
+
+    def __del__(self):
+        try:
+            _load().oracle_space_destroy(self.h)
+        except Exception:
+            pass
+
+    def volumes(self):
+        return (self.hz[:, None, None] * self.hy[None, :, None] * self.hx[None, None, :]).ravel()
+
+    def local(self, e, D, Sigma):
+        """LocalMatrices::Compute (src/FEM.cpp:748-953) -> (A_loc, B_loc, C_loc)."""
+        A = np.zeros((self.nJ_loc, self.nJ_loc))
+        B = np.zeros((self.nphi_loc, self.nJ_loc))
+        C = np.zeros((self.nphi_loc, self.nphi_loc))
+        _load().oracle_local(self.h, int(e), float(D), float(Sigma), _dptr(A), _dptr(B), _dptr(C))
+        return A, B, C
+
+    def global_indices(self, e):
+        j = np.zeros(self.nJ_loc, dtype=np.int64)
+        p = np.zeros(self.nphi_loc, dtype=np.int64)
+        _load().oracle_global_indices(self.h, int(e), _lptr(j), _lptr(p))
+        return j, p
+
+    def assemble(self, which, coef, shape, skip_small=False, fast=False):
+        L = _load()
+        coef = None if coef is None else np.ascontiguousarray(coef, dtype=np.float64)
+        cp = _dptr(coef) if coef is not None else None
+        n = L.oracle_assemble(self.h, which, cp, int(skip_small), int(fast), None, None, None, 0)
+        r = np.zeros(max(n, 1), dtype=np.int64)
+        c = np.zeros(max(n, 1), dtype=np.int64)
+        v = np.zeros(max(n, 1), dtype=np.float64)
+        L.oracle_assemble(self.h, which, cp, int(skip_small), int(fast), _lptr(r), _lptr(c), _dptr(v), n)
+        M = sp.coo_matrix((v[:n], (r[:n], c[:n])), shape=shape).tocsc()     # sums duplicates like setFromTriplets
+        M.sort_indices()
+        return M
+
+    def dirichlet_terms(self, D, flags):
+        L = _load()
+        D = np.ascontiguousarray(D, dtype=np.float64)
+        fl = (ctypes.c_int * 6)(*[int(f) for f in flags])
+        n = L.oracle_dirichlet_terms(self.h, _dptr(D), fl, None, None)
+        dof = np.zeros(max(n, 1), dtype=np.int64)
+        val = np.zeros(max(n, 1), dtype=np.float64)
+        L.oracle_dirichlet_terms(self.h, _dptr(D), fl, _lptr(dof), _dptr(val))
+        return dof[:n], val[:n]
+
+    def boundary_attribute(self, direction, is_upper):
+        return _load().oracle_boundary_attribute(self.dim, direction, int(is_upper))
+
+
+class ChebyshevAccel:
+    """reference src/solvers.cpp:664-756 (nmax, sigma)."""
+
+    def __init__(self, nmax=15, sigma=0.98):
+        self.nmax, self.sigma, self.it = nmax, sigma, 0
+        G = math.acosh(2.0 / sigma - 1.0)
+        self.a = [0.0] * nmax
+        self.b = [0.0] * nmax
+        self.a[1] = 2.0 / (2.0 - sigma)
+        for k in range(2, nmax):
+            self.a[k] = math.cosh((k - 1) * G) / math.cosh(k * G)
+            self.b[k] = math.cosh((k - 2) * G) / math.cosh(k * G)
+        self.p0 = None
+        self.p1 = None
+
+    def __call__(self, phi):
+        if self.it == self.nmax:
+            self.it, self.p0, self.p1 = 0, None, None
+        if self.it == 0:
+            self.p0 = phi.copy()
+            self.it += 1
+            return phi
+        if self.it == 1:
+            self.p1 = self.p0 + self.a[1] * (phi - self.p0)
+            self.it += 1
+            return self.p1.copy()
+        new = self.p1 + (4.0 / self.sigma) * self.a[self.it] * (phi - self.p1) + self.b[self.it] * (self.p1 - self.p0)
+        self.p0, self.p1 = self.p1, new
+        self.it += 1
+        return new.copy()
+
+
+@dataclass
+class SolveStats:
+    outer_iterations: int = 0
+    cg_iterations: list = field(default_factory=list)   # one entry per group solve
+    cg_dof_iterations: int = 0                          # sum(cg_its * n_phi)
+    t_schur: float = 0.0                                # seconds inside SchurSolver.Solve (incl. LU per F4)
+    t_cg: float = 0.0                                   # seconds inside the CG loop only
+    t_lu: float = 0.0                                   # seconds inside SparseLU::compute
+    t_total: float = 0.0
+    converged: bool = False
+
+
+class SchurSolverOracle:
+    """reference include/solvers.hpp:251-483, src/solvers.cpp:67-240, 259-314, 535-636."""
+
+    def __init__(self):
+        self.solver_type = DIRECT_LU          # solvers.cpp:67-76
+        self.tol = 1e-10
+        self.max_iter = 1000
+        self.last_iterations = 0
+        self.last_residual = 0.0
+        self.stats = None
+        self.A = self.B = self.C = self.BT = self.lu = None
+        self.S = None
+
+    def is_direct(self):
+        return self.solver_type in (DIRECT_LU, DIRECT_LDLT, DIRECT_LLT)
+
+    def needs_explicit(self):                # solvers.cpp:114-124
+        return self.is_direct() or self.C is None or self.C.shape[0] < 200
+
+    def set_matrices(self, A, B, C):         # solvers.cpp:149-179 -- re-factorises on every call
+        self.A, self.B, self.C = A, B, C
+        self.BT = B.T.tocsc()
+        t0 = time.perf_counter()
+        self.lu = spla.splu(A.tocsc())
+        if self.stats is not None:
+            self.stats.t_lu += time.perf_counter() - t0
+        self.S = None
+        if self.needs_explicit():
+            self.form_schur()
+
+    def form_schur(self):                    # solvers.cpp:259-314
+        BTd = self.BT.toarray()
+        X = self.lu.solve(BTd)
+        X[np.abs(X) <= 1e-14] = 0.0
+        self.S = (self.C + self.B @ sp.csc_matrix(X)).tocsc()
+
+    def schur_product(self, x):              # solvers.cpp:535-547
+        t1 = self.BT @ x
+        t2 = self.lu.solve(t1)
+        t3 = self.B @ t2
+        return self.C @ x + t3
+
+    def solve(self, rhs):                    # solvers.cpp:203-240
+        t0 = time.perf_counter()
+        if self.needs_explicit():
+            phi = spla.splu(self.S).solve(rhs)       # direct; Eigen Krylov classes only approximate this
+            self.last_iterations = 1
+        else:
+            phi = self.solve_implicit(rhs)
+        J = -self.lu.solve(self.BT @ phi)
+        if self.stats is not None:
+            self.stats.t_schur += time.perf_counter() - t0
+        return J, phi
+
+    def solve_implicit(self, rhs):           # solvers.cpp:577-636: unpreconditioned CG, x0 = 0
+        t0 = time.perf_counter()
+        n = rhs.size
+        phi = np.zeros(n)
+        r = rhs.copy()
+        p = r.copy()
+        rr = float(r @ r)
+        rhs_norm = float(np.linalg.norm(rhs))
+        tol_sq = self.tol * self.tol * rhs_norm * rhs_norm
+        self.last_iterations = 0
+        done = False
+        for k in range(self.max_iter):
+            Ap = self.schur_product(p)
+            pAp = float(p @ Ap)
+            if abs(pAp) < 1e-30:
+                break
+            alpha = rr / pAp
+            phi += alpha * p
+            r -= alpha * Ap
+            rr_new = float(r @ r)
+            self.last_iterations = k + 1
+            if rr_new < tol_sq:
+                self.last_residual = math.sqrt(rr_new) / rhs_norm
+                done = True
+                break
+            beta = rr_new / rr
+            p = r + beta * p
+            rr = rr_new
+        if not done:
+            self.last_residual = math.sqrt(rr) / rhs_norm if rhs_norm > 0 else 0.0
+        if self.stats is not None:
+            self.stats.t_cg += time.perf_counter() - t0
+            self.stats.cg_iterations.append(self.last_iterations)
+            self.stats.cg_dof_iterations += self.last_iterations * n
+        return phi
+
+
+class OracleNeutFEM:
+    """Mirror of the reference class `NeutFEM` for the k-eff path (names follow src/wrapper.cpp)."""
+
+    def __init__(self, rt_order, p_order, ng, x_breaks, y_breaks, z_breaks, fast_assembly=False):
+        rt = min(int(rt_order), 2)
+        pp = min(int(p_order), 2)
+        if rt < pp:                          # NeutFEM.cpp:149-169
+            pp = rt
+        self.rt_order, self.p_order, self.ng = rt, pp, int(ng)
+        self.fes = FESpaceOracle(rt, pp, x_breaks, y_breaks, z_breaks)
+        f = self.fes
+        ne = f.ne
+        self.fast_assembly = fast_assembly
+        # XS defaults NeutFEM.cpp:184-218
+        self.D = np.ones(ng * ne)
+        self.SRC = np.zeros(ng * ne)
+        self.SigR = np.full(ng * ne, 0.01)
+        self.NSF = np.zeros(ng * ne)
+        self.KSF = np.zeros(ng * ne)
+        self.Chi = np.zeros(ng * ne)
+        self.Chi[:ne] = 1.0
+        self.SigS = np.zeros(ng * ng * ne)
+        self.Sol_Phi = np.ones(ng * f.n_Phi)
+        self.Sol_J = np.zeros(ng * f.n_J)
+        self.Sol_Phi_adj = np.ones(ng * f.n_Phi)
+        self.Sol_J_adj = np.zeros(ng * f.n_J)
+        self.linear_solver_type = BICGSTAB   # NeutFEM.cpp:126
+        self.tol_keff = self.tol_flux = self.tol_L2 = 1e-5
+        self.max_outer, self.max_inner = 200, 1000
+        self.last_keff = 1.0
+        self.last_keff_adj = 1.0
+        self.has_valid_keff = False
+        self.bc_types = {}
+        self.bc_values = {}
+        self.schur = SchurSolverOracle()
+        self.diag_cache = None
+        self.stats = SolveStats()
+        self.A = [None] * ng
+        self.C = [None] * ng
+        self.M_fiss = [None] * ng
+        self.M_scatter = [None] * (ng * ng)
+        self.M_chi = [None] * ng
+        self.M_nsf = [None] * ng
+        self.B = self.BT = None
+
+    # ---- views in the reference's numpy shapes (NeutFEM.cpp:2626-2693)
+    def _shape(self):
+        f = self.fes
+        s = [self.ng]
+        if f.dim >= 3:
+            s.append(f.nz)
+        if f.dim >= 2:
+            s.append(f.ny)
+        s.append(f.nx)
+        return s
+
+    def get_D(self): return self.D.reshape(self._shape())
+    def get_SigR(self): return self.SigR.reshape(self._shape())
+    def get_NSF(self): return self.NSF.reshape(self._shape())
+    def get_KSF(self): return self.KSF.reshape(self._shape())
+    def get_Chi(self): return self.Chi.reshape(self._shape())
+    def get_SRC(self): return self.SRC.reshape(self._shape())
+    def get_SigS(self): return self.SigS.reshape([self.ng] + self._shape())
+
+    def get_flux(self):
+        f = self.fes
+        if f.nphi_loc == 1:
+            return self.Sol_Phi.reshape(self._shape())
+        return self.Sol_Phi.reshape(self.ng, f.ne, f.nphi_loc)[:, :, 0].reshape(self._shape()).copy()
+
+    def get_flux_adj(self):
+        f = self.fes
+        if f.nphi_loc == 1:
+            return self.Sol_Phi_adj.reshape(self._shape())
+        return self.Sol_Phi_adj.reshape(self.ng, f.ne, f.nphi_loc)[:, :, 0].reshape(self._shape()).copy()
+
+    # ---- configuration (NeutFEM.cpp:322-354)
+    def set_linear_solver(self, t):
+        self.linear_solver_type = int(t)
+        self.schur.solver_type = int(t)
+
+    def set_tol(self, tol_keff, tol_flux, tol_L2, max_outer, max_inner):
+        self.tol_keff, self.tol_flux, self.tol_L2 = tol_keff, tol_flux, tol_L2
+        self.max_outer, self.max_inner = int(max_outer), int(max_inner)
+        self.schur.tol = tol_flux
+        self.schur.max_iter = int(max_inner)
+
+    def set_bc(self, attr, bctype, value=0.0):
+        self.bc_types[int(attr)] = int(bctype)
+        self.bc_values[int(attr)] = float(value)
+
+    def reset_flux(self):
+        self.Sol_Phi[:] = 1.0
+        self.Sol_J[:] = 0.0
+        self.Sol_Phi_adj[:] = 1.0
+        self.Sol_J_adj[:] = 0.0
+        self.has_valid_keff = False
+
+    def _dirichlet_flags(self):
+        f = self.fes
+        flags = [0] * 6
+        for d in range(f.dim):
+            for up in (0, 1):
+                attr = f.boundary_attribute(d, up)
+                flags[2 * d + up] = int(self.bc_types.get(attr, -1) == DIRICHLET)
+        return flags
+
+    # ---- assembly (NeutFEM.cpp:402-457)
+    def _mass(self, coef):
+        """P0: coef*V on the diagonal with |coef|>1e-14 (NeutFEM.cpp:1209-1216); P>=1: C-type local matrices."""
+        f = self.fes
+        if self.p_order == 0:
+            c = np.where(np.abs(coef) > 1e-14, coef * f.volumes(), 0.0)
+            M = sp.diags(c).tocsc()
+            M.eliminate_zeros()
+            return M
+        return f.assemble(2, coef, (f.n_Phi, f.n_Phi), skip_small=True, fast=self.fast_assembly)
+
+    def BuildMatrices(self):
+        f, ng, ne = self.fes, self.ng, self.fes.ne
+        fast = self.fast_assembly
+        self.B = f.assemble(1, None, (f.n_Phi, f.n_J), fast=fast)
+        self.BT = self.B.T.tocsc()
+        flags = self._dirichlet_flags()
+        for g in range(ng):
+            Dg = self.D[g * ne:(g + 1) * ne]
+            A = f.assemble(0, Dg, (f.n_J, f.n_J), fast=fast)
+            dof, val = f.dirichlet_terms(Dg, flags)                      # ApplyDirichletToA
+            if dof.size:
+                A = (A + sp.coo_matrix((val, (dof, dof)), shape=A.shape).tocsc()).tocsc()
+            self.A[g] = A
+            self.C[g] = f.assemble(2, self.SigR[g * ne:(g + 1) * ne], (f.n_Phi, f.n_Phi), skip_small=False, fast=fast)
+            self.M_fiss[g] = self._mass(self.NSF[g * ne:(g + 1) * ne])
+            for gp in range(ng):                                          # AssembleScatteringMatrix(gp -> g)
+                off = (g * ng + gp) * ne
+                self.M_scatter[g * ng + gp] = self._mass(self.SigS[off:off + ne])
+            # AssembleWeightedMassMatrix always goes through the local matrices (NeutFEM.cpp:1495-1529)
+            self.M_chi[g] = f.assemble(2, self.Chi[g * ne:(g + 1) * ne], (f.n_Phi, f.n_Phi), skip_small=True, fast=fast)
+            self.M_nsf[g] = f.assemble(2, self.NSF[g * ne:(g + 1) * ne], (f.n_Phi, f.n_Phi), skip_small=True, fast=fast)
+        self.diag_cache = None
+
+    # ---- diagonal RT0-P0 path (NeutFEM.cpp:483-634)
+    def build_diagonal_cache(self):
+        if self.rt_order != 0 or self.p_order != 0 or self.diag_cache is not None:
+            return
+        f, ng = self.fes, self.ng
+        e = np.arange(f.ne)
+        ix = e % f.nx
+        iy = (e // f.nx) % f.ny
+        iz = e // (f.nx * f.ny)
+        faces = []
+        if True:
+            if f.dim == 1:
+                fl = ix
+            elif f.dim == 2:
+                fl = iy * (f.nx + 1) + ix
+            else:
+                fl = iz * f.ny * (f.nx + 1) + iy * (f.nx + 1) + ix
+            faces += [fl, fl + 1]
+        if f.dim >= 2:
+            if f.dim == 2:
+                fb = iy * f.nx + ix
+            else:
+                fb = iz * (f.ny + 1) * f.nx + iy * f.nx + ix
+            faces += [f.nJx + fb, f.nJx + fb + f.nx]
+        if f.dim == 3:
+            fk = iz * f.ny * f.nx + iy * f.nx + ix
+            faces += [f.nJx + f.nJy + fk, f.nJx + f.nJy + fk + f.nx * f.ny]
+        Bcsr = self.B.tocsr()
+        self.diag_cache = []
+        for g in range(ng):
+            S = self.C[g].diagonal().copy()
+            Ad = self.A[g].diagonal()
+            for fidx in faces:
+                Bv = np.asarray(Bcsr[e, fidx]).ravel()
+                Af = Ad[fidx]
+                ok = np.abs(Af) > 1e-14
+                S += np.where(ok, Bv * Bv / np.where(ok, Af, 1.0), 0.0)
+            self.diag_cache.append(np.where(np.abs(S) > 1e-14, 1.0 / np.where(np.abs(S) > 1e-14, S, 1.0), 0.0))
+
+    def solve_diagonal(self, g, rhs):
+        """phi = rhs/S_ee. J: the reference loop (NeutFEM.cpp:622-633) indexes out of bounds;
+        the formula written in its comment (J_f = sum_e B_ef phi_e / A_ff) is used here. J UNPINNED."""
+        phi = self.diag_cache[g] * rhs
+        Ad = self.A[g].diagonal()
+        t = self.BT @ phi
+        J = np.where(np.abs(Ad) >= 1e-14, t / np.where(np.abs(Ad) >= 1e-14, Ad, 1.0), 0.0)
+        return J, phi
+
+    # ---- sources (NeutFEM.cpp:1539-1589)
+    def _fission_rhs(self, g, total_fiss, keff, adjoint=False):
+        f, ne = self.fes, self.fes.ne
+        inv_k = 1.0 / keff
+        coef = (self.NSF if adjoint else self.Chi)[g * ne:(g + 1) * ne]
+        if f.nphi_loc == 1:
+            return inv_k * (coef * total_fiss)
+        c = coef * inv_k
+        c = np.where(np.abs(c) < 1e-14, 0.0, c)
+        return (np.repeat(c, f.nphi_loc)) * total_fiss
+
+    def _solve_group(self, g, rhs, adjoint=False):      # NeutFEM.cpp:2084-2126
+        self.schur.stats = self.stats
+        self.schur.set_matrices(self.A[g], self.B, self.C[g])
+        J, phi = self.schur.solve(rhs)
+        f = self.fes
+        if adjoint:
+            self.Sol_J_adj[g * f.n_J:(g + 1) * f.n_J] = J
+            self.Sol_Phi_adj[g * f.n_Phi:(g + 1) * f.n_Phi] = phi
+        else:
+            self.Sol_J[g * f.n_J:(g + 1) * f.n_J] = J
+            self.Sol_Phi[g * f.n_Phi:(g + 1) * f.n_Phi] = phi
+
+    # ---- SolveKeff (NeutFEM.cpp:1627-1815)
+    def SolveKeff(self, use_coarse_init=False, coarse_factors=(), use_diagonal_solver=False, use_cmfd=False,
+                  max_outer_override=None):
+        assert not use_cmfd, "CMFD is out of scope (SURVEY section 2)"
+        f, ng, nP, nJ = self.fes, self.ng, self.fes.n_Phi, self.fes.n_J
+        st = self.stats = SolveStats()
+        t_start = time.perf_counter()
+        if use_diagonal_solver and not (self.rt_order == 0 and self.p_order == 0):
+            use_diagonal_solver = False
+        if use_diagonal_solver:
+            self.build_diagonal_cache()
+        keff = self.last_keff if self.has_valid_keff else 1.0
+        if use_coarse_init and len(coarse_factors) > 0:
+            keff_c, flux_c = self.SolveCoarse(list(coarse_factors))
+            self.Sol_Phi = flux_c
+            keff = keff_c
+        accel = ChebyshevAccel(15, 0.98)
+        n_outer = self.max_outer if max_outer_override is None else int(max_outer_override)
+        for it in range(n_outer):
+            old = self.Sol_Phi.copy()
+            total_fiss = np.zeros(nP)
+            for g in range(ng):
+                total_fiss += self.M_fiss[g] @ self.Sol_Phi[g * nP:(g + 1) * nP]
+            prod_old = float(total_fiss.sum())
+            for g in range(ng):
+                rhs = self._fission_rhs(g, total_fiss, keff)
+                for gp in range(ng):
+                    if gp == g:
+                        continue
+                    M = self.M_scatter[g * ng + gp]
+                    if M.nnz == 0:
+                        continue
+                    rhs = rhs + M @ self.Sol_Phi[gp * nP:(gp + 1) * nP]
+                if use_diagonal_solver:
+                    J, phi = self.solve_diagonal(g, rhs)
+                    self.Sol_Phi[g * nP:(g + 1) * nP] = phi
+                    self.Sol_J[g * nJ:(g + 1) * nJ] = J
+                else:
+                    self._solve_group(g, rhs)
+            prod_new = 0.0
+            for g in range(ng):
+                prod_new += float((self.M_fiss[g] @ self.Sol_Phi[g * nP:(g + 1) * nP]).sum())
+            keff_new = keff * (prod_new / prod_old)
+            diff_k = abs(keff_new - keff)
+            if it >= 1:
+                keff = keff_new
+            sol_sq = float(self.Sol_Phi @ self.Sol_Phi)
+            d = self.Sol_Phi - old
+            diff_flux = math.sqrt(float(d @ d) / sol_sq)
+            norm = math.sqrt(sol_sq)
+            if norm > 1e-14:
+                self.Sol_Phi /= norm
+            if it >= 2:
+                self.Sol_Phi = accel(self.Sol_Phi)
+            st.outer_iterations = it + 1
+            if diff_k < self.tol_keff and diff_flux < self.tol_flux:
+                st.converged = True
+                break
+        self.has_valid_keff = True
+        self.last_keff = keff
+        st.t_total = time.perf_counter() - t_start
+        return keff
+
+    # ---- SolveAdjoint (NeutFEM.cpp:1877-2082)
+    def SolveAdjoint(self, normalize_to_direct=True, use_direct_keff=True):
+        f, ng, nP, ne = self.fes, self.ng, self.fes.n_Phi, self.fes.ne
+        nl = f.nphi_loc
+        self.stats = SolveStats()
+        k = 1.0
+        if use_direct_keff and self.has_valid_keff:
+            k = self.last_keff
+        self.Sol_Phi_adj[:] = 1.0
+        self.Sol_Phi_adj /= np.linalg.norm(self.Sol_Phi_adj)
+        accel = ChebyshevAccel(15, 0.98)
+        nsf_tot = self.NSF.reshape(ng, ne).sum(axis=0)
+        for it in range(self.max_outer):
+            old = self.Sol_Phi_adj.copy()
+            tot = np.zeros(nP)
+            for g in range(ng):
+                tot += self.M_chi[g] @ self.Sol_Phi_adj[g * nP:(g + 1) * nP]
+            prod_old = float(nsf_tot @ tot[::nl])
+            for g in range(ng):
+                rhs = self._fission_rhs(g, tot, k, adjoint=True)
+                for gp in range(ng):
+                    if gp == g:
+                        continue
+                    M = self.M_scatter[gp * ng + g]
+                    if M.nnz == 0:
+                        continue
+                    rhs = rhs + M @ self.Sol_Phi_adj[gp * nP:(gp + 1) * nP]
+                self._solve_group(g, rhs, adjoint=True)
+            tot_new = np.zeros(nP)
+            for g in range(ng):
+                tot_new += self.M_chi[g] @ self.Sol_Phi_adj[g * nP:(g + 1) * nP]
+            prod_new = float(nsf_tot @ tot_new[::nl])
+            if (not use_direct_keff) or (not self.has_valid_keff):
+                k_new = k
+                if abs(prod_old) > 1e-14 and it > 0:
+                    k_new = k * (prod_new / prod_old)
+                diff_k = abs(k_new - k)
+                k = k_new
+            else:
+                diff_k = 0.0
+            nrm = float(np.linalg.norm(self.Sol_Phi_adj))
+            diff_flux = float(np.linalg.norm(self.Sol_Phi_adj - old)) / nrm
+            if nrm > 1e-14:
+                self.Sol_Phi_adj /= nrm
+            if (not use_direct_keff) and it >= 5:
+                self.Sol_Phi_adj = accel(self.Sol_Phi_adj)
+            self.stats.outer_iterations = it + 1
+            conv = diff_flux < self.tol_flux
+            if not use_direct_keff:
+                conv = conv and diff_k < self.tol_keff
+            if conv:
+                break
+        if normalize_to_direct and self.has_valid_keff:
+            m1 = self.p_order + 1
+            d = np.arange(nl)
+            if f.dim == 1:
+                idx = (d, 0 * d, 0 * d)
+            elif f.dim == 2:
+                idx = (d % m1, d // m1, 0 * d)
+            else:
+                idx = (d % m1, (d // m1) % m1, d // (m1 * m1))
+            w = (2.0 / (2.0 * idx[0] + 1.0)) / 2.0
+            if f.dim >= 2:
+                w = w * (2.0 / (2.0 * idx[1] + 1.0)) / 2.0
+            if f.dim >= 3:
+                w = w * (2.0 / (2.0 * idx[2] + 1.0)) / 2.0
+            wv = (f.volumes()[:, None] * w[None, :]).ravel()
+            ip = 0.0
+            for g in range(ng):
+                ip += float(np.sum(self.Sol_Phi[g * nP:(g + 1) * nP] * self.Sol_Phi_adj[g * nP:(g + 1) * nP] * wv))
+            if abs(ip) > 1e-14:
+                self.Sol_Phi_adj /= ip
+        self.last_keff_adj = k
+        return k
+
+    # ---- SolveCoarse (NeutFEM.cpp:2380-2611)
+    def SolveCoarse(self, refine):
+        f, ng, ne = self.fes, self.ng, self.fes.ne
+        if len(refine) == 0:
+            return 1.0, self.Sol_Phi.copy()
+        rx = max(int(refine[0]), 1)
+        ry = max(int(refine[1]), 1) if (len(refine) > 1 and f.dim >= 2) else 1
+        rz = max(int(refine[2]), 1) if (len(refine) > 2 and f.dim >= 3) else 1
+        if f.nx % rx or f.ny % ry or f.nz % rz:
+            return 1.0, self.Sol_Phi.copy()
+        nxc, nyc, nzc = f.nx // rx, f.ny // ry, f.nz // rz
+        xbc = f.xb[::rx]
+        ybc = f.yb[::ry] if f.dim >= 2 else np.array([0.0])
+        zbc = f.zb[::rz] if f.dim >= 3 else np.array([0.0])
+        c = OracleNeutFEM(0, 0, ng, xbc, ybc, zbc, fast_assembly=self.fast_assembly)
+        c.set_linear_solver(self.linear_solver_type)
+        c.set_tol(self.tol_keff * 10.0, self.tol_flux * 10.0, self.tol_L2, self.max_outer // 2, self.max_inner)
+        for a, t in self.bc_types.items():
+            c.set_bc(a, t, self.bc_values.get(a, 0.0))
+        # volumes from break differences (NeutFEM.cpp:2486-2491)
+        vx = np.diff(f.xb)
+        vy = np.diff(f.yb) if f.dim >= 2 else np.ones(1)
+        vz = np.diff(f.zb) if f.dim >= 3 else np.ones(1)
+        vol = (vz[:, None, None] * vy[None, :, None] * vx[None, None, :])
+
+        def coarsen(a):
+            a = a.reshape(f.nz, f.ny, f.nx)
+            num = (a * vol).reshape(nzc, rz, nyc, ry, nxc, rx).sum(axis=(1, 3, 5))
+            den = vol.reshape(nzc, rz, nyc, ry, nxc, rx).sum(axis=(1, 3, 5))
+            return (num / den).ravel()
+
+        nec = nxc * nyc * nzc
+        for g in range(ng):
+            c.D[g * nec:(g + 1) * nec] = coarsen(self.D[g * ne:(g + 1) * ne])
+            c.SigR[g * nec:(g + 1) * nec] = coarsen(self.SigR[g * ne:(g + 1) * ne])
+            c.NSF[g * nec:(g + 1) * nec] = coarsen(self.NSF[g * ne:(g + 1) * ne])
+            c.KSF[g * nec:(g + 1) * nec] = coarsen(self.KSF[g * ne:(g + 1) * ne])
+            c.Chi[g * nec:(g + 1) * nec] = coarsen(self.Chi[g * ne:(g + 1) * ne])
+            for gp in range(ng):
+                off = (g * ng + gp) * ne
+                offc = (g * ng + gp) * nec
+                c.SigS[offc:offc + nec] = coarsen(self.SigS[off:off + ne])
+        c.BuildMatrices()
+        kc = c.SolveKeff(False, (), False, False)
+        self.coarse_stats = c.stats
+        nl = f.nphi_loc
+        proj = np.zeros(ng * f.n_Phi)
+        ez, ey, ex = np.meshgrid(np.arange(f.nz), np.arange(f.ny), np.arange(f.nx), indexing="ij")
+        ec = ((ez // rz) * (nyc * nxc) + (ey // ry) * nxc + (ex // rx)).ravel()
+        for g in range(ng):
+            proj[g * f.n_Phi:(g + 1) * f.n_Phi:nl] = c.Sol_Phi[g * nec:(g + 1) * nec][ec]
+        return kc, proj
+
+    # ---- test hooks
+    def schur_product(self, g, x):
+        s = SchurSolverOracle()
+        s.solver_type = CG
+        s.A, s.B, s.C = self.A[g], self.B, self.C[g]
+        s.BT = self.BT
+        s.lu = spla.splu(self.A[g].tocsc())
+        return s.schur_product(np.asarray(x, dtype=np.float64))
+
+    def current_from_flux(self, g, phi):
+        lu = spla.splu(self.A[g].tocsc())
+        return -lu.solve(self.BT @ np.asarray(phi, dtype=np.float64))
