@@ -1,0 +1,950 @@
+// nf_api.cu -- context, launch logic and the C ABI of libneutfem_b200.so (see include/neutfem_b200.h).
+// Host-side control flow restates reference NeutFEM::SolveKeff / SolveAdjoint (src/NeutFEM.cpp:1627-2082) and
+// SchurSolver::SolveSchurImplicit (src/solvers.cpp:577-636); all arithmetic runs in the kernels of
+// nf_sweeps.cuh / nf_vector.cuh. No CPU fallback exists: every entry point needs a CUDA device.
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/neutfem_b200.h"
+#include "nf_common.cuh"
+#include "nf_sweeps.cuh"
+#include "nf_vector.cuh"
+#include "nf_current.cuh"
+
+using namespace nf;
+
+static std::atomic<long long> g_launches{0};
+static thread_local std::string g_create_error;
+
+struct nf_ctx {
+    int dev = 0;
+    cudaStream_t stream = nullptr;
+    int dim = 1, nx = 1, ny = 1, nz = 1, K = 0, M = 0, M1 = 1, nt = 1, nloc = 1, nf = 1, ni = 0, ng = 1;
+    long long ne = 0, nphi = 0, nJ = 0, nJx = 0, nJy = 0, nJz = 0, nJface = 0;
+    std::vector<double> hx, hy, hz;
+    double *d_hx = nullptr, *d_hy = nullptr, *d_hz = nullptr, *d_vol = nullptr;
+    double *d_F[3][3] = {{nullptr}};       // [dir][axis]
+    double *d_D = nullptr, *d_SigR = nullptr, *d_NSF = nullptr, *d_Chi = nullptr, *d_SigS = nullptr, *d_SRC = nullptr;
+    std::vector<double *> d_minv, d_u;     // [g*3 + d]
+    long long nfaces[3] = {0, 0, 0};
+    double *d_sinv = nullptr; bool diag_valid = false;
+    double *d_jac = nullptr; bool jac_valid = false;
+    double *d_phi = nullptr, *d_phi_adj = nullptr, *d_old = nullptr, *d_h0 = nullptr, *d_h1 = nullptr;
+    double *d_tot = nullptr, *d_rhs = nullptr, *d_r = nullptr, *d_p = nullptr, *d_Ap = nullptr, *d_tmp = nullptr;
+    double *d_zscratch = nullptr; size_t zscratch_bytes = 0;
+    double *d_J = nullptr;                 // staging for nf_get_current, allocated on demand
+    CgState *d_cg = nullptr;
+    double *d_part = nullptr; unsigned *d_ticket = nullptr; double *d_scal = nullptr;
+    double *h_scal = nullptr; CgState *h_cg = nullptr;     // pinned
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    std::map<int, int> bc_types; std::map<int, double> bc_values;
+    int solver_type = NF_BICGSTAB; int mode = NF_MODE_PARITY;
+    double tol_keff = 1e-5, tol_flux = 1e-5; int max_outer = 200, max_inner = 1000;
+    double inner_tol = 1e-10; int inner_max = 1000; bool tol_set = false;   // SchurSolver keeps its own defaults
+    double last_keff = 1.0, last_keff_adj = 1.0; bool has_valid = false;
+    bool built = false;
+    int sm_count = 148; size_t smem_optin = 0;
+    // mode tables
+    int tmode[3][kMaxT][3]; double tw[3][kMaxT];
+    double wC[kMaxModes], cb[3][kMaxModes], wM[kMaxModes], wface[3][kMaxModes];
+    std::string err;
+    long long launches_call = 0;
+};
+
+#define NF_FAIL(ctx, code, ...)                                  \
+    do {                                                         \
+        char _b[512];                                            \
+        snprintf(_b, sizeof(_b), __VA_ARGS__);                   \
+        (ctx)->err = _b;                                         \
+        return (code);                                           \
+    } while (0)
+
+#define CU(ctx, call)                                                                                     \
+    do {                                                                                                  \
+        cudaError_t _e = (call);                                                                          \
+        if (_e != cudaSuccess) NF_FAIL(ctx, NF_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), \
+                                       __FILE__, __LINE__);                                               \
+    } while (0)
+
+#define LAUNCH(ctx, kern, grid, block, smem, ...)                      \
+    do {                                                               \
+        kern<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__); \
+        ++g_launches; ++(ctx)->launches_call;                          \
+    } while (0)
+
+static inline int ew_blocks(long long n) { return (int)std::max<long long>(1, std::min<long long>(kRedBlocks, (n + 255) / 256)); }
+
+template <typename T>
+static int dalloc(nf_ctx *c, T **p, size_t n)
+{
+    CU(c, cudaMalloc((void **)p, std::max<size_t>(n, 1) * sizeof(T)));
+    return NF_OK;
+}
+
+static int upload(nf_ctx *c, double *dst, const double *src, size_t n)
+{
+    CU(c, cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    return NF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+static void build_mode_tables(nf_ctx *c)
+{
+    const int M1 = c->M1, dim = c->dim;
+    const double two_dim = (dim == 1) ? 2.0 : (dim == 2 ? 4.0 : 8.0);
+    for (int mode = 0; mode < c->nloc; ++mode) {
+        int a[3] = {mode % M1, (dim >= 2) ? (mode / M1) % M1 : 0, (dim == 3) ? mode / (M1 * M1) : 0};
+        double wfull = 1.0;
+        for (int t = 0; t < dim; ++t) wfull *= 2.0 / (2.0 * a[t] + 1.0);
+        c->wC[mode] = wfull / two_dim;                // times cell volume = det_J * prod 2/(2a+1)   (FEM.cpp:941-949)
+        c->wM[mode] = (c->M == 0) ? 1.0 : wfull / two_dim;
+        for (int d = 0; d < 3; ++d) {
+            c->cb[d][mode] = 0.0; c->wface[d][mode] = 0.0;
+            if (d >= dim) continue;
+            double wt = 1.0;
+            for (int t = 0; t < dim; ++t) if (t != d) wt *= 2.0 / (2.0 * a[t] + 1.0);
+            if (a[d] == 0) c->wface[d][mode] = wt;
+            if (a[d] == 1) { c->cb[d][mode] = (5.0 / 3.0) * wt; c->wface[d][mode] = wt * 25.0 / 36.0; }
+            if (a[d] == 2) { c->cb[d][mode] = (21.0 / 5.0) * wt; c->wface[d][mode] = wt * 49.0 / 100.0; }
+        }
+    }
+    c->nt = (dim == 1) ? 1 : (dim == 2 ? M1 : M1 * M1);
+    for (int d = 0; d < dim; ++d)
+        for (int t = 0; t < c->nt; ++t) {
+            const int i = (dim == 1) ? 0 : t % M1, j = (dim == 3) ? t / M1 : 0;
+            for (int p = 0; p < M1; ++p) {
+                int a[3];
+                if (d == 0) { a[0] = p; a[1] = i; a[2] = j; }
+                else if (d == 1) { a[0] = i; a[1] = p; a[2] = j; }
+                else { a[0] = i; a[1] = j; a[2] = p; }
+                c->tmode[d][t][p] = a[0] + M1 * a[1] + M1 * M1 * a[2];
+            }
+            double w = 1.0;
+            if (dim >= 2) w *= 2.0 / (2.0 * i + 1.0);
+            if (dim == 3) w *= 2.0 / (2.0 * j + 1.0);
+            c->tw[d][t] = w;
+        }
+}
+
+static void fill_sweep_args(nf_ctx *c, SweepArgs &a, int g, int d, const double *x, double *y, bool use_cg)
+{
+    memset(&a, 0, sizeof(a));
+    a.x = x; a.y = y;
+    a.minv = c->d_minv[g * 3 + d]; a.u = c->d_u[g * 3 + d];
+    a.D = c->d_D + (size_t)g * c->ne; a.SigR = c->d_SigR + (size_t)g * c->ne; a.vol = c->d_vol;
+    for (int dd = 0; dd < 3; ++dd) { a.Fx[dd] = c->d_F[dd][0]; a.Fy[dd] = c->d_F[dd][1]; a.Fz[dd] = c->d_F[dd][2]; }
+    a.zscratch = c->d_zscratch;
+    a.red_part = c->d_part + (size_t)d * kRedBlocks;
+    a.ticket = c->d_ticket + d;
+    a.red_out = use_cg ? &c->d_cg->pAp[d] : nullptr;
+    a.done = use_cg ? &c->d_cg->done : nullptr;
+    a.ne = c->ne; a.nx = c->nx; a.ny = c->ny; a.nz = c->nz; a.dim = c->dim; a.nt = c->nt;
+    a.first = (d == 0);
+    for (int t = 0; t < c->nt; ++t) {
+        for (int p = 0; p < c->M1; ++p) a.mode[t][p] = c->tmode[d][t][p];
+        a.w[t] = c->tw[d][t];
+    }
+    memcpy(a.wC, c->wC, sizeof(a.wC));
+    memcpy(a.cb, c->cb, sizeof(a.cb));
+}
+
+template <int K, int M1>
+static int launch_sweeps_t(nf_ctx *c, int g, const double *x, double *y, bool use_cg)
+{
+    SweepArgs a;
+    {   // x pass
+        fill_sweep_args(c, a, g, 0, x, y, use_cg);
+        int Lc = (c->nx + 1 + 31) / 32;
+        Lc |= 1;
+        a.Lc = Lc;
+        const int RL = 32 * Lc;
+        const size_t per_warp = (size_t)(3 + M1) * RL * sizeof(double);
+        int WPB = 4;
+        while (WPB > 1 && per_warp * WPB > c->smem_optin) WPB >>= 1;
+        if (per_warp * WPB > c->smem_optin) NF_FAIL(c, NF_ERR_ARG, "nx=%d too large for the shared-memory line solver", c->nx);
+        const size_t smem = per_warp * WPB;
+        static size_t configured = 0;
+        if (smem > configured) {
+            CU(c, cudaFuncSetAttribute(k_sweep_x<K, M1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
+            configured = c->smem_optin;
+        }
+        const long long nlines = (long long)c->ny * c->nz;
+        const int grid = (int)std::max<long long>(1, std::min<long long>(kRedBlocks, (nlines + WPB - 1) / WPB));
+        LAUNCH(c, (k_sweep_x<K, M1>), grid, WPB * 32, smem, a);
+    }
+    for (int d = 1; d < c->dim; ++d) {
+        fill_sweep_args(c, a, g, d, x, y, use_cg);
+        MarchGeom mg;
+        if (d == 1) {
+            mg.n = c->ny; mg.north = c->nz; mg.stride = c->nx;
+            mg.ostride_cell = (long long)c->ny * c->nx; mg.ostride_face = (long long)(c->ny + 1) * c->nx;
+        } else {
+            mg.n = c->nz; mg.north = c->ny; mg.stride = (long long)c->nx * c->ny;
+            mg.ostride_cell = c->nx; mg.ostride_face = c->nx;
+        }
+        const int WPB = 4;
+        const int nxb = (c->nx + 31) / 32;
+        const long long nitems = (long long)mg.north * c->nt * nxb;
+        const int grid = (int)std::max<long long>(1, std::min<long long>(kRedBlocks, (nitems + WPB - 1) / WPB));
+        const size_t zs = (size_t)(mg.n + 1) * 32 * sizeof(double) * WPB;
+        if (zs <= 96 * 1024) {
+            static bool conf = false;
+            if (!conf) {
+                CU(c, cudaFuncSetAttribute(k_sweep_march<K, M1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+                conf = true;
+            }
+            LAUNCH(c, (k_sweep_march<K, M1, true>), grid, WPB * 32, zs, a, mg);
+        } else {
+            const size_t need = zs * (size_t)grid;
+            if (need > c->zscratch_bytes) {
+                CU(c, cudaStreamSynchronize(c->stream));
+                if (c->d_zscratch) cudaFree(c->d_zscratch);
+                c->d_zscratch = nullptr; c->zscratch_bytes = 0;
+                CU(c, cudaMalloc((void **)&c->d_zscratch, need));
+                c->zscratch_bytes = need;
+                a.zscratch = c->d_zscratch;
+            }
+            LAUNCH(c, (k_sweep_march<K, M1, false>), grid, WPB * 32, 0, a, mg);
+        }
+    }
+    CU(c, cudaGetLastError());
+    return NF_OK;
+}
+
+// y = S_g x (SoA). use_cg: accumulate p.Ap into the CG state and honour its done flag.
+static int apply_schur(nf_ctx *c, int g, const double *x, double *y, bool use_cg)
+{
+    switch (c->K * 4 + c->M1) {
+    case 0 * 4 + 1: return launch_sweeps_t<0, 1>(c, g, x, y, use_cg);
+    case 1 * 4 + 1: return launch_sweeps_t<1, 1>(c, g, x, y, use_cg);
+    case 1 * 4 + 2: return launch_sweeps_t<1, 2>(c, g, x, y, use_cg);
+    case 2 * 4 + 1: return launch_sweeps_t<2, 1>(c, g, x, y, use_cg);
+    case 2 * 4 + 2: return launch_sweeps_t<2, 2>(c, g, x, y, use_cg);
+    case 2 * 4 + 3: return launch_sweeps_t<2, 3>(c, g, x, y, use_cg);
+    }
+    NF_FAIL(c, NF_ERR_STATE, "unsupported order RT%d-P%d", c->K, c->M);
+}
+
+static int dirichlet_flags(const nf_ctx *c, int *fl)
+{
+    // side -> attribute map of the reference (NeutFEM::GetBoundaryAttribute, src/NeutFEM.cpp:2338-2347)
+    for (int i = 0; i < 6; ++i) fl[i] = 0;
+    for (int d = 0; d < c->dim; ++d)
+        for (int up = 0; up < 2; ++up) {
+            int attr;
+            if (c->dim == 1) attr = up ? 2 : 1;
+            else if (c->dim == 2) attr = (d == 0) ? (up ? 2 : 1) : (up ? 3 : 4);
+            else attr = (d == 0) ? (up ? 4 : 3) : (d == 1 ? (up ? 5 : 6) : (up ? 2 : 1));
+            auto it = c->bc_types.find(attr);
+            fl[2 * d + up] = (it != c->bc_types.end() && it->second == NF_BC_DIRICHLET) ? 1 : 0;
+        }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+int nf_version(int32_t out[3])
+{
+    int rt = 0;
+    cudaRuntimeGetVersion(&rt);
+    out[0] = 1; out[1] = rt; out[2] = 100;
+    return NF_OK;
+}
+
+int64_t nf_kernel_launch_count(void) { return (int64_t)g_launches.load(); }
+
+const char *nf_last_error(const nf_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int nf_create(nf_ctx **out, int rt_order, int p_order, int ng, const double *xb, int nxb, const double *yb, int nyb,
+              const double *zb, int nzb, int device)
+{
+    if (!out) return NF_ERR_ARG;
+    *out = nullptr;
+    if (!xb || nxb < 2 || ng < 1 || rt_order < 0 || p_order < 0) { g_create_error = "nf_create: bad arguments"; return NF_ERR_ARG; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        g_create_error = "nf_create: no CUDA device available (this library has no CPU fallback)";
+        cudaGetLastError();
+        return NF_ERR_NODEVICE;
+    }
+    nf_ctx *c = new nf_ctx();
+    auto fail = [&](int code) { g_create_error = c->err; delete c; return code; };
+    if (device >= 0) { if (cudaSetDevice(device) != cudaSuccess) { c->err = "cudaSetDevice failed"; return fail(NF_ERR_CUDA); } }
+    cudaGetDevice(&c->dev);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, c->dev) != cudaSuccess) { c->err = "cudaGetDeviceProperties failed"; return fail(NF_ERR_CUDA); }
+    c->sm_count = prop.multiProcessorCount;
+    c->smem_optin = prop.sharedMemPerBlockOptin;
+    // mesh (reference CartesianMesh ctor, src/FEM.cpp:23-58)
+    c->nx = nxb - 1;
+    c->ny = (yb && nyb > 1) ? nyb - 1 : 1;
+    c->nz = (zb && nzb > 1) ? nzb - 1 : 1;
+    c->dim = (c->nz > 1) ? 3 : (c->ny > 1 ? 2 : 1);
+    c->hx.resize(c->nx); c->hy.assign(c->ny, 1.0); c->hz.assign(c->nz, 1.0);
+    for (int i = 0; i < c->nx; ++i) c->hx[i] = xb[i + 1] - xb[i];
+    if (c->dim >= 2) for (int i = 0; i < c->ny; ++i) c->hy[i] = yb[i + 1] - yb[i];
+    if (c->dim == 3) for (int i = 0; i < c->nz; ++i) c->hz[i] = zb[i + 1] - zb[i];
+    // orders (src/NeutFEM.cpp:119-169)
+    c->K = std::min(rt_order, 2); c->M = std::min(p_order, 2);
+    if (c->K < c->M) c->M = c->K;
+    c->M1 = c->M + 1; c->ng = ng;
+    const int k1 = c->K + 1;
+    c->nloc = (c->dim == 1) ? c->M1 : (c->dim == 2 ? c->M1 * c->M1 : c->M1 * c->M1 * c->M1);
+    c->nf = (c->dim == 1) ? 1 : (c->dim == 2 ? k1 : k1 * k1);
+    c->ni = (c->dim == 1) ? c->K : (c->dim == 2 ? c->K * k1 : c->K * k1 * k1);
+    c->ne = (long long)c->nx * c->ny * c->nz;
+    c->nphi = c->ne * c->nloc;
+    c->nfaces[0] = (long long)(c->nx + 1) * c->ny * c->nz;
+    c->nfaces[1] = (c->dim >= 2) ? (long long)c->nx * (c->ny + 1) * c->nz : 0;
+    c->nfaces[2] = (c->dim == 3) ? (long long)c->nx * c->ny * (c->nz + 1) : 0;
+    c->nJx = c->nfaces[0] * c->nf; c->nJy = c->nfaces[1] * c->nf; c->nJz = c->nfaces[2] * c->nf;
+    c->nJface = c->nJx + c->nJy + c->nJz;
+    c->nJ = c->nJface + c->ne * c->dim * c->ni;
+    build_mode_tables(c);
+
+#define CK(x) do { int _r = (x); if (_r != NF_OK) return fail(_r); } while (0)
+#define CKU(x) do { if ((x) != cudaSuccess) { c->err = std::string(#x) + ": " + cudaGetErrorString(cudaGetLastError()); return fail(NF_ERR_CUDA); } } while (0)
+    CKU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CKU(cudaEventCreate(&c->ev0)); CKU(cudaEventCreate(&c->ev1)); CKU(cudaEventCreate(&c->ev2)); CKU(cudaEventCreate(&c->ev3));
+    const size_t ne = (size_t)c->ne, np = (size_t)c->nphi, G = (size_t)ng;
+    CK(dalloc(c, &c->d_hx, c->nx)); CK(dalloc(c, &c->d_hy, c->ny)); CK(dalloc(c, &c->d_hz, c->nz));
+    CK(dalloc(c, &c->d_vol, ne));
+    CK(dalloc(c, &c->d_D, G * ne)); CK(dalloc(c, &c->d_SigR, G * ne)); CK(dalloc(c, &c->d_NSF, G * ne));
+    CK(dalloc(c, &c->d_Chi, G * ne)); CK(dalloc(c, &c->d_SRC, G * ne)); CK(dalloc(c, &c->d_SigS, G * G * ne));
+    CK(dalloc(c, &c->d_phi, G * np)); CK(dalloc(c, &c->d_phi_adj, G * np)); CK(dalloc(c, &c->d_old, G * np));
+    CK(dalloc(c, &c->d_h0, G * np)); CK(dalloc(c, &c->d_h1, G * np)); CK(dalloc(c, &c->d_tmp, G * np));
+    CK(dalloc(c, &c->d_tot, np)); CK(dalloc(c, &c->d_rhs, np)); CK(dalloc(c, &c->d_r, np));
+    CK(dalloc(c, &c->d_p, np)); CK(dalloc(c, &c->d_Ap, np));
+    CK(dalloc(c, &c->d_cg, 1)); CK(dalloc(c, &c->d_part, (size_t)8 * kRedBlocks)); CK(dalloc(c, &c->d_ticket, 16));
+    CK(dalloc(c, &c->d_scal, 16));
+    CKU(cudaMemset(c->d_ticket, 0, 16 * sizeof(unsigned)));
+    CKU(cudaMemset(c->d_cg, 0, sizeof(CgState)));
+    CKU(cudaMallocHost((void **)&c->h_scal, 16 * sizeof(double)));
+    CKU(cudaMallocHost((void **)&c->h_cg, sizeof(CgState)));
+    c->d_minv.assign(G * 3, nullptr); c->d_u.assign(G * 3, nullptr);
+    for (size_t g = 0; g < G; ++g)
+        for (int d = 0; d < c->dim; ++d) {
+            CK(dalloc(c, &c->d_minv[g * 3 + d], (size_t)c->nfaces[d]));
+            CK(dalloc(c, &c->d_u[g * 3 + d], (size_t)c->nfaces[d]));
+        }
+    // geometry factors f_d(e) = Fx[d][ix]*Fy[d][iy]*Fz[d][iz]   (Piola factors, src/FEM.cpp:794-813)
+    {
+        std::vector<double> F[3][3];
+        const std::vector<double> *h[3] = {&c->hx, &c->hy, &c->hz};
+        for (int d = 0; d < 3; ++d)
+            for (int ax = 0; ax < 3; ++ax) {
+                const size_t n = h[ax]->size();
+                F[d][ax].assign(n, 1.0);
+                if (d >= c->dim || ax >= c->dim) continue;
+                for (size_t i = 0; i < n; ++i) {
+                    const double hv = (*h[ax])[i];
+                    if (c->dim == 1) F[d][ax][i] = hv / 2.0;
+                    else if (c->dim == 2) F[d][ax][i] = (ax == d) ? 1.0 / hv : hv;       // f_x = hy/hx, f_y = hx/hy
+                    else F[d][ax][i] = (ax == d) ? 2.0 * hv : 1.0 / hv;                  // f_x = 2hx/(hy hz), ...
+                }
+            }
+        for (int d = 0; d < 3; ++d)
+            for (int ax = 0; ax < 3; ++ax) {
+                CK(dalloc(c, &c->d_F[d][ax], F[d][ax].size()));
+                CKU(cudaMemcpy(c->d_F[d][ax], F[d][ax].data(), F[d][ax].size() * sizeof(double), cudaMemcpyHostToDevice));
+            }
+        std::vector<double> vol(ne);
+        for (int iz = 0; iz < c->nz; ++iz)
+            for (int iy = 0; iy < c->ny; ++iy)
+                for (int ix = 0; ix < c->nx; ++ix)
+                    vol[((size_t)iz * c->ny + iy) * c->nx + ix] = c->hx[ix] * c->hy[iy] * c->hz[iz];
+        CKU(cudaMemcpy(c->d_vol, vol.data(), ne * sizeof(double), cudaMemcpyHostToDevice));
+        CKU(cudaMemcpy(c->d_hx, c->hx.data(), c->hx.size() * sizeof(double), cudaMemcpyHostToDevice));
+        CKU(cudaMemcpy(c->d_hy, c->hy.data(), c->hy.size() * sizeof(double), cudaMemcpyHostToDevice));
+        CKU(cudaMemcpy(c->d_hz, c->hz.data(), c->hz.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    // XS defaults (src/NeutFEM.cpp:184-218) and flat initial flux (:226-235)
+    {
+        std::vector<double> v(G * ne, 1.0);
+        CKU(cudaMemcpy(c->d_D, v.data(), v.size() * sizeof(double), cudaMemcpyHostToDevice));
+        std::fill(v.begin(), v.end(), 0.01);
+        CKU(cudaMemcpy(c->d_SigR, v.data(), v.size() * sizeof(double), cudaMemcpyHostToDevice));
+        std::fill(v.begin(), v.end(), 0.0);
+        CKU(cudaMemcpy(c->d_NSF, v.data(), v.size() * sizeof(double), cudaMemcpyHostToDevice));
+        CKU(cudaMemcpy(c->d_SRC, v.data(), v.size() * sizeof(double), cudaMemcpyHostToDevice));
+        std::fill(v.begin(), v.begin() + ne, 1.0);
+        CKU(cudaMemcpy(c->d_Chi, v.data(), v.size() * sizeof(double), cudaMemcpyHostToDevice));
+        CKU(cudaMemset(c->d_SigS, 0, G * G * ne * sizeof(double)));
+    }
+    k_fill<<<ew_blocks(G * np), 256, 0, c->stream>>>(c->d_phi, (long long)(G * np), 1.0);
+    k_fill<<<ew_blocks(G * np), 256, 0, c->stream>>>(c->d_phi_adj, (long long)(G * np), 1.0);
+    g_launches += 2;
+    CKU(cudaStreamSynchronize(c->stream));
+#undef CK
+#undef CKU
+    *out = c;
+    return NF_OK;
+}
+
+int nf_destroy(nf_ctx *c)
+{
+    if (!c) return NF_OK;
+    cudaSetDevice(c->dev);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    double *ptrs[] = {c->d_hx, c->d_hy, c->d_hz, c->d_vol, c->d_D, c->d_SigR, c->d_NSF, c->d_Chi, c->d_SigS, c->d_SRC,
+                      c->d_sinv, c->d_jac, c->d_phi, c->d_phi_adj, c->d_old, c->d_h0, c->d_h1, c->d_tot, c->d_rhs, c->d_r,
+                      c->d_p, c->d_Ap, c->d_tmp, c->d_zscratch, c->d_J, c->d_part, c->d_scal};
+    for (double *p : ptrs) if (p) cudaFree(p);
+    for (int d = 0; d < 3; ++d) for (int ax = 0; ax < 3; ++ax) if (c->d_F[d][ax]) cudaFree(c->d_F[d][ax]);
+    for (double *p : c->d_minv) if (p) cudaFree(p);
+    for (double *p : c->d_u) if (p) cudaFree(p);
+    if (c->d_cg) cudaFree(c->d_cg);
+    if (c->d_ticket) cudaFree(c->d_ticket);
+    if (c->h_scal) cudaFreeHost(c->h_scal);
+    if (c->h_cg) cudaFreeHost(c->h_cg);
+    for (cudaEvent_t e : {c->ev0, c->ev1, c->ev2, c->ev3}) if (e) cudaEventDestroy(e);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return NF_OK;
+}
+
+int nf_get_sizes(const nf_ctx *c, int32_t *out, int64_t *out64)
+{
+    if (!c) return NF_ERR_ARG;
+    if (out) {
+        out[0] = c->dim; out[1] = c->nx; out[2] = c->ny; out[3] = c->nz; out[4] = c->nloc; out[5] = c->nf;
+        out[6] = c->ni; out[7] = c->K; out[8] = c->M; out[9] = c->ng;
+    }
+    if (out64) {
+        out64[0] = c->ne; out64[1] = c->nphi; out64[2] = c->nJ; out64[3] = c->nJx; out64[4] = c->nJy; out64[5] = c->nJz;
+    }
+    return NF_OK;
+}
+
+int nf_set_bc(nf_ctx *c, int attr, int bc_type, double value)
+{
+    if (!c) return NF_ERR_ARG;
+    c->bc_types[attr] = bc_type; c->bc_values[attr] = value;
+    return NF_OK;
+}
+
+int nf_set_solver(nf_ctx *c, int solver_type, double tol_keff, double tol_flux, int max_outer, int max_inner, int mode)
+{
+    if (!c) return NF_ERR_ARG;
+    if (solver_type >= 0) c->solver_type = solver_type;
+    if (tol_keff > 0) c->tol_keff = tol_keff;
+    if (tol_flux > 0) { c->tol_flux = tol_flux; c->inner_tol = tol_flux; }     // SetTolerance forwards tol_flux (NeutFEM.cpp:334)
+    if (max_outer > 0) c->max_outer = max_outer;
+    if (max_inner > 0) { c->max_inner = max_inner; c->inner_max = max_inner; }
+    if (mode == NF_MODE_PARITY || mode == NF_MODE_FAST) c->mode = mode;
+    return NF_OK;
+}
+
+int nf_upload_xs(nf_ctx *c, const double *D, const double *SigR, const double *NSF, const double *Chi, const double *SigS,
+                 const double *SRC)
+{
+    if (!c) return NF_ERR_ARG;
+    CU(c, cudaSetDevice(c->dev));
+    const size_t n = (size_t)c->ng * c->ne;
+    if (D) { int r = upload(c, c->d_D, D, n); if (r) return r; }
+    if (SigR) { int r = upload(c, c->d_SigR, SigR, n); if (r) return r; }
+    if (NSF) { int r = upload(c, c->d_NSF, NSF, n); if (r) return r; }
+    if (Chi) { int r = upload(c, c->d_Chi, Chi, n); if (r) return r; }
+    if (SRC) { int r = upload(c, c->d_SRC, SRC, n); if (r) return r; }
+    if (SigS) { int r = upload(c, c->d_SigS, SigS, n * c->ng); if (r) return r; }
+    CU(c, cudaStreamSynchronize(c->stream));
+    c->built = false; c->diag_valid = false; c->jac_valid = false;
+    return NF_OK;
+}
+
+int nf_build(nf_ctx *c)
+{
+    if (!c) return NF_ERR_ARG;
+    CU(c, cudaSetDevice(c->dev));
+    int fl[6];
+    dirichlet_flags(c, fl);
+    for (int g = 0; g < c->ng; ++g)
+        for (int d = 0; d < c->dim; ++d) {
+            FactorArgs a;
+            a.D = c->d_D + (size_t)g * c->ne;
+            a.Fa = c->d_F[d][0]; a.Fb = c->d_F[d][1]; a.Fc = c->d_F[d][2];
+            a.hx = c->d_hx; a.hy = c->d_hy; a.hz = c->d_hz;
+            a.minv = c->d_minv[g * 3 + d]; a.u = c->d_u[g * 3 + d];
+            a.nx = c->nx; a.ny = c->ny; a.nz = c->nz; a.dim = c->dim; a.dir = d; a.K = c->K;
+            a.dir_lo = fl[2 * d]; a.dir_hi = fl[2 * d + 1];
+            const int n = (d == 0) ? c->nx : (d == 1 ? c->ny : c->nz);
+            const long long nlines = c->ne / n;
+            LAUNCH(c, k_factor_lines, (int)((nlines + 127) / 128), 128, 0, a);
+        }
+    CU(c, cudaGetLastError());
+    CU(c, cudaStreamSynchronize(c->stream));
+    c->built = true; c->diag_valid = false; c->jac_valid = false;
+    return NF_OK;
+}
+
+static int fill_geom_ptrs(nf_ctx *c, const double *(&Fx)[3], const double *(&Fy)[3], const double *(&Fz)[3])
+{
+    for (int d = 0; d < 3; ++d) { Fx[d] = c->d_F[d][0]; Fy[d] = c->d_F[d][1]; Fz[d] = c->d_F[d][2]; }
+    return 0;
+}
+
+int nf_build_diagonal_cache(nf_ctx *c)
+{
+    if (!c) return NF_ERR_ARG;
+    if (c->K != 0 || c->M != 0) return NF_OK;                    // "non applicable (ordre > 0)", NeutFEM.cpp:485-488
+    if (!c->built) NF_FAIL(c, NF_ERR_STATE, "nf_build_diagonal_cache: call nf_build first");
+    if (c->diag_valid) return NF_OK;
+    CU(c, cudaSetDevice(c->dev));
+    if (!c->d_sinv) { int r = dalloc(c, &c->d_sinv, (size_t)c->ng * c->ne); if (r) return r; }
+    for (int g = 0; g < c->ng; ++g) {
+        DiagArgs a;
+        a.D = c->d_D + (size_t)g * c->ne; a.SigR = c->d_SigR + (size_t)g * c->ne; a.vol = c->d_vol;
+        fill_geom_ptrs(c, a.Fx, a.Fy, a.Fz);
+        a.hx = c->d_hx; a.hy = c->d_hy; a.hz = c->d_hz;
+        a.sinv = c->d_sinv + (size_t)g * c->ne;
+        a.nx = c->nx; a.ny = c->ny; a.nz = c->nz; a.dim = c->dim;
+        dirichlet_flags(c, a.dirichlet);
+        LAUNCH(c, k_build_diag, (int)((c->ne + 255) / 256), 256, 0, a);
+    }
+    CU(c, cudaGetLastError());
+    CU(c, cudaStreamSynchronize(c->stream));
+    c->diag_valid = true;
+    return NF_OK;
+}
+
+static int build_jacobi(nf_ctx *c)
+{
+    if (c->jac_valid) return NF_OK;
+    if (!c->d_jac) { int r = dalloc(c, &c->d_jac, (size_t)c->ng * c->nphi); if (r) return r; }
+    for (int g = 0; g < c->ng; ++g) {
+        JacobiArgs a;
+        a.D = c->d_D + (size_t)g * c->ne; a.SigR = c->d_SigR + (size_t)g * c->ne; a.vol = c->d_vol;
+        fill_geom_ptrs(c, a.Fx, a.Fy, a.Fz);
+        a.hx = c->d_hx; a.hy = c->d_hy; a.hz = c->d_hz;
+        a.minv = c->d_jac + (size_t)g * c->nphi;
+        a.ne = c->ne; a.nx = c->nx; a.ny = c->ny; a.nz = c->nz; a.dim = c->dim; a.K = c->K; a.nloc = c->nloc; a.M1 = c->M1;
+        dirichlet_flags(c, a.dirichlet);
+        memcpy(a.wC, c->wC, sizeof(a.wC)); memcpy(a.cb, c->cb, sizeof(a.cb)); memcpy(a.wface, c->wface, sizeof(a.wface));
+        LAUNCH(c, k_build_jacobi, (int)((c->ne + 127) / 128), 128, 0, a);
+    }
+    CU(c, cudaGetLastError());
+    c->jac_valid = true;
+    return NF_OK;
+}
+
+// ---- flux state ---------------------------------------------------------------------------------------------------
+static int set_flux_impl(nf_ctx *c, double *dst, const double *phi)
+{
+    CU(c, cudaSetDevice(c->dev));
+    const size_t n = (size_t)c->ng * c->nphi;
+    CU(c, cudaMemcpyAsync(c->d_tmp, phi, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    LAUNCH(c, k_aos_to_soa, ew_blocks(n), 256, 0, c->d_tmp, dst, c->ne, c->nloc, c->ng);
+    CU(c, cudaStreamSynchronize(c->stream));
+    return NF_OK;
+}
+
+static int get_flux_impl(nf_ctx *c, const double *src, double *phi)
+{
+    CU(c, cudaSetDevice(c->dev));
+    const size_t n = (size_t)c->ng * c->nphi;
+    LAUNCH(c, k_soa_to_aos, ew_blocks(n), 256, 0, src, c->d_tmp, c->ne, c->nloc, c->ng);
+    CU(c, cudaMemcpyAsync(phi, c->d_tmp, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return NF_OK;
+}
+
+int nf_set_flux(nf_ctx *c, const double *phi) { if (!c || !phi) return NF_ERR_ARG; return set_flux_impl(c, c->d_phi, phi); }
+int nf_get_flux(nf_ctx *c, double *phi) { if (!c || !phi) return NF_ERR_ARG; return get_flux_impl(c, c->d_phi, phi); }
+int nf_get_flux_adjoint(nf_ctx *c, double *phi) { if (!c || !phi) return NF_ERR_ARG; return get_flux_impl(c, c->d_phi_adj, phi); }
+
+int nf_reset_flux(nf_ctx *c)
+{
+    if (!c) return NF_ERR_ARG;
+    CU(c, cudaSetDevice(c->dev));
+    const long long n = (long long)c->ng * c->nphi;
+    LAUNCH(c, k_fill, ew_blocks(n), 256, 0, c->d_phi, n, 1.0);
+    LAUNCH(c, k_fill, ew_blocks(n), 256, 0, c->d_phi_adj, n, 1.0);
+    CU(c, cudaStreamSynchronize(c->stream));
+    c->has_valid = false;
+    return NF_OK;
+}
+
+int nf_get_last_keff(const nf_ctx *c, double *keff, double *keff_adj, int *has_valid)
+{
+    if (!c) return NF_ERR_ARG;
+    if (keff) *keff = c->last_keff;
+    if (keff_adj) *keff_adj = c->last_keff_adj;
+    if (has_valid) *has_valid = c->has_valid ? 1 : 0;
+    return NF_OK;
+}
+
+// ---- inner solve -----------------------------------------------------------------------------------------------------
+// S_g x = b, b and x SoA device vectors. Parity mode restates SolveSchurImplicit (solvers.cpp:577-636); for the
+// solver types / sizes where the reference forms S explicitly and solves it directly or with an Eigen Krylov class
+// (n_phi < 200 or DIRECT_*, solvers.cpp:114-124, 437-509) the same CG is run to 1e-13 instead ("exact" solve).
+static int solve_group(nf_ctx *c, int g, const double *b, double *x, int *iters_out, double *res_out, nf_stats *st)
+{
+    const long long n = c->nphi;
+    const int blocks = ew_blocks(n);
+    double tol = c->inner_tol; int maxit = c->inner_max;
+    const bool direct = (c->solver_type <= NF_DIRECT_LLT) || (c->nphi < 200);
+    const bool fast = (c->mode == NF_MODE_FAST);
+    if (direct) { tol = std::min(tol, 1e-13); maxit = std::max(maxit, (int)std::min<long long>(20000, 4 * n + 100)); }
+    if (fast || direct) { int r = build_jacobi(c); if (r) return r; }
+    const bool pcg = fast || direct;
+    const double *jac = pcg ? c->d_jac + (size_t)g * c->nphi : nullptr;
+    CU(c, cudaEventRecord(c->ev2, c->stream));
+    if (!pcg) {
+        LAUNCH(c, k_cg_init, blocks, 256, 0, b, x, c->d_r, c->d_p, n, tol, c->d_cg, c->d_part + 4 * kRedBlocks, c->d_ticket + 4);
+    } else {
+        if (!fast) LAUNCH(c, k_fill, blocks, 256, 0, x, n, 0.0);      // "direct": x0 = 0
+        { int r = apply_schur(c, g, x, c->d_Ap, false); if (r) return r; }
+        LAUNCH(c, k_pcg_init, blocks, 256, 0, b, c->d_Ap, jac, c->d_r, c->d_p, n, tol, c->d_cg, c->d_part + 4 * kRedBlocks,
+               c->d_ticket + 4);
+    }
+    // poll the device-side done flag every few iterations; iterations after convergence are no-ops on the device
+    const double est_us = (double)n * 160.0 / 6.0e6 + 15.0;
+    int poll = (int)std::max(1.0, std::min(16.0, 200.0 / est_us));
+    int k = 0;
+    bool done = false;
+    while (k < maxit && !done) {
+        const int chunk = std::min(poll, maxit - k);
+        for (int j = 0; j < chunk; ++j) {
+            { int r = apply_schur(c, g, c->d_p, c->d_Ap, true); if (r) return r; }
+            if (!pcg) {
+                LAUNCH(c, k_cg_update, blocks, 256, 0, c->d_p, c->d_Ap, x, c->d_r, n, c->d_cg, c->d_part + 4 * kRedBlocks, c->d_ticket + 4);
+                LAUNCH(c, k_cg_pupdate, blocks, 256, 0, c->d_r, c->d_p, n, c->d_cg);
+            } else {
+                LAUNCH(c, k_pcg_update, blocks, 256, 0, c->d_p, c->d_Ap, jac, x, c->d_r, n, c->d_cg, c->d_part + 4 * kRedBlocks, c->d_ticket + 4);
+                LAUNCH(c, k_pcg_pupdate, blocks, 256, 0, c->d_r, jac, c->d_p, n, c->d_cg);
+            }
+        }
+        k += chunk;
+        CU(c, cudaMemcpyAsync(c->h_cg, c->d_cg, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+        done = c->h_cg->done != 0;
+    }
+    if (!done) {   // max_iter reached: freeze further no-op semantics
+        CU(c, cudaMemcpyAsync(c->h_cg, c->d_cg, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+    }
+    CU(c, cudaEventRecord(c->ev3, c->stream));
+    CU(c, cudaEventSynchronize(c->ev3));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->ev2, c->ev3);
+    const int iters = c->h_cg->iters;
+    const double res = (c->h_cg->bnorm_sq > 0) ? std::sqrt(c->h_cg->rr_true / c->h_cg->bnorm_sq) : 0.0;
+    if (iters_out) *iters_out = iters;
+    if (res_out) *res_out = res;
+    if (st) {
+        st->cg_iterations += iters; st->cg_dof_iterations += (long long)iters * n; st->group_solves += 1;
+        st->ms_schur_cg += ms; st->last_cg_residual = res;
+    }
+    return NF_OK;
+}
+
+static void fill_outer(nf_ctx *c, OuterArgs &a, const double *phi)
+{
+    a.phi = phi; a.vol = c->d_vol; a.NSF = c->d_NSF; a.Chi = c->d_Chi; a.SigS = c->d_SigS;
+    a.ne = c->ne; a.nloc = c->nloc; a.ng = c->ng;
+    memcpy(a.wM, c->wM, sizeof(a.wM));
+}
+
+struct Cheb {   // coefficients of ChebyshevAccel(15, 0.98), src/solvers.cpp:664-693
+    int nmax = 15, it = 0; double sigma = 0.98; double a[16], b[16];
+    Cheb() {
+        const double G = std::acosh(2.0 / sigma - 1.0);
+        a[0] = b[0] = 0.0; a[1] = 2.0 / (2.0 - sigma); b[1] = 0.0;
+        for (int k = 2; k < nmax; ++k) { a[k] = std::cosh((k - 1) * G) / std::cosh(k * G); b[k] = std::cosh((k - 2) * G) / std::cosh(k * G); }
+    }
+    // returns (step, ca, cb) for the kernel and advances the state like operator()
+    void next(int &step, double &ca, double &cb) {
+        if (it == nmax) it = 0;
+        if (it == 0) { step = 0; ca = cb = 0.0; }
+        else if (it == 1) { step = 1; ca = a[1]; cb = 0.0; }
+        else { step = 2; ca = (4.0 / sigma) * a[it]; cb = b[it]; }
+        ++it;
+    }
+};
+
+static int power_iteration(nf_ctx *c, bool adjoint, int use_diag, int accel, double keff0, bool fixed_k, bool check_k,
+                           int cheb_from, double *keff_out, nf_stats *st)
+{
+    // Direct: src/NeutFEM.cpp:1694-1803. Adjoint: :1915-2012.
+    const long long np = c->nphi, ntot = np * c->ng;
+    double *phi = adjoint ? c->d_phi_adj : c->d_phi;
+    double keff = keff0;
+    Cheb cheb;
+    OuterArgs oa;
+    fill_outer(c, oa, phi);
+    const int blocks = ew_blocks(np), blocks_all = ew_blocks(ntot);
+    for (int it = 0; it < c->max_outer; ++it) {
+        CU(c, cudaMemcpyAsync(c->d_old, phi, ntot * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        LAUNCH(c, k_total_fission, blocks, 256, 0, oa, c->d_tot, adjoint ? 1 : 0, c->d_part + 5 * kRedBlocks, c->d_ticket + 5, c->d_scal + 0);
+        for (int g = 0; g < c->ng; ++g) {
+            LAUNCH(c, k_group_rhs, blocks, 256, 0, oa, c->d_tot, g, 1.0 / keff, adjoint ? 1 : 0, (const double *)nullptr, c->d_rhs);
+            if (use_diag) {
+                LAUNCH(c, k_diag_solve, ew_blocks(c->ne), 256, 0, c->d_sinv + (size_t)g * c->ne, c->d_rhs, phi + (size_t)g * np, c->ne);
+            } else {
+                int r = solve_group(c, g, c->d_rhs, phi + (size_t)g * np, nullptr, nullptr, st);
+                if (r) return r;
+            }
+        }
+        LAUNCH(c, k_outer_post, blocks, 256, 0, oa, c->d_old, adjoint ? 1 : 0, c->d_part + 5 * kRedBlocks, c->d_ticket + 5, c->d_scal + 1);
+        CU(c, cudaMemcpyAsync(c->h_scal, c->d_scal, 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+        const double prod_old = c->h_scal[0], prod_new = c->h_scal[1], sol_sq = c->h_scal[2], diff_sq = c->h_scal[3];
+        double diff_k;
+        if (!adjoint) {
+            const double keff_new = keff * (prod_new / prod_old);
+            diff_k = std::fabs(keff_new - keff);
+            if (it >= 1) keff = keff_new;                          // NeutFEM.cpp:1774
+        } else if (!fixed_k) {
+            double keff_new = keff;
+            if (std::fabs(prod_old) > 1e-14 && it > 0) keff_new = keff * (prod_new / prod_old);
+            diff_k = std::fabs(keff_new - keff);
+            keff = keff_new;
+        } else diff_k = 0.0;
+        const double diff_flux = std::sqrt(diff_sq / sol_sq);
+        const double norm = std::sqrt(sol_sq);
+        const double scale = (norm > 1e-14) ? 1.0 / norm : 1.0;
+        int step = -1; double ca = 0.0, cb = 0.0;
+        if (accel == NF_ACCEL_CHEBYSHEV && it >= cheb_from) cheb.next(step, ca, cb);
+        LAUNCH(c, k_scale_chebyshev, blocks_all, 256, 0, phi, c->d_h0, c->d_h1, ntot, scale, step, ca, cb);
+        if (st) { st->outer_iterations = it + 1; st->last_dk = diff_k; st->last_dphi = diff_flux; }
+        const bool conv = diff_flux < c->tol_flux && (!check_k || diff_k < c->tol_keff);
+        if (conv) { if (st) st->converged = 1; break; }
+    }
+    CU(c, cudaStreamSynchronize(c->stream));
+    *keff_out = keff;
+    return NF_OK;
+}
+
+int nf_solve_keff(nf_ctx *c, int use_diag, int accel, double keff_init, double *keff, nf_stats *stats)
+{
+    if (!c || !keff) return NF_ERR_ARG;
+    if (!c->built) NF_FAIL(c, NF_ERR_STATE, "nf_solve_keff: call nf_build first");
+    CU(c, cudaSetDevice(c->dev));
+    nf_stats st;
+    memset(&st, 0, sizeof(st));
+    c->launches_call = 0;
+    if (use_diag && !(c->K == 0 && c->M == 0)) use_diag = 0;      // NeutFEM.cpp:1640-1644
+    if (use_diag) { int r = nf_build_diagonal_cache(c); if (r) return r; }
+    CU(c, cudaEventRecord(c->ev0, c->stream));
+    double k0 = (keff_init > 0) ? keff_init : (c->has_valid ? c->last_keff : 1.0);
+    double k = k0;
+    int r = power_iteration(c, false, use_diag, accel, k0, false, true, 2, &k, &st);   // Chebyshev from it >= 2 (:1786)
+    if (r) return r;
+    CU(c, cudaEventRecord(c->ev1, c->stream));
+    CU(c, cudaEventSynchronize(c->ev1));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    st.ms_total = ms; st.kernel_launches = c->launches_call;
+    c->has_valid = true; c->last_keff = k;
+    *keff = k;
+    if (stats) *stats = st;
+    return NF_OK;
+}
+
+int nf_solve_adjoint(nf_ctx *c, int normalize_to_direct, int use_direct_keff, double *keff_adj, nf_stats *stats)
+{
+    if (!c || !keff_adj) return NF_ERR_ARG;
+    if (!c->built) NF_FAIL(c, NF_ERR_STATE, "nf_solve_adjoint: call nf_build first");
+    CU(c, cudaSetDevice(c->dev));
+    nf_stats st;
+    memset(&st, 0, sizeof(st));
+    c->launches_call = 0;
+    CU(c, cudaEventRecord(c->ev0, c->stream));
+    double k = 1.0;
+    const bool fixed = use_direct_keff && c->has_valid;
+    if (fixed) k = c->last_keff;
+    const long long ntot = (long long)c->ng * c->nphi;
+    LAUNCH(c, k_fill, ew_blocks(ntot), 256, 0, c->d_phi_adj, ntot, 1.0 / std::sqrt((double)ntot));    // NeutFEM.cpp:1894-1895
+    // Chebyshev only in power-iteration mode and from it >= 5 (NeutFEM.cpp:1990-1992)
+    const int accel = use_direct_keff ? NF_ACCEL_NONE : NF_ACCEL_CHEBYSHEV;
+    int r = power_iteration(c, true, 0, accel, k, fixed, !use_direct_keff, 5, &k, &st);
+    if (r) return r;
+    if (normalize_to_direct && c->has_valid) {                   // bi-orthogonal normalisation, NeutFEM.cpp:2020-2066
+        LAUNCH(c, k_biorth, ew_blocks(c->nphi), 256, 0, c->d_phi, c->d_phi_adj, c->d_vol, c->ne, c->nloc, c->ng,
+               c->d_part + 5 * kRedBlocks, c->d_ticket + 5, c->d_scal + 4, WVec(c->wC, c->dim));
+        CU(c, cudaMemcpyAsync(c->h_scal + 4, c->d_scal + 4, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+        const double ip = c->h_scal[4];
+        if (std::fabs(ip) > 1e-14)
+            LAUNCH(c, k_scale_chebyshev, ew_blocks(ntot), 256, 0, c->d_phi_adj, c->d_h0, c->d_h1, ntot, 1.0 / ip, -1, 0.0, 0.0);
+    }
+    CU(c, cudaEventRecord(c->ev1, c->stream));
+    CU(c, cudaEventSynchronize(c->ev1));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    st.ms_total = ms; st.kernel_launches = c->launches_call;
+    c->last_keff_adj = k;
+    *keff_adj = k;
+    if (stats) *stats = st;
+    return NF_OK;
+}
+
+int nf_solve_source(nf_ctx *c, double *amplification, nf_stats *stats)
+{
+    // The reference declares SolveSubcritical (include/NeutFEM.hpp:279) and documents it (src/wrapper.cpp:699-715)
+    // but never defines it. Defined here as the source iteration phi <- L^-1 (F phi + Q), amplification =
+    // <phi>/<phi_0> with phi_0 = L^-1 Q (no fission), volume-weighted cell averages. PARITY UNPINNED.
+    if (!c || !amplification) return NF_ERR_ARG;
+    if (!c->built) NF_FAIL(c, NF_ERR_STATE, "nf_solve_source: call nf_build first");
+    CU(c, cudaSetDevice(c->dev));
+    nf_stats st;
+    memset(&st, 0, sizeof(st));
+    c->launches_call = 0;
+    CU(c, cudaEventRecord(c->ev0, c->stream));
+    const long long np = c->nphi, ntot = np * c->ng;
+    const int blocks = ew_blocks(np);
+    OuterArgs oa;
+    fill_outer(c, oa, c->d_phi);
+    double total0 = 0.0, total = 0.0;
+    for (int pass = 0; pass < 2; ++pass) {              // pass 0: without fission, pass 1: with fission
+        LAUNCH(c, k_fill, ew_blocks(ntot), 256, 0, c->d_phi, ntot, 0.0);
+        double prev = -1.0;
+        for (int it = 0; it < c->max_outer; ++it) {
+            CU(c, cudaMemcpyAsync(c->d_old, c->d_phi, ntot * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+            LAUNCH(c, k_total_fission, blocks, 256, 0, oa, c->d_tot, 0, c->d_part + 5 * kRedBlocks, c->d_ticket + 5, c->d_scal + 0);
+            for (int g = 0; g < c->ng; ++g) {
+                LAUNCH(c, k_group_rhs, blocks, 256, 0, oa, c->d_tot, g, pass ? 1.0 : 0.0, 0, (const double *)c->d_SRC, c->d_rhs);
+                int r = solve_group(c, g, c->d_rhs, c->d_phi + (size_t)g * np, nullptr, nullptr, &st);
+                if (r) return r;
+            }
+            LAUNCH(c, k_flux_integral, blocks, 256, 0, c->d_phi, c->d_old, c->d_vol, c->ne, c->nloc, c->ng,
+                   c->d_part + 5 * kRedBlocks, c->d_ticket + 5, c->d_scal + 5);
+            CU(c, cudaMemcpyAsync(c->h_scal + 5, c->d_scal + 5, 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            CU(c, cudaStreamSynchronize(c->stream));
+            const double integral = c->h_scal[5], nsq = c->h_scal[6], dsq = c->h_scal[7];
+            st.outer_iterations += 1;
+            (pass ? total : total0) = integral;
+            const double dphi = (nsq > 0) ? std::sqrt(dsq / nsq) : 0.0;
+            st.last_dphi = dphi;
+            if (dphi < c->tol_flux || nsq == 0.0) { st.converged = 1; break; }
+            if (prev > 0 && integral > 1e30) NF_FAIL(c, NF_ERR_STATE, "nf_solve_source: source iteration diverges (system is not subcritical)");
+            prev = integral;
+        }
+    }
+    CU(c, cudaEventRecord(c->ev1, c->stream));
+    CU(c, cudaEventSynchronize(c->ev1));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    st.ms_total = ms; st.kernel_launches = c->launches_call;
+    *amplification = (total0 != 0.0) ? total / total0 : 0.0;
+    if (stats) *stats = st;
+    return NF_OK;
+}
+
+// ---- operator-level hooks -----------------------------------------------------------------------------------------
+int nf_schur_apply(nf_ctx *c, int g, const double *x, double *y)
+{
+    if (!c || !x || !y || g < 0 || g >= c->ng) return NF_ERR_ARG;
+    if (!c->built) NF_FAIL(c, NF_ERR_STATE, "nf_schur_apply: call nf_build first");
+    CU(c, cudaSetDevice(c->dev));
+    const size_t n = (size_t)c->nphi;
+    CU(c, cudaMemcpyAsync(c->d_tmp, x, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    LAUNCH(c, k_aos_to_soa, ew_blocks(n), 256, 0, c->d_tmp, c->d_p, c->ne, c->nloc, 1);
+    { int r = apply_schur(c, g, c->d_p, c->d_Ap, false); if (r) return r; }
+    LAUNCH(c, k_soa_to_aos, ew_blocks(n), 256, 0, c->d_Ap, c->d_tmp, c->ne, c->nloc, 1);
+    CU(c, cudaMemcpyAsync(y, c->d_tmp, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return NF_OK;
+}
+
+int nf_schur_solve(nf_ctx *c, int g, const double *rhs, double *phi, int *iterations, double *residual)
+{
+    if (!c || !rhs || !phi || g < 0 || g >= c->ng) return NF_ERR_ARG;
+    if (!c->built) NF_FAIL(c, NF_ERR_STATE, "nf_schur_solve: call nf_build first");
+    CU(c, cudaSetDevice(c->dev));
+    const size_t n = (size_t)c->nphi;
+    CU(c, cudaMemcpyAsync(c->d_tmp, rhs, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    LAUNCH(c, k_aos_to_soa, ew_blocks(n), 256, 0, c->d_tmp, c->d_rhs, c->ne, c->nloc, 1);
+    LAUNCH(c, k_fill, ew_blocks(n), 256, 0, c->d_tot, (long long)n, 0.0);
+    { int r = solve_group(c, g, c->d_rhs, c->d_tot, iterations, residual, nullptr); if (r) return r; }
+    LAUNCH(c, k_soa_to_aos, ew_blocks(n), 256, 0, c->d_tot, c->d_tmp, c->ne, c->nloc, 1);
+    CU(c, cudaMemcpyAsync(phi, c->d_tmp, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return NF_OK;
+}
+
+static int current_group(nf_ctx *c, int g, const double *phi_soa, double *dJ)
+{
+    CU(c, cudaMemsetAsync(dJ, 0, (size_t)c->nJ * sizeof(double), c->stream));
+    for (int d = 0; d < c->dim; ++d) {
+        CurrentArgs a;
+        memset(&a, 0, sizeof(a));
+        a.phi = phi_soa; a.J = dJ;
+        a.minv = c->d_minv[g * 3 + d]; a.u = c->d_u[g * 3 + d];
+        a.D = c->d_D + (size_t)g * c->ne;
+        a.Fa = c->d_F[d][0]; a.Fb = c->d_F[d][1]; a.Fc = c->d_F[d][2];
+        a.ne = c->ne; a.nx = c->nx; a.ny = c->ny; a.nz = c->nz; a.dim = c->dim; a.dir = d; a.K = c->K; a.M1 = c->M1;
+        a.nt = c->nt; a.nf = c->nf; a.ni = c->ni;
+        a.face_off = (d == 0) ? 0 : (d == 1 ? c->nJx : c->nJx + c->nJy);
+        a.bub_off = c->nJface + (long long)d * c->ne * c->ni;
+        for (int t = 0; t < c->nt; ++t) for (int p = 0; p < c->M1; ++p) a.mode[t][p] = c->tmode[d][t][p];
+        const int n = (d == 0) ? c->nx : (d == 1 ? c->ny : c->nz);
+        const long long nthreads = (c->ne / n) * c->nt;
+        LAUNCH(c, k_current_lines, (int)((nthreads + 127) / 128), 128, 0, a);
+    }
+    CU(c, cudaGetLastError());
+    return NF_OK;
+}
+
+int nf_current_from_flux(nf_ctx *c, int g, const double *phi, double *J)
+{
+    if (!c || !phi || !J || g < 0 || g >= c->ng) return NF_ERR_ARG;
+    if (!c->built) NF_FAIL(c, NF_ERR_STATE, "nf_current_from_flux: call nf_build first");
+    CU(c, cudaSetDevice(c->dev));
+    if (!c->d_J) { int r = dalloc(c, &c->d_J, (size_t)c->nJ); if (r) return r; }
+    const size_t n = (size_t)c->nphi;
+    CU(c, cudaMemcpyAsync(c->d_tmp, phi, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    LAUNCH(c, k_aos_to_soa, ew_blocks(n), 256, 0, c->d_tmp, c->d_p, c->ne, c->nloc, 1);
+    { int r = current_group(c, g, c->d_p, c->d_J); if (r) return r; }
+    CU(c, cudaMemcpyAsync(J, c->d_J, (size_t)c->nJ * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return NF_OK;
+}
+
+int nf_get_current(nf_ctx *c, double *J, int adjoint)
+{
+    if (!c || !J) return NF_ERR_ARG;
+    if (!c->built) NF_FAIL(c, NF_ERR_STATE, "nf_get_current: call nf_build first");
+    CU(c, cudaSetDevice(c->dev));
+    if (!c->d_J) { int r = dalloc(c, &c->d_J, (size_t)c->nJ); if (r) return r; }
+    const double *phi = adjoint ? c->d_phi_adj : c->d_phi;
+    for (int g = 0; g < c->ng; ++g) {
+        int r = current_group(c, g, phi + (size_t)g * c->nphi, c->d_J);
+        if (r) return r;
+        CU(c, cudaMemcpyAsync(J + (size_t)g * c->nJ, c->d_J, (size_t)c->nJ * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+    }
+    return NF_OK;
+}
+
+int nf_get_diagonal_cache(nf_ctx *c, int g, double *s_inv)
+{
+    if (!c || !s_inv || g < 0 || g >= c->ng) return NF_ERR_ARG;
+    if (!c->diag_valid) NF_FAIL(c, NF_ERR_STATE, "nf_get_diagonal_cache: cache not built");
+    CU(c, cudaSetDevice(c->dev));
+    CU(c, cudaMemcpy(s_inv, c->d_sinv + (size_t)g * c->ne, (size_t)c->ne * sizeof(double), cudaMemcpyDeviceToHost));
+    return NF_OK;
+}
+
+int nf_comm_unique_id(char id[128])
+{
+    (void)id;
+    return NF_ERR_STATE;   // multi-GPU slabs: see nf_slab.cu (round-1: single GPU per context)
+}
+
+int nf_comm_init(nf_ctx *c, const char id[128], int rank, int nranks)
+{
+    (void)id; (void)rank;
+    if (!c) return NF_ERR_ARG;
+    if (nranks == 1) return NF_OK;
+    NF_FAIL(c, NF_ERR_STATE, "nf_comm_init: z-slab decomposition is not available in this build");
+}
+
+}  // extern "C"

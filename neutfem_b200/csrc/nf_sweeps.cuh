@@ -1,0 +1,322 @@
+// nf_sweeps.cuh -- matrix-free application of the Schur complement S_g = C_g + B A_g^-1 B^T
+// (reference SchurSolver::SchurProduct, src/solvers.cpp:535-547, where A^-1 is an Eigen::SparseLU solve).
+//
+// A_g is a direct sum over direction x grid line x transverse Legendre mode of one block-tridiagonal matrix per
+// line. After condensing the cell-local bubbles, each (line, mode) is a scalar symmetric
+// tridiagonal system in the face unknowns whose LDL^T factors (minv, u) are precomputed per group in nf_build.
+// One sweep kernel per direction:
+//   k_sweep_x      lines are contiguous in memory: one warp per (line, transverse pair), the line lives in shared
+//                  memory, each lane owns a chunk of faces and the chunks are stitched with a warp scan of affine
+//                  maps (exact, no truncation).
+//   k_sweep_march  y / z lines: one thread per (x position, transverse pair) marching along the line, fully
+//                  coalesced across the warp; forward intermediates go to shared memory when the line is short
+//                  enough, otherwise to a per-warp global scratch strip.
+// x^T S x is accumulated on the fly (sum diag*x^2 + w * sum z_f^2/m_f) so CG never re-reads Ap for p.Ap.
+#pragma once
+#include "nf_common.cuh"
+
+namespace nf {
+
+// rhs of the condensed face system at face f from the flux modes of the two adjacent cells
+//   t_f = x0_{f-1} - x0_f ; bubbles: tb_l = -beta_l x^{l+1}, beta = 4/3, 4/5 ;
+//   T_f = t_f - sum_adjacent_cells [ 5/8 tb0 + s 7/8 tb1 ],  s = -1 if f is the cell's lower face, +1 if upper.
+template <int K, int M1>
+__device__ __forceinline__ double face_rhs(double x0m, double tb0m, double tb1m, double x0, double tb0, double tb1)
+{
+    double T = x0m - x0;
+    if (K >= 1 && M1 >= 2) T -= 0.625 * (tb0m + tb0);
+    if (K >= 2 && M1 >= 3) T -= 0.875 * (tb1m - tb1);
+    return T;
+}
+
+template <int K, int M1>
+__global__ void __launch_bounds__(128) k_sweep_x(const SweepArgs a)
+{
+    if (a.done && *a.done) return;
+    extern __shared__ double sm[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, WPB = blockDim.x >> 5;
+    const int n = a.nx, Lc = a.Lc, RL = 32 * Lc;
+    constexpr int NROW = 3 + M1;
+    double *MINV = sm + (size_t)wib * NROW * RL;
+    double *U = MINV + RL, *T = U + RL, *Y = T + RL;
+    const long long nlines = (long long)a.ny * a.nz;
+    double acc = 0.0;
+
+    for (long long line = (long long)blockIdx.x * WPB + wib; line < nlines; line += (long long)gridDim.x * WPB) {
+        const int iy = (int)(line % a.ny), iz = (int)(line / a.ny);
+        __syncwarp();
+        {
+            const double *gm = a.minv + line * (n + 1), *gu = a.u + line * (n + 1);
+            for (int f = lane; f < RL; f += 32) {
+                MINV[f] = (f <= n) ? gm[f] : 0.0;
+                U[f] = (f < n) ? gu[f] : 0.0;
+            }
+        }
+      for (int t = 0; t < a.nt; ++t) {
+        double fyz[3] = {0.0, 0.0, 0.0};
+        for (int d = 0; d < a.dim; ++d) fyz[d] = a.Fy[d][iy] * a.Fz[d][iz];
+        const double w = a.w[t];
+        int md[3];
+#pragma unroll
+        for (int p = 0; p < M1; ++p) md[p] = a.mode[t][p];
+
+        // ---- P1: load the line, form diag*x and the condensed face rhs
+        double cx0 = 0.0, ctb0 = 0.0, ctb1 = 0.0;   // values of cell f-1 carried across 32-blocks
+        for (int fb = 0; fb < RL; fb += 32) {
+            const int f = fb + lane;
+            const bool cell = f < n;
+            const long long e = line * n + f;
+            double xv[3] = {0.0, 0.0, 0.0};
+            if (cell) {
+                const double Dv = a.D[e], Sv = a.SigR[e] * a.vol[e];
+                double q[3];
+                for (int d = 0; d < a.dim; ++d) q[d] = Dv / (a.Fx[d][f] * fyz[d]);
+#pragma unroll
+                for (int p = 0; p < M1; ++p) {
+                    xv[p] = a.x[(size_t)md[p] * a.ne + e];
+                    double dg = Sv * a.wC[md[p]];
+                    for (int d = 0; d < a.dim; ++d) dg += q[d] * a.cb[d][md[p]];
+                    const double yv = dg * xv[p];
+                    Y[p * RL + f] = yv;
+                    acc += yv * xv[p];
+                }
+            }
+            const double tb0 = (K >= 1 && M1 >= 2) ? -(4.0 / 3.0) * xv[1] : 0.0;
+            const double tb1 = (K >= 2 && M1 >= 3) ? -(4.0 / 5.0) * xv[2] : 0.0;
+            double x0m = __shfl_up_sync(0xffffffffu, xv[0], 1);
+            double tb0m = __shfl_up_sync(0xffffffffu, tb0, 1);
+            double tb1m = __shfl_up_sync(0xffffffffu, tb1, 1);
+            if (lane == 0) { x0m = cx0; tb0m = ctb0; tb1m = ctb1; }
+            T[f] = (f <= n) ? face_rhs<K, M1>(x0m, tb0m, tb1m, xv[0], tb0, tb1) : 0.0;
+            cx0 = __shfl_sync(0xffffffffu, xv[0], 31);
+            ctb0 = __shfl_sync(0xffffffffu, tb0, 31);
+            ctb1 = __shfl_sync(0xffffffffu, tb1, 31);
+        }
+        __syncwarp();
+
+        // ---- P2: forward substitution z_f = T_f - u_{f-1} z_{f-1}, chunk per lane + affine scan
+        const int f0 = lane * Lc;
+        {
+            double z = 0.0, A = 1.0;
+            for (int j = 0; j < Lc; ++j) {
+                const int f = f0 + j;
+                const double um = (f > 0) ? U[f - 1] : 0.0;
+                z = T[f] - um * z;
+                A *= -um;
+            }
+#pragma unroll
+            for (int s = 1; s < 32; s <<= 1) {
+                const double Ap = __shfl_up_sync(0xffffffffu, A, s), zp = __shfl_up_sync(0xffffffffu, z, s);
+                if (lane >= s) { z = A * zp + z; A = A * Ap; }
+            }
+            double carry = __shfl_up_sync(0xffffffffu, z, 1);
+            if (lane == 0) carry = 0.0;
+            z = carry;
+            double q = 0.0;
+            for (int j = 0; j < Lc; ++j) {
+                const int f = f0 + j;
+                const double um = (f > 0) ? U[f - 1] : 0.0;
+                z = T[f] - um * z;
+                T[f] = z;
+                q += z * z * MINV[f];
+            }
+            acc += w * q;
+        }
+        // ---- P3: backward substitution J_f = z_f/m_f - u_f J_{f+1}
+        {
+            double J = 0.0, Bp = 1.0;
+            for (int j = Lc - 1; j >= 0; --j) {
+                const int f = f0 + j;
+                const double uf = U[f];
+                J = MINV[f] * T[f] - uf * J;
+                Bp *= -uf;
+            }
+#pragma unroll
+            for (int s = 1; s < 32; s <<= 1) {
+                const double Bq = __shfl_down_sync(0xffffffffu, Bp, s), Jq = __shfl_down_sync(0xffffffffu, J, s);
+                if (lane + s < 32) { J = Bp * Jq + J; Bp = Bp * Bq; }
+            }
+            double carry = __shfl_down_sync(0xffffffffu, J, 1);
+            if (lane == 31) carry = 0.0;
+            J = carry;
+            for (int j = Lc - 1; j >= 0; --j) {
+                const int f = f0 + j;
+                J = MINV[f] * T[f] - U[f] * J;
+                T[f] = J;
+            }
+        }
+        __syncwarp();
+        // ---- P4: y = diag*x + w * B J
+        for (int fb = 0; fb < n; fb += 32) {
+            const int f = fb + lane;
+            if (f < n) {
+                const long long e = line * n + f;
+                const double JL = T[f], JR = T[f + 1];
+                double out[3];
+                out[0] = Y[f] + w * (JR - JL);
+                if (M1 >= 2) out[1] = Y[RL + f] + ((K >= 1) ? w * (5.0 / 6.0) * (JL + JR) : 0.0);
+                if (M1 >= 3) out[2] = Y[2 * RL + f] + ((K >= 2) ? w * (7.0 / 10.0) * (JR - JL) : 0.0);
+#pragma unroll
+                for (int p = 0; p < M1; ++p) {
+                    double *yp = a.y + (size_t)md[p] * a.ne + e;
+                    *yp = a.first ? out[p] : (*yp + out[p]);
+                }
+            }
+        }
+        __syncwarp();
+      }  // t
+    }
+    if (a.red_out) {
+        double v[1] = {acc};
+        grid_reduce<1>(v, a.red_part, a.ticket, a.red_out);
+    }
+}
+
+// y / z sweeps. stride = distance between consecutive cells of a line (nx for y, nx*ny for z);
+// n = cells per line; lines are indexed by (orth, ix): y: orth = iz, z: orth = iy.
+struct MarchGeom {
+    int n;            // cells per line
+    int north;        // number of orthogonal indices
+    long long stride; // cell stride along the line
+    long long ostride_cell;  // cell offset per orth index
+    long long ostride_face;  // face-array offset per orth index
+};
+
+template <int K, int M1, bool SMEMZ>
+__global__ void __launch_bounds__(128) k_sweep_march(const SweepArgs a, const MarchGeom g)
+{
+    if (a.done && *a.done) return;
+    extern __shared__ double sm[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, WPB = blockDim.x >> 5;
+    const int n = g.n;
+    const int nxb = (a.nx + 31) >> 5;
+    const long long nitems = (long long)g.north * a.nt * nxb;
+    double *zb = SMEMZ ? (sm + (size_t)wib * (n + 1) * 32)
+                       : (a.zscratch + ((size_t)blockIdx.x * WPB + wib) * (size_t)(n + 1) * 32);
+    double acc = 0.0;
+    for (long long item = (long long)blockIdx.x * WPB + wib; item < nitems; item += (long long)gridDim.x * WPB) {
+        const int xb = (int)(item % nxb);
+        const long long r = item / nxb;
+        const int t = (int)(r % a.nt);
+        const int orth = (int)(r / a.nt);
+        const int ix = xb * 32 + lane;
+        if (ix < a.nx) {
+            const double w = a.w[t];
+            const long long c0 = (long long)orth * g.ostride_cell + ix;
+            const long long s0 = (long long)orth * g.ostride_face + ix;
+            const double *xp[3];
+            double *yp[3];
+#pragma unroll
+            for (int p = 0; p < M1; ++p) {
+                xp[p] = a.x + (size_t)a.mode[t][p] * a.ne + c0;
+                yp[p] = a.y + (size_t)a.mode[t][p] * a.ne + c0;
+            }
+            const double *um = a.u + s0, *mi = a.minv + s0;
+            // forward
+            double x0m = 0.0, tb0m = 0.0, tb1m = 0.0, z = 0.0, uprev = 0.0, q = 0.0;
+#pragma unroll 4
+            for (int f = 0; f <= n; ++f) {
+                double x0 = 0.0, tb0 = 0.0, tb1 = 0.0;
+                if (f < n) {
+                    const long long o = (long long)f * g.stride;
+                    x0 = xp[0][o];
+                    if (K >= 1 && M1 >= 2) tb0 = -(4.0 / 3.0) * xp[1][o];
+                    if (K >= 2 && M1 >= 3) tb1 = -(4.0 / 5.0) * xp[2][o];
+                }
+                const double T = face_rhs<K, M1>(x0m, tb0m, tb1m, x0, tb0, tb1);
+                z = T - uprev * z;
+                const long long so = (long long)f * g.stride;
+                uprev = um[so];
+                q += z * z * mi[so];
+                zb[(size_t)f * 32 + lane] = z;
+                x0m = x0; tb0m = tb0; tb1m = tb1;
+            }
+            acc += w * q;
+            // backward
+            double Jn = 0.0;
+#pragma unroll 4
+            for (int f = n; f >= 0; --f) {
+                const long long so = (long long)f * g.stride;
+                const double J = mi[so] * zb[(size_t)f * 32 + lane] - um[so] * Jn;
+                if (f < n) {
+                    yp[0][so] += w * (Jn - J);
+                    if (K >= 1 && M1 >= 2) yp[1][so] += w * (5.0 / 6.0) * (J + Jn);
+                    if (K >= 2 && M1 >= 3) yp[2][so] += w * (7.0 / 10.0) * (Jn - J);
+                }
+                Jn = J;
+            }
+        }
+    }
+    if (a.red_out) {
+        double v[1] = {acc};
+        grid_reduce<1>(v, a.red_part, a.ticket, a.red_out);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// LDL^T factors of the condensed line matrices of A_g for one direction (build step; replaces the
+// Eigen::SparseLU::compute(A_g) of SchurSolver::SetMatrices, src/solvers.cpp:163, and ApplyDirichletToA,
+// src/NeutFEM.cpp:1328-1456). One thread per line.
+struct FactorArgs {
+    const double *D;        // D_g[e]
+    const double *Fa, *Fb, *Fc;   // 1-D factors of f_d along x, y, z
+    const double *hx, *hy, *hz;
+    double *minv, *u;
+    int nx, ny, nz, dim, dir, K;
+    int dir_lo, dir_hi;     // Dirichlet flags of the two sides
+};
+
+__global__ void k_factor_lines(const FactorArgs a)
+{
+    const int n = (a.dir == 0) ? a.nx : (a.dir == 1 ? a.ny : a.nz);
+    const long long nlines = (long long)a.nx * a.ny * a.nz / n;
+    const long long L = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (L >= nlines) return;
+    // line coordinates and strides: cells e0 + f*cs, faces s0 + f*fs
+    int i0, i1;          // the two transverse indices (fast, slow)
+    long long e0, cs, s0, fs;
+    if (a.dir == 0) {            // lines (iy,iz), faces ((iz*ny+iy)*(nx+1) + f)
+        i0 = (int)(L % a.ny); i1 = (int)(L / a.ny);
+        e0 = L * a.nx; cs = 1; s0 = L * (a.nx + 1); fs = 1;
+    } else if (a.dir == 1) {     // lines (ix,iz), faces ((iz*(ny+1)+f)*nx + ix)
+        i0 = (int)(L % a.nx); i1 = (int)(L / a.nx);
+        e0 = (long long)i1 * a.ny * a.nx + i0; cs = a.nx; s0 = (long long)i1 * (a.ny + 1) * a.nx + i0; fs = a.nx;
+    } else {                     // lines (ix,iy), faces ((f*ny+iy)*nx + ix)
+        i0 = (int)(L % a.nx); i1 = (int)(L / a.nx);
+        e0 = (long long)i1 * a.nx + i0; cs = (long long)a.nx * a.ny; s0 = e0; fs = cs;
+    }
+    const double alpha = rt_alpha(a.K), off = rt_off(a.K);
+    // transverse part of f_d and of the boundary-face area
+    double ftr, inv_area, cdim;
+    if (a.dir == 0) { ftr = a.Fb[i0] * a.Fc[i1]; }
+    else if (a.dir == 1) { ftr = a.Fa[i0] * a.Fc[i1]; }
+    else { ftr = a.Fa[i0] * a.Fb[i1]; }
+    if (a.dim == 1) { inv_area = 1.0; cdim = 1.0; }
+    else if (a.dim == 2) { cdim = 2.0; inv_area = 1.0 / ((a.dir == 0) ? a.hy[i0] : a.hx[i0]); }
+    else {
+        cdim = 4.0;
+        if (a.dir == 0) inv_area = 1.0 / (a.hy[i0] * a.hz[i1]);
+        else if (a.dir == 1) inv_area = 1.0 / (a.hx[i0] * a.hz[i1]);
+        else inv_area = 1.0 / (a.hx[i0] * a.hy[i1]);
+    }
+    const double *Fl = (a.dir == 0) ? a.Fa : (a.dir == 1 ? a.Fb : a.Fc);
+    double cprev = 0.0, uprev = 0.0, offprev = 0.0;
+    for (int f = 0; f <= n; ++f) {
+        double c = 0.0, bc = 0.0;
+        if (f < n) {
+            const double Dv = a.D[e0 + f * cs];
+            c = Fl[f] * ftr / Dv;
+            if (f == 0 && a.dir_lo) bc = 2.0 * Dv * cdim * inv_area;
+        }
+        if (f == n && a.dir_hi) bc = 2.0 * a.D[e0 + (long long)(n - 1) * cs] * cdim * inv_area;
+        const double diag = alpha * (cprev + c) + bc;
+        const double m = diag - offprev * uprev;
+        const double mi = 1.0 / m;
+        const double o = off * c;         // coupling f <-> f+1 (0 past the last cell)
+        a.minv[s0 + f * fs] = mi;
+        a.u[s0 + f * fs] = o * mi;
+        uprev = o * mi; offprev = o; cprev = c;
+    }
+}
+
+}  // namespace nf

@@ -1,0 +1,96 @@
+"""
+CPU tests of the oracle: internal identities that pin the restatement in the absence of
+reference golden vectors, and the closed forms the CUDA path relies on.
+"""
+import numpy as np
+import pytest
+import scipy.sparse.linalg as spla
+
+from closed_form_model import schur_apply_model
+from helpers import make_oracle, random_problem, relerr
+from oracle.neutfem_oracle import CG, FESpaceOracle, OracleNeutFEM, SchurSolverOracle
+
+
+def test_dof_counts_match_reference_formulas():
+    # FESpace::ComputeDofCounts (src/FEM.cpp:177-259); sizes quoted in SURVEY 8(a)
+    f = FESpaceOracle(0, 0, np.arange(39.0), np.arange(39.0), np.array([0.0]))
+    assert (f.n_Phi, f.n_J) == (1444, 2964)
+    f = FESpaceOracle(1, 1, np.arange(35.0), np.arange(35.0), np.array([0.0]))
+    assert (f.n_Phi, f.n_J, f.nJ_loc, f.nphi_loc) == (4624, 9384, 12, 4)
+    f = FESpaceOracle(2, 2, np.arange(35.0), np.arange(35.0), np.array([0.0]))
+    assert (f.n_Phi, f.n_J, f.nJ_loc, f.nphi_loc) == (10404, 21012, 24, 9)
+    f = FESpaceOracle(0, 0, np.arange(39.0), np.arange(39.0), np.arange(20.0))
+    assert (f.ne, f.n_J) == (27436, 85196)
+    f = FESpaceOracle(1, 1, np.arange(4.0), np.arange(5.0), np.arange(6.0))
+    assert (f.nJ_loc, f.nphi_loc) == (36, 8)
+
+
+def test_local_matrices_closed_form_1d_principal_block():
+    # 1-D principal mass matrix on [L, R, b0, b1] times (hx/2)/D
+    f = FESpaceOracle(2, 2, np.array([0.0, 0.7]), np.array([0.0]), np.array([0.0]))
+    A, B, C = f.local(0, 1.3, 0.2)
+    M = np.array([[2 / 3, 1 / 3, 2 / 3, -2 / 15], [1 / 3, 2 / 3, 2 / 3, 2 / 15], [2 / 3, 2 / 3, 16 / 15, 0], [-2 / 15, 2 / 15, 0, 16 / 105]])
+    assert np.allclose(A, M * (0.7 / 2) / 1.3, atol=1e-14)
+    Bexp = np.array([[-1, 1, 0, 0], [0, 0, -4 / 3, 0], [0, 0, 0, -4 / 5]])
+    assert np.allclose(B, Bexp, atol=1e-14)
+    assert np.allclose(C, np.diag([0.2 * 0.35 * 2, 0.2 * 0.35 * 2 / 3, 0.2 * 0.35 * 2 / 5]), atol=1e-15)
+
+
+def test_local_matrices_2d_piola_quirk():
+    # 2-D uses factor_x = hy/hx (src/FEM.cpp:803-804), not jac^2/det
+    f = FESpaceOracle(0, 0, np.array([0.0, 2.0]), np.array([0.0, 0.5, 1.0]), np.array([0.0]))   # ny must be > 1 for dim = 2
+    A, B, C = f.local(0, 1.0, 1.0)
+    assert np.isclose(A[0, 0], (0.5 / 2.0) * (2.0 / 3.0) * 2.0)     # f_x * M_LL * w(=2)
+    assert np.isclose(A[2, 2], (2.0 / 0.5) * (2.0 / 3.0) * 2.0)
+    assert np.allclose(np.abs(B), 2.0)
+    assert np.isclose(C[0, 0], 1.0)
+
+
+@pytest.mark.parametrize("dim,n,rt,pp", [(1, (9, 1, 1), 2, 2), (2, (4, 3, 1), 1, 1), (2, (3, 4, 1), 2, 1), (3, (3, 2, 2), 1, 1), (3, (2, 2, 3), 2, 2)])
+def test_implicit_product_equals_explicit_schur(dim, n, rt, pp):
+    p = random_problem(1, dim, n, ng=1, bc="mixed")
+    o = make_oracle(p, rt, pp)
+    A, B, C = o.A[0].toarray(), o.B.toarray(), o.C[0].toarray()
+    assert np.allclose(A, A.T, atol=1e-13)
+    assert np.all(np.linalg.eigvalsh(A) > 0)
+    S = C + B @ np.linalg.solve(A, B.T)
+    assert np.all(np.linalg.eigvalsh(0.5 * (S + S.T)) > 0)
+    x = np.random.default_rng(0).uniform(0.5, 1.5, o.fes.n_Phi)
+    assert relerr(o.schur_product(0, x), S @ x) < 1e-12
+
+
+CF_CASES = [(1, (7, 1, 1), 0, 0), (1, (6, 1, 1), 1, 1), (1, (5, 1, 1), 2, 2), (1, (5, 1, 1), 2, 1), (1, (5, 1, 1), 1, 0),
+            (2, (4, 3, 1), 0, 0), (2, (3, 4, 1), 1, 1), (2, (3, 3, 1), 2, 2), (2, (3, 2, 1), 2, 0), (2, (2, 3, 1), 2, 1),
+            (3, (3, 2, 2), 0, 0), (3, (2, 3, 2), 1, 1), (3, (2, 2, 2), 2, 2), (3, (2, 2, 2), 2, 1), (3, (2, 2, 2), 1, 0)]
+
+
+@pytest.mark.parametrize("dim,n,rt,pp", CF_CASES)
+@pytest.mark.parametrize("bc", ["mixed", "all"])
+def test_closed_form_model_equals_oracle(dim, n, rt, pp, bc):
+    """The closed forms (Appendix A) used by the CUDA kernels reproduce the quadrature-assembled operator."""
+    p = random_problem(7, dim, n, ng=1, bc=bc)
+    o = make_oracle(p, rt, pp)
+    x = np.random.default_rng(3).uniform(0.5, 1.5, o.fes.n_Phi)
+    y_ref = o.schur_product(0, x)
+    f = o.fes
+    y = schur_apply_model(dim, o.rt_order, o.p_order, f.hx, f.hy, f.hz, p["D"], p["SigR"], o._dirichlet_flags(), x)
+    assert relerr(y, y_ref) < 1e-12
+
+
+def test_cg_matches_direct_solve():
+    p = random_problem(2, 2, (16, 15, 1), ng=1, bc="all")
+    o = make_oracle(p, 1, 1)
+    s = SchurSolverOracle()
+    s.solver_type, s.tol, s.max_iter = CG, 1e-12, 5000
+    s.set_matrices(o.A[0], o.B, o.C[0])
+    rhs = np.random.default_rng(0).uniform(size=o.fes.n_Phi)
+    phi = s.solve_implicit(rhs)
+    S = (o.C[0] + o.B @ spla.splu(o.A[0].tocsc()).solve(o.B.T.toarray()))
+    assert relerr(phi, np.linalg.solve(S, rhs)) < 1e-9
+
+
+def test_order_clamp_and_defaults():
+    o = OracleNeutFEM(1, 2, 2, np.arange(4.0), np.array([0.0]), np.array([0.0]))
+    assert (o.rt_order, o.p_order) == (1, 1)            # p forced down to rt (NeutFEM.cpp:149-169)
+    assert np.all(o.D == 1.0) and np.all(o.SigR == 0.01) and np.all(o.Chi[:3] == 1.0) and np.all(o.Chi[3:] == 0.0)
+    assert o.schur.solver_type == 0 and o.schur.tol == 1e-10   # SchurSolver keeps DIRECT_LU until set (solvers.cpp:67-76)
