@@ -23,6 +23,12 @@
 extern "C" {
 #endif
 
+#if defined(__GNUC__)
+#define NF_API __attribute__((visibility("default")))
+#else
+#define NF_API
+#endif
+
 typedef struct nf_ctx nf_ctx;
 
 /* enum values identical to the reference: BCType (NeutFEM.hpp:51-57), LinearSolverType (solvers.hpp:176-190) */
@@ -56,79 +62,79 @@ typedef struct nf_stats {
  * a direction with a single break is absent (dim is inferred the same way, FEM.cpp:28-34).
  * Orders are clamped to <= 2 and p_order is forced down to rt_order (NeutFEM.cpp:119-169). `device` = CUDA
  * ordinal (-1: current device). */
-int nf_create(nf_ctx **out, int rt_order, int p_order, int ng,
+NF_API int nf_create(nf_ctx **out, int rt_order, int p_order, int ng,
               const double *x_breaks, int n_x_breaks,
               const double *y_breaks, int n_y_breaks,
               const double *z_breaks, int n_z_breaks, int device);
-int nf_destroy(nf_ctx *ctx);
-const char *nf_last_error(const nf_ctx *ctx);   /* ctx may be NULL: last error of a failed nf_create */
+NF_API int nf_destroy(nf_ctx *ctx);
+NF_API const char *nf_last_error(const nf_ctx *ctx);   /* ctx may be NULL: last error of a failed nf_create */
 
 /* sizes: out[0..9] = dim, nx, ny, nz, n_phi_loc, n_face_dofs, n_bubble_dofs_per_dir, rt_order, p_order, ng;
  * out64[0..5] = NE, n_Phi, n_J, n_Jx, n_Jy, n_Jz   (FESpace::ComputeDofCounts, src/FEM.cpp:177-259) */
-int nf_get_sizes(const nf_ctx *ctx, int32_t *out, int64_t *out64);
+NF_API int nf_get_sizes(const nf_ctx *ctx, int32_t *out, int64_t *out64);
 
 /* ---- configuration ---------------------------------------------------------------------------------------
  * NeutFEM::SetBC (src/NeutFEM.cpp:337-340); only DIRICHLET changes the operator (ApplyDirichletToA,
  * NeutFEM.cpp:1328-1456) -- the others are stored and ignored exactly like the reference (NeutFEM.cpp:2128-2131). */
-int nf_set_bc(nf_ctx *ctx, int attr, int bc_type, double value);
+NF_API int nf_set_bc(nf_ctx *ctx, int attr, int bc_type, double value);
 /* NeutFEM::SetLinearSolver + SetTolerance (src/NeutFEM.cpp:322-335). */
-int nf_set_solver(nf_ctx *ctx, int solver_type, double tol_keff, double tol_flux, int max_outer, int max_inner,
+NF_API int nf_set_solver(nf_ctx *ctx, int solver_type, double tol_keff, double tol_flux, int max_outer, int max_inner,
                   int mode);
 
 /* ---- operators -------------------------------------------------------------------------------------------
  * Host->device snapshot of the cross-sections (the reference's public Vec members, NeutFEM.hpp:373-379, that
  * python fills through the numpy views). Any pointer may be NULL = keep current/default value. */
-int nf_upload_xs(nf_ctx *ctx, const double *D, const double *SigR, const double *NSF, const double *Chi,
+NF_API int nf_upload_xs(nf_ctx *ctx, const double *D, const double *SigR, const double *NSF, const double *Chi,
                  const double *SigS, const double *SRC);
 /* NeutFEM::BuildMatrices (src/NeutFEM.cpp:402-457): no matrix is formed; builds the per-line factorisations of
  * the RT mass matrix A_g (incl. the Dirichlet diagonal) and invalidates the diagonal cache. */
-int nf_build(nf_ctx *ctx);
+NF_API int nf_build(nf_ctx *ctx);
 /* NeutFEM::BuildDiagonalSchurCache (src/NeutFEM.cpp:483-597), RT0-P0 only. */
-int nf_build_diagonal_cache(nf_ctx *ctx);
+NF_API int nf_build_diagonal_cache(nf_ctx *ctx);
 
 /* ---- state -----------------------------------------------------------------------------------------------
  * Sol_Phi_ / Sol_Phi_adj_ (NeutFEM.hpp:385-388) in reference numbering [ng * n_Phi]. */
-int nf_set_flux(nf_ctx *ctx, const double *phi);
-int nf_get_flux(nf_ctx *ctx, double *phi);
-int nf_get_flux_adjoint(nf_ctx *ctx, double *phi);
-int nf_reset_flux(nf_ctx *ctx);                 /* NeutFEM::ResetFlux (src/NeutFEM.cpp:347-354) */
+NF_API int nf_set_flux(nf_ctx *ctx, const double *phi);
+NF_API int nf_get_flux(nf_ctx *ctx, double *phi);
+NF_API int nf_get_flux_adjoint(nf_ctx *ctx, double *phi);
+NF_API int nf_reset_flux(nf_ctx *ctx);                 /* NeutFEM::ResetFlux (src/NeutFEM.cpp:347-354) */
 /* J = -A_g^-1 B^T phi_g for all groups in reference numbering [ng * n_J] (solvers.cpp:227-228); the reference
  * binds no accessor for it. adjoint != 0 uses the adjoint flux. */
-int nf_get_current(nf_ctx *ctx, double *J, int adjoint);
+NF_API int nf_get_current(nf_ctx *ctx, double *J, int adjoint);
 
 /* ---- solves ----------------------------------------------------------------------------------------------
  * NeutFEM::SolveKeff(use_coarse_init=false, {}, use_diagonal_solver, use_cmfd=false) (src/NeutFEM.cpp:1627-1815);
  * the coarse-mesh initial guess is composed by the host class out of a second context. keff_init <= 0 means
  * "1.0 or the last k" like the reference (NeutFEM.cpp:1662). */
-int nf_solve_keff(nf_ctx *ctx, int use_diagonal_solver, int accel, double keff_init, double *keff, nf_stats *stats);
+NF_API int nf_solve_keff(nf_ctx *ctx, int use_diagonal_solver, int accel, double keff_init, double *keff, nf_stats *stats);
 /* NeutFEM::SolveAdjoint (src/NeutFEM.cpp:1877-2082). */
-int nf_solve_adjoint(nf_ctx *ctx, int normalize_to_direct, int use_direct_keff, double *keff_adj, nf_stats *stats);
+NF_API int nf_solve_adjoint(nf_ctx *ctx, int normalize_to_direct, int use_direct_keff, double *keff_adj, nf_stats *stats);
 /* Fixed-source problem (L - F/k) phi = Q with the stored SRC and k = last k-eff: named by the reference surface
  * (SolveSubcritical, include/NeutFEM.hpp:279, src/wrapper.cpp:699-715) but has no body there. Parity unpinned. */
-int nf_solve_source(nf_ctx *ctx, double *amplification, nf_stats *stats);
-int nf_get_last_keff(const nf_ctx *ctx, double *keff, double *keff_adj, int *has_valid);
+NF_API int nf_solve_source(nf_ctx *ctx, double *amplification, nf_stats *stats);
+NF_API int nf_get_last_keff(const nf_ctx *ctx, double *keff, double *keff_adj, int *has_valid);
 
 /* ---- operator-level test hooks (SchurSolver, src/solvers.cpp:535-636, 227-228) -----------------------------
  * y = (C_g + B A_g^-1 B^T) x        x,y: [n_Phi] reference numbering */
-int nf_schur_apply(nf_ctx *ctx, int g, const double *x, double *y);
+NF_API int nf_schur_apply(nf_ctx *ctx, int g, const double *x, double *y);
 /* S_g phi = rhs by the configured inner solver; iterations/residual returned */
-int nf_schur_solve(nf_ctx *ctx, int g, const double *rhs, double *phi, int *iterations, double *residual);
+NF_API int nf_schur_solve(nf_ctx *ctx, int g, const double *rhs, double *phi, int *iterations, double *residual);
 /* J = -A_g^-1 B^T phi for one group, [n_J] reference numbering */
-int nf_current_from_flux(nf_ctx *ctx, int g, const double *phi, double *J);
+NF_API int nf_current_from_flux(nf_ctx *ctx, int g, const double *phi, double *J);
 /* 1/S_ee of the diagonal RT0-P0 path for group g, [NE] */
-int nf_get_diagonal_cache(nf_ctx *ctx, int g, double *s_inv);
+NF_API int nf_get_diagonal_cache(nf_ctx *ctx, int g, double *s_inv);
 
 /* ---- multi-GPU (z-slabs, one process per GPU) -------------------------------------------------------------
  * The reference is single-process; these have no counterpart there. nf_comm_unique_id fills a 128-byte NCCL id
  * on the caller (rank 0), the host distributes it (torch.distributed / MPI / files), every rank then calls
  * nf_create_slab + nf_comm_init. See DESIGN.md "z-slabs". */
-int nf_comm_unique_id(char id[128]);
-int nf_comm_init(nf_ctx *ctx, const char id[128], int rank, int nranks);
+NF_API int nf_comm_unique_id(char id[128]);
+NF_API int nf_comm_init(nf_ctx *ctx, const char id[128], int rank, int nranks);
 
 /* library info: out[0]=ABI version, out[1]=CUDA runtime version, out[2]=compiled sm arch (100) */
-int nf_version(int32_t out[3]);
+NF_API int nf_version(int32_t out[3]);
 /* number of kernels this library has launched in the process so far (bench.py's gpu_launches) */
-int64_t nf_kernel_launch_count(void);
+NF_API int64_t nf_kernel_launch_count(void);
 
 #ifdef __cplusplus
 }

@@ -165,15 +165,18 @@ static int launch_sweeps_t(nf_ctx *c, int g, const double *x, double *y, bool us
         a.Lc = Lc;
         const int RL = 32 * Lc;
         const size_t per_warp = (size_t)(3 + M1) * RL * sizeof(double);
-        int WPB = 4;
-        while (WPB > 1 && per_warp * WPB > c->smem_optin) WPB >>= 1;
-        if (per_warp * WPB > c->smem_optin) NF_FAIL(c, NF_ERR_ARG, "nx=%d too large for the shared-memory line solver", c->nx);
-        const size_t smem = per_warp * WPB;
-        static size_t configured = 0;
-        if (smem > configured) {
-            CU(c, cudaFuncSetAttribute(k_sweep_x<K, M1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
-            configured = c->smem_optin;
+        static size_t maxdyn = 0;          // opt-in dynamic shared memory of this instantiation (static part excluded)
+        if (maxdyn == 0) {
+            cudaFuncAttributes fa;
+            CU(c, cudaFuncGetAttributes(&fa, k_sweep_x<K, M1>));
+            const size_t lim = c->smem_optin - fa.sharedSizeBytes - 1024;
+            CU(c, cudaFuncSetAttribute(k_sweep_x<K, M1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lim));
+            maxdyn = lim;
         }
+        int WPB = 4;
+        while (WPB > 1 && per_warp * WPB > maxdyn / 2) WPB >>= 1;      // keep two CTAs per SM when possible
+        if (per_warp * WPB > maxdyn) NF_FAIL(c, NF_ERR_ARG, "nx=%d too large for the shared-memory line solver", c->nx);
+        const size_t smem = per_warp * WPB;
         const long long nlines = (long long)c->ny * c->nz;
         const int grid = (int)std::max<long long>(1, std::min<long long>(kRedBlocks, (nlines + WPB - 1) / WPB));
         LAUNCH(c, (k_sweep_x<K, M1>), grid, WPB * 32, smem, a);
