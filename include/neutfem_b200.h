@@ -124,6 +124,11 @@ NF_API int nf_current_from_flux(nf_ctx *ctx, int g, const double *phi, double *J
 /* 1/S_ee of the diagonal RT0-P0 path for group g, [NE] */
 NF_API int nf_get_diagonal_cache(nf_ctx *ctx, int g, double *s_inv);
 
+/* Average device time (ms) per launch of the hot-path kernels, CUDA events on the library's stream:
+ * ms_out[0..2] x/y/z sweep, [3] CG update, [4] CG direction update, [5] one full CG iteration. fast != 0 times
+ * the Jacobi-PCG variants. Measurement hook for bench.py's roofline; no reference counterpart. */
+NF_API int nf_time_kernels(nf_ctx *ctx, int g, int reps, int fast, double *ms_out);
+
 /* ---- multi-GPU (z-slabs, one process per GPU) -------------------------------------------------------------
  * The reference is single-process; these have no counterpart there. nf_comm_unique_id fills a 128-byte NCCL id
  * on the caller (rank 0), the host distributes it (torch.distributed / MPI / files), every rank then calls

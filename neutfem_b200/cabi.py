@@ -27,7 +27,7 @@ EXPORTED = [
     "nf_build", "nf_build_diagonal_cache", "nf_set_flux", "nf_get_flux", "nf_get_flux_adjoint", "nf_reset_flux",
     "nf_get_current", "nf_solve_keff", "nf_solve_adjoint", "nf_solve_source", "nf_get_last_keff", "nf_schur_apply",
     "nf_schur_solve", "nf_current_from_flux", "nf_get_diagonal_cache", "nf_comm_unique_id", "nf_comm_init",
-    "nf_version", "nf_kernel_launch_count",
+    "nf_version", "nf_kernel_launch_count", "nf_time_kernels",
 ]
 
 
@@ -84,6 +84,7 @@ def load():
     L.nf_get_diagonal_cache.argtypes = [vp, ctypes.c_int, dp]
     L.nf_comm_unique_id.argtypes = [ctypes.c_char_p]
     L.nf_comm_init.argtypes = [vp, ctypes.c_char_p, ctypes.c_int, ctypes.c_int]
+    L.nf_time_kernels.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, dp]
     L.nf_version.argtypes = [ctypes.POINTER(ctypes.c_int32)]
     L.nf_kernel_launch_count.restype = ctypes.c_int64
     _lib = L
@@ -218,6 +219,11 @@ class Context:
         J = np.empty(self.n_J)
         self._ck(self._L.nf_current_from_flux(self._h, int(g), _dp(a), _dp(J)), "nf_current_from_flux")
         return J
+
+    def time_kernels(self, g=0, reps=5, fast=False):
+        out = np.zeros(8)
+        self._ck(self._L.nf_time_kernels(self._h, int(g), int(reps), int(fast), _dp(out)), "nf_time_kernels")
+        return dict(sweep_x=out[0], sweep_y=out[1], sweep_z=out[2], cg_update=out[3], cg_pupdate=out[4], cg_iteration=out[5])
 
     def diagonal_cache(self, g):
         out = np.empty(self.ne)

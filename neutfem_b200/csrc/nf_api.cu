@@ -155,10 +155,10 @@ static void fill_sweep_args(nf_ctx *c, SweepArgs &a, int g, int d, const double 
 }
 
 template <int K, int M1>
-static int launch_sweeps_t(nf_ctx *c, int g, const double *x, double *y, bool use_cg)
+static int launch_sweeps_t(nf_ctx *c, int g, const double *x, double *y, bool use_cg, int pass_mask)
 {
     SweepArgs a;
-    {   // x pass
+    if (pass_mask & 1) {   // x pass
         fill_sweep_args(c, a, g, 0, x, y, use_cg);
         int Lc = (c->nx + 1 + 31) / 32;
         Lc |= 1;
@@ -182,6 +182,7 @@ static int launch_sweeps_t(nf_ctx *c, int g, const double *x, double *y, bool us
         LAUNCH(c, (k_sweep_x<K, M1>), grid, WPB * 32, smem, a);
     }
     for (int d = 1; d < c->dim; ++d) {
+        if (!(pass_mask & (1 << d))) continue;
         fill_sweep_args(c, a, g, d, x, y, use_cg);
         MarchGeom mg;
         if (d == 1) {
@@ -221,15 +222,15 @@ static int launch_sweeps_t(nf_ctx *c, int g, const double *x, double *y, bool us
 }
 
 // y = S_g x (SoA). use_cg: accumulate p.Ap into the CG state and honour its done flag.
-static int apply_schur(nf_ctx *c, int g, const double *x, double *y, bool use_cg)
+static int apply_schur(nf_ctx *c, int g, const double *x, double *y, bool use_cg, int pass_mask = 7)
 {
     switch (c->K * 4 + c->M1) {
-    case 0 * 4 + 1: return launch_sweeps_t<0, 1>(c, g, x, y, use_cg);
-    case 1 * 4 + 1: return launch_sweeps_t<1, 1>(c, g, x, y, use_cg);
-    case 1 * 4 + 2: return launch_sweeps_t<1, 2>(c, g, x, y, use_cg);
-    case 2 * 4 + 1: return launch_sweeps_t<2, 1>(c, g, x, y, use_cg);
-    case 2 * 4 + 2: return launch_sweeps_t<2, 2>(c, g, x, y, use_cg);
-    case 2 * 4 + 3: return launch_sweeps_t<2, 3>(c, g, x, y, use_cg);
+    case 0 * 4 + 1: return launch_sweeps_t<0, 1>(c, g, x, y, use_cg, pass_mask);
+    case 1 * 4 + 1: return launch_sweeps_t<1, 1>(c, g, x, y, use_cg, pass_mask);
+    case 1 * 4 + 2: return launch_sweeps_t<1, 2>(c, g, x, y, use_cg, pass_mask);
+    case 2 * 4 + 1: return launch_sweeps_t<2, 1>(c, g, x, y, use_cg, pass_mask);
+    case 2 * 4 + 2: return launch_sweeps_t<2, 2>(c, g, x, y, use_cg, pass_mask);
+    case 2 * 4 + 3: return launch_sweeps_t<2, 3>(c, g, x, y, use_cg, pass_mask);
     }
     NF_FAIL(c, NF_ERR_STATE, "unsupported order RT%d-P%d", c->K, c->M);
 }
@@ -321,7 +322,7 @@ int nf_create(nf_ctx **out, int rt_order, int p_order, int ng, const double *xb,
     CK(dalloc(c, &c->d_vol, ne));
     CK(dalloc(c, &c->d_D, G * ne)); CK(dalloc(c, &c->d_SigR, G * ne)); CK(dalloc(c, &c->d_NSF, G * ne));
     CK(dalloc(c, &c->d_Chi, G * ne)); CK(dalloc(c, &c->d_SRC, G * ne)); CK(dalloc(c, &c->d_SigS, G * G * ne));
-    CK(dalloc(c, &c->d_phi, G * np)); CK(dalloc(c, &c->d_phi_adj, G * np)); CK(dalloc(c, &c->d_old, G * np));
+    CK(dalloc(c, &c->d_phi, G * np)); CK(dalloc(c, &c->d_old, G * np));
     CK(dalloc(c, &c->d_h0, G * np)); CK(dalloc(c, &c->d_h1, G * np)); CK(dalloc(c, &c->d_tmp, G * np));
     CK(dalloc(c, &c->d_tot, np)); CK(dalloc(c, &c->d_rhs, np)); CK(dalloc(c, &c->d_r, np));
     CK(dalloc(c, &c->d_p, np)); CK(dalloc(c, &c->d_Ap, np));
@@ -382,8 +383,7 @@ int nf_create(nf_ctx **out, int rt_order, int p_order, int ng, const double *xb,
         CKU(cudaMemset(c->d_SigS, 0, G * G * ne * sizeof(double)));
     }
     k_fill<<<ew_blocks(G * np), 256, 0, c->stream>>>(c->d_phi, (long long)(G * np), 1.0);
-    k_fill<<<ew_blocks(G * np), 256, 0, c->stream>>>(c->d_phi_adj, (long long)(G * np), 1.0);
-    g_launches += 2;
+    g_launches += 1;
     CKU(cudaStreamSynchronize(c->stream));
 #undef CK
 #undef CKU
@@ -548,6 +548,16 @@ static int set_flux_impl(nf_ctx *c, double *dst, const double *phi)
     return NF_OK;
 }
 
+static int ensure_adjoint(nf_ctx *c)
+{
+    if (c->d_phi_adj) return NF_OK;
+    const long long n = (long long)c->ng * c->nphi;
+    int r = dalloc(c, &c->d_phi_adj, (size_t)n);
+    if (r) return r;
+    LAUNCH(c, k_fill, ew_blocks(n), 256, 0, c->d_phi_adj, n, 1.0);
+    return NF_OK;
+}
+
 static int get_flux_impl(nf_ctx *c, const double *src, double *phi)
 {
     CU(c, cudaSetDevice(c->dev));
@@ -560,7 +570,13 @@ static int get_flux_impl(nf_ctx *c, const double *src, double *phi)
 
 int nf_set_flux(nf_ctx *c, const double *phi) { if (!c || !phi) return NF_ERR_ARG; return set_flux_impl(c, c->d_phi, phi); }
 int nf_get_flux(nf_ctx *c, double *phi) { if (!c || !phi) return NF_ERR_ARG; return get_flux_impl(c, c->d_phi, phi); }
-int nf_get_flux_adjoint(nf_ctx *c, double *phi) { if (!c || !phi) return NF_ERR_ARG; return get_flux_impl(c, c->d_phi_adj, phi); }
+int nf_get_flux_adjoint(nf_ctx *c, double *phi)
+{
+    if (!c || !phi) return NF_ERR_ARG;
+    CU(c, cudaSetDevice(c->dev));
+    { int r = ensure_adjoint(c); if (r) return r; }
+    return get_flux_impl(c, c->d_phi_adj, phi);
+}
 
 int nf_reset_flux(nf_ctx *c)
 {
@@ -568,7 +584,7 @@ int nf_reset_flux(nf_ctx *c)
     CU(c, cudaSetDevice(c->dev));
     const long long n = (long long)c->ng * c->nphi;
     LAUNCH(c, k_fill, ew_blocks(n), 256, 0, c->d_phi, n, 1.0);
-    LAUNCH(c, k_fill, ew_blocks(n), 256, 0, c->d_phi_adj, n, 1.0);
+    if (c->d_phi_adj) LAUNCH(c, k_fill, ew_blocks(n), 256, 0, c->d_phi_adj, n, 1.0);
     CU(c, cudaStreamSynchronize(c->stream));
     c->has_valid = false;
     return NF_OK;
@@ -759,6 +775,7 @@ int nf_solve_adjoint(nf_ctx *c, int normalize_to_direct, int use_direct_keff, do
     nf_stats st;
     memset(&st, 0, sizeof(st));
     c->launches_call = 0;
+    { int r = ensure_adjoint(c); if (r) return r; }
     CU(c, cudaEventRecord(c->ev0, c->stream));
     double k = 1.0;
     const bool fixed = use_direct_keff && c->has_valid;
@@ -917,6 +934,7 @@ int nf_get_current(nf_ctx *c, double *J, int adjoint)
     if (!c->built) NF_FAIL(c, NF_ERR_STATE, "nf_get_current: call nf_build first");
     CU(c, cudaSetDevice(c->dev));
     if (!c->d_J) { int r = dalloc(c, &c->d_J, (size_t)c->nJ); if (r) return r; }
+    if (adjoint) { int r = ensure_adjoint(c); if (r) return r; }
     const double *phi = adjoint ? c->d_phi_adj : c->d_phi;
     for (int g = 0; g < c->ng; ++g) {
         int r = current_group(c, g, phi + (size_t)g * c->nphi, c->d_J);
@@ -933,6 +951,49 @@ int nf_get_diagonal_cache(nf_ctx *c, int g, double *s_inv)
     if (!c->diag_valid) NF_FAIL(c, NF_ERR_STATE, "nf_get_diagonal_cache: cache not built");
     CU(c, cudaSetDevice(c->dev));
     CU(c, cudaMemcpy(s_inv, c->d_sinv + (size_t)g * c->ne, (size_t)c->ne * sizeof(double), cudaMemcpyDeviceToHost));
+    return NF_OK;
+}
+
+int nf_time_kernels(nf_ctx *c, int g, int reps, int fast, double *ms_out)
+{
+    // Average device time per launch of each hot-path kernel, CUDA events on the context stream, operands resident
+    // in HBM. ms_out[0..2] = x / y / z sweep, [3] = CG update, [4] = CG direction update, [5] = one full CG
+    // iteration (the five launches back to back). Destroys the CG work vectors, not the flux.
+    if (!c || !ms_out || g < 0 || g >= c->ng || reps < 1) return NF_ERR_ARG;
+    if (!c->built) NF_FAIL(c, NF_ERR_STATE, "nf_time_kernels: call nf_build first");
+    CU(c, cudaSetDevice(c->dev));
+    const long long n = c->nphi;
+    const int blocks = ew_blocks(n);
+    if (fast) { int r = build_jacobi(c); if (r) return r; }
+    const double *jac = fast ? c->d_jac + (size_t)g * c->nphi : nullptr;
+    LAUNCH(c, k_fill, blocks, 256, 0, c->d_rhs, n, 1.0);
+    LAUNCH(c, k_cg_init, blocks, 256, 0, c->d_rhs, c->d_tot, c->d_r, c->d_p, n, 0.0, c->d_cg, c->d_part + 4 * kRedBlocks, c->d_ticket + 4);
+    for (int i = 0; i < 8; ++i) ms_out[i] = 0.0;
+    auto iteration = [&](int mask, bool upd, bool pupd) -> int {
+        if (mask) { int r = apply_schur(c, g, c->d_p, c->d_Ap, true, mask); if (r) return r; }
+        if (upd) {
+            if (!fast) LAUNCH(c, k_cg_update, blocks, 256, 0, c->d_p, c->d_Ap, c->d_tot, c->d_r, n, c->d_cg, c->d_part + 4 * kRedBlocks, c->d_ticket + 4);
+            else LAUNCH(c, k_pcg_update, blocks, 256, 0, c->d_p, c->d_Ap, jac, c->d_tot, c->d_r, n, c->d_cg, c->d_part + 4 * kRedBlocks, c->d_ticket + 4);
+        }
+        if (pupd) {
+            if (!fast) LAUNCH(c, k_cg_pupdate, blocks, 256, 0, c->d_r, c->d_p, n, c->d_cg);
+            else LAUNCH(c, k_pcg_pupdate, blocks, 256, 0, c->d_r, jac, c->d_p, n, c->d_cg);
+        }
+        return NF_OK;
+    };
+    { int r = iteration(7, true, true); if (r) return r; }    // warm-up, also makes p.Ap non-zero
+    struct { int mask; bool upd, pupd; } what[6] = {{1, false, false}, {2, false, false}, {4, false, false},
+                                                    {0, true, false}, {0, false, true}, {7, true, true}};
+    for (int w = 0; w < 6; ++w) {
+        if (what[w].mask && what[w].mask != 7 && !(what[w].mask < (1 << c->dim))) continue;
+        CU(c, cudaEventRecord(c->ev2, c->stream));
+        for (int i = 0; i < reps; ++i) { int r = iteration(what[w].mask, what[w].upd, what[w].pupd); if (r) return r; }
+        CU(c, cudaEventRecord(c->ev3, c->stream));
+        CU(c, cudaEventSynchronize(c->ev3));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, c->ev2, c->ev3);
+        ms_out[w] = ms / reps;
+    }
     return NF_OK;
 }
 
