@@ -14,7 +14,7 @@ import os
 import numpy as np
 
 _LIBDIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib")
-LIB_PATH = os.path.join(_LIBDIR, "libneutfem_b200.so")
+LIB_PATH = os.environ.get("NF_LIB", os.path.join(_LIBDIR, "libneutfem_b200.so"))   # NF_LIB: development A/B builds
 
 # enums (include/neutfem_b200.h)
 BC_DIRICHLET, BC_NEUMANN, BC_MIRROR, BC_ROBIN, BC_PERIODIC = range(5)

@@ -30,6 +30,7 @@ struct nf_ctx {
     std::vector<double> hx, hy, hz;
     double *d_hx = nullptr, *d_hy = nullptr, *d_hz = nullptr, *d_vol = nullptr;
     double *d_F[3][3] = {{nullptr}};       // [dir][axis]
+    double *d_iFx[3] = {nullptr, nullptr, nullptr};   // 1/F[dir][x axis]
     double *d_D = nullptr, *d_SigR = nullptr, *d_NSF = nullptr, *d_Chi = nullptr, *d_SigS = nullptr, *d_SRC = nullptr;
     std::vector<double *> d_minv, d_u;     // [g*3 + d]
     long long nfaces[3] = {0, 0, 0};
@@ -138,7 +139,7 @@ static void fill_sweep_args(nf_ctx *c, SweepArgs &a, int g, int d, const double 
     a.x = x; a.y = y;
     a.minv = c->d_minv[g * 3 + d]; a.u = c->d_u[g * 3 + d];
     a.D = c->d_D + (size_t)g * c->ne; a.SigR = c->d_SigR + (size_t)g * c->ne; a.vol = c->d_vol;
-    for (int dd = 0; dd < 3; ++dd) { a.Fx[dd] = c->d_F[dd][0]; a.Fy[dd] = c->d_F[dd][1]; a.Fz[dd] = c->d_F[dd][2]; }
+    for (int dd = 0; dd < 3; ++dd) { a.Fx[dd] = c->d_F[dd][0]; a.Fy[dd] = c->d_F[dd][1]; a.Fz[dd] = c->d_F[dd][2]; a.iFx[dd] = c->d_iFx[dd]; }
     a.zscratch = c->d_zscratch;
     a.red_part = c->d_part + (size_t)d * kRedBlocks;
     a.ticket = c->d_ticket + d;
@@ -164,7 +165,7 @@ static int launch_sweeps_t(nf_ctx *c, int g, const double *x, double *y, bool us
         Lc |= 1;
         a.Lc = Lc;
         const int RL = 32 * Lc;
-        const size_t per_warp = (size_t)(3 + M1) * RL * sizeof(double);
+        const size_t per_warp = ((size_t)(3 + M1) * RL + 2) * sizeof(double);
         static size_t maxdyn = 0;          // opt-in dynamic shared memory of this instantiation (static part excluded)
         if (maxdyn == 0) {
             cudaFuncAttributes fa;
@@ -359,6 +360,12 @@ int nf_create(nf_ctx **out, int rt_order, int p_order, int ng, const double *xb,
                 CK(dalloc(c, &c->d_F[d][ax], F[d][ax].size()));
                 CKU(cudaMemcpy(c->d_F[d][ax], F[d][ax].data(), F[d][ax].size() * sizeof(double), cudaMemcpyHostToDevice));
             }
+        for (int d = 0; d < 3; ++d) {
+            std::vector<double> inv(F[d][0].size());
+            for (size_t i = 0; i < inv.size(); ++i) inv[i] = 1.0 / F[d][0][i];
+            CK(dalloc(c, &c->d_iFx[d], inv.size()));
+            CKU(cudaMemcpy(c->d_iFx[d], inv.data(), inv.size() * sizeof(double), cudaMemcpyHostToDevice));
+        }
         std::vector<double> vol(ne);
         for (int iz = 0; iz < c->nz; ++iz)
             for (int iy = 0; iy < c->ny; ++iy)
@@ -401,6 +408,7 @@ int nf_destroy(nf_ctx *c)
                       c->d_p, c->d_Ap, c->d_tmp, c->d_zscratch, c->d_J, c->d_part, c->d_scal};
     for (double *p : ptrs) if (p) cudaFree(p);
     for (int d = 0; d < 3; ++d) for (int ax = 0; ax < 3; ++ax) if (c->d_F[d][ax]) cudaFree(c->d_F[d][ax]);
+    for (int d = 0; d < 3; ++d) if (c->d_iFx[d]) cudaFree(c->d_iFx[d]);
     for (double *p : c->d_minv) if (p) cudaFree(p);
     for (double *p : c->d_u) if (p) cudaFree(p);
     if (c->d_cg) cudaFree(c->d_cg);

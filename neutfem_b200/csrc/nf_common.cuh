@@ -32,6 +32,7 @@ struct SweepArgs {
     const double *SigR;   // SigR_g[e]   (x pass only)
     const double *vol;    // cell volumes
     const double *Fx[3], *Fy[3], *Fz[3];   // 1-D factors of f_d(e) = Fx[d][ix]*Fy[d][iy]*Fz[d][iz]
+    const double *iFx[3];                  // 1/Fx[d][ix]
     double *zscratch;     // forward-sweep intermediates for long strided lines
     double *red_part;     // [kRedBlocks] partial sums of this pass
     unsigned *ticket;

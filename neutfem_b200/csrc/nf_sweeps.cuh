@@ -37,8 +37,9 @@ __global__ void __launch_bounds__(128) k_sweep_x(const SweepArgs a)
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, WPB = blockDim.x >> 5;
     const int n = a.nx, Lc = a.Lc, RL = 32 * Lc;
     constexpr int NROW = 3 + M1;
-    double *MINV = sm + (size_t)wib * NROW * RL;
-    double *U = MINV + RL, *T = U + RL, *Y = T + RL;
+    // rows per warp: MINV[RL], UB[RL+1] (UB[1+f] = u_f, UB[0] = 0), T[RL], Y[M1][RL]; one pad double per warp
+    double *MINV = sm + (size_t)wib * (NROW * RL + 2);
+    double *UB = MINV + RL, *T = UB + RL + 2, *Y = T + RL;
     const long long nlines = (long long)a.ny * a.nz;
     double acc = 0.0;
 
@@ -48,123 +49,127 @@ __global__ void __launch_bounds__(128) k_sweep_x(const SweepArgs a)
         {
             const double *gm = a.minv + line * (n + 1), *gu = a.u + line * (n + 1);
             for (int f = lane; f < RL; f += 32) {
-                MINV[f] = (f <= n) ? gm[f] : 0.0;
-                U[f] = (f < n) ? gu[f] : 0.0;
+                MINV[f] = (f <= n) ? __ldg(gm + f) : 0.0;
+                UB[1 + f] = (f < n) ? __ldg(gu + f) : 0.0;
             }
+            if (lane == 0) UB[0] = 0.0;
         }
-      for (int t = 0; t < a.nt; ++t) {
-        double fyz[3] = {0.0, 0.0, 0.0};
-        for (int d = 0; d < a.dim; ++d) fyz[d] = a.Fy[d][iy] * a.Fz[d][iz];
-        const double w = a.w[t];
-        int md[3];
+        // reciprocal transverse parts of f_d for this line (unused directions carry cb = 0)
+        const double ify0 = 1.0 / (a.Fy[0][iy] * a.Fz[0][iz]);
+        const double ify1 = 1.0 / (a.Fy[1][iy] * a.Fz[1][iz]);
+        const double ify2 = 1.0 / (a.Fy[2][iy] * a.Fz[2][iz]);
+        for (int t = 0; t < a.nt; ++t) {
+            const double w = a.w[t];
+            int md[3];
+            double wc[3], c0[3], c1[3], c2[3];
 #pragma unroll
-        for (int p = 0; p < M1; ++p) md[p] = a.mode[t][p];
-
-        // ---- P1: load the line, form diag*x and the condensed face rhs
-        double cx0 = 0.0, ctb0 = 0.0, ctb1 = 0.0;   // values of cell f-1 carried across 32-blocks
-        for (int fb = 0; fb < RL; fb += 32) {
-            const int f = fb + lane;
-            const bool cell = f < n;
-            const long long e = line * n + f;
-            double xv[3] = {0.0, 0.0, 0.0};
-            if (cell) {
-                const double Dv = a.D[e], Sv = a.SigR[e] * a.vol[e];
-                double q[3];
-                for (int d = 0; d < a.dim; ++d) q[d] = Dv / (a.Fx[d][f] * fyz[d]);
-#pragma unroll
-                for (int p = 0; p < M1; ++p) {
-                    xv[p] = a.x[(size_t)md[p] * a.ne + e];
-                    double dg = Sv * a.wC[md[p]];
-                    for (int d = 0; d < a.dim; ++d) dg += q[d] * a.cb[d][md[p]];
-                    const double yv = dg * xv[p];
-                    Y[p * RL + f] = yv;
-                    acc += yv * xv[p];
-                }
+            for (int p = 0; p < M1; ++p) {
+                md[p] = a.mode[t][p];
+                wc[p] = a.wC[md[p]]; c0[p] = a.cb[0][md[p]] * ify0; c1[p] = a.cb[1][md[p]] * ify1; c2[p] = a.cb[2][md[p]] * ify2;
             }
-            const double tb0 = (K >= 1 && M1 >= 2) ? -(4.0 / 3.0) * xv[1] : 0.0;
-            const double tb1 = (K >= 2 && M1 >= 3) ? -(4.0 / 5.0) * xv[2] : 0.0;
-            double x0m = __shfl_up_sync(0xffffffffu, xv[0], 1);
-            double tb0m = __shfl_up_sync(0xffffffffu, tb0, 1);
-            double tb1m = __shfl_up_sync(0xffffffffu, tb1, 1);
-            if (lane == 0) { x0m = cx0; tb0m = ctb0; tb1m = ctb1; }
-            T[f] = (f <= n) ? face_rhs<K, M1>(x0m, tb0m, tb1m, xv[0], tb0, tb1) : 0.0;
-            cx0 = __shfl_sync(0xffffffffu, xv[0], 31);
-            ctb0 = __shfl_sync(0xffffffffu, tb0, 31);
-            ctb1 = __shfl_sync(0xffffffffu, tb1, 31);
-        }
-        __syncwarp();
-
-        // ---- P2: forward substitution z_f = T_f - u_{f-1} z_{f-1}, chunk per lane + affine scan
-        const int f0 = lane * Lc;
-        {
-            double z = 0.0, A = 1.0;
-            for (int j = 0; j < Lc; ++j) {
-                const int f = f0 + j;
-                const double um = (f > 0) ? U[f - 1] : 0.0;
-                z = T[f] - um * z;
-                A *= -um;
-            }
-#pragma unroll
-            for (int s = 1; s < 32; s <<= 1) {
-                const double Ap = __shfl_up_sync(0xffffffffu, A, s), zp = __shfl_up_sync(0xffffffffu, z, s);
-                if (lane >= s) { z = A * zp + z; A = A * Ap; }
-            }
-            double carry = __shfl_up_sync(0xffffffffu, z, 1);
-            if (lane == 0) carry = 0.0;
-            z = carry;
-            double q = 0.0;
-            for (int j = 0; j < Lc; ++j) {
-                const int f = f0 + j;
-                const double um = (f > 0) ? U[f - 1] : 0.0;
-                z = T[f] - um * z;
-                T[f] = z;
-                q += z * z * MINV[f];
-            }
-            acc += w * q;
-        }
-        // ---- P3: backward substitution J_f = z_f/m_f - u_f J_{f+1}
-        {
-            double J = 0.0, Bp = 1.0;
-            for (int j = Lc - 1; j >= 0; --j) {
-                const int f = f0 + j;
-                const double uf = U[f];
-                J = MINV[f] * T[f] - uf * J;
-                Bp *= -uf;
-            }
-#pragma unroll
-            for (int s = 1; s < 32; s <<= 1) {
-                const double Bq = __shfl_down_sync(0xffffffffu, Bp, s), Jq = __shfl_down_sync(0xffffffffu, J, s);
-                if (lane + s < 32) { J = Bp * Jq + J; Bp = Bp * Bq; }
-            }
-            double carry = __shfl_down_sync(0xffffffffu, J, 1);
-            if (lane == 31) carry = 0.0;
-            J = carry;
-            for (int j = Lc - 1; j >= 0; --j) {
-                const int f = f0 + j;
-                J = MINV[f] * T[f] - U[f] * J;
-                T[f] = J;
-            }
-        }
-        __syncwarp();
-        // ---- P4: y = diag*x + w * B J
-        for (int fb = 0; fb < n; fb += 32) {
-            const int f = fb + lane;
-            if (f < n) {
+            // ---- P1: load the line, form diag*x and the condensed face rhs
+            double cx0 = 0.0, ctb0 = 0.0, ctb1 = 0.0;   // values of cell f-1 carried across 32-blocks
+            for (int fb = 0; fb < RL; fb += 32) {
+                const int f = fb + lane;
+                const bool cell = f < n;
                 const long long e = line * n + f;
-                const double JL = T[f], JR = T[f + 1];
-                double out[3];
-                out[0] = Y[f] + w * (JR - JL);
-                if (M1 >= 2) out[1] = Y[RL + f] + ((K >= 1) ? w * (5.0 / 6.0) * (JL + JR) : 0.0);
-                if (M1 >= 3) out[2] = Y[2 * RL + f] + ((K >= 2) ? w * (7.0 / 10.0) * (JR - JL) : 0.0);
+                double xv[3] = {0.0, 0.0, 0.0};
+                if (cell) {
+                    const double Dv = __ldg(a.D + e), Sv = __ldg(a.SigR + e) * __ldg(a.vol + e);
+                    const double q0 = Dv * __ldg(a.iFx[0] + f), q1 = Dv * __ldg(a.iFx[1] + f), q2 = Dv * __ldg(a.iFx[2] + f);
 #pragma unroll
-                for (int p = 0; p < M1; ++p) {
-                    double *yp = a.y + (size_t)md[p] * a.ne + e;
-                    *yp = a.first ? out[p] : (*yp + out[p]);
+                    for (int p = 0; p < M1; ++p) {
+                        xv[p] = __ldg(a.x + (size_t)md[p] * a.ne + e);
+                        const double dg = Sv * wc[p] + q0 * c0[p] + q1 * c1[p] + q2 * c2[p];
+                        const double yv = dg * xv[p];
+                        Y[p * RL + f] = yv;
+                        acc += yv * xv[p];
+                    }
+                }
+                const double tb0 = (K >= 1 && M1 >= 2) ? -(4.0 / 3.0) * xv[1] : 0.0;
+                const double tb1 = (K >= 2 && M1 >= 3) ? -(4.0 / 5.0) * xv[2] : 0.0;
+                double x0m = __shfl_up_sync(0xffffffffu, xv[0], 1);
+                double tb0m = 0.0, tb1m = 0.0;
+                if (K >= 1 && M1 >= 2) tb0m = __shfl_up_sync(0xffffffffu, tb0, 1);
+                if (K >= 2 && M1 >= 3) tb1m = __shfl_up_sync(0xffffffffu, tb1, 1);
+                if (lane == 0) { x0m = cx0; tb0m = ctb0; tb1m = ctb1; }
+                T[f] = (f <= n) ? face_rhs<K, M1>(x0m, tb0m, tb1m, xv[0], tb0, tb1) : 0.0;
+                cx0 = __shfl_sync(0xffffffffu, xv[0], 31);
+                if (K >= 1 && M1 >= 2) ctb0 = __shfl_sync(0xffffffffu, tb0, 31);
+                if (K >= 2 && M1 >= 3) ctb1 = __shfl_sync(0xffffffffu, tb1, 31);
+            }
+            __syncwarp();
+
+            // ---- P2: forward substitution z_f = T_f - u_{f-1} z_{f-1}, chunk per lane + affine scan
+            const int f0 = lane * Lc;
+            {
+                double z = 0.0, A = 1.0;
+#pragma unroll 4
+                for (int j = 0; j < Lc; ++j) {
+                    const double um = UB[f0 + j];
+                    z = T[f0 + j] - um * z;
+                    A *= -um;
+                }
+#pragma unroll
+                for (int s = 1; s < 32; s <<= 1) {
+                    const double Ap = __shfl_up_sync(0xffffffffu, A, s), zp = __shfl_up_sync(0xffffffffu, z, s);
+                    if (lane >= s) { z = A * zp + z; A = A * Ap; }
+                }
+                double carry = __shfl_up_sync(0xffffffffu, z, 1);
+                if (lane == 0) carry = 0.0;
+                z = carry;
+                double q = 0.0;
+#pragma unroll 4
+                for (int j = 0; j < Lc; ++j) {
+                    z = T[f0 + j] - UB[f0 + j] * z;
+                    T[f0 + j] = z;
+                    q += z * z * MINV[f0 + j];
+                }
+                acc += w * q;
+            }
+            // ---- P3: backward substitution J_f = z_f/m_f - u_f J_{f+1}
+            {
+                double J = 0.0, Bp = 1.0;
+#pragma unroll 4
+                for (int j = Lc - 1; j >= 0; --j) {
+                    const double uf = UB[f0 + j + 1];
+                    J = MINV[f0 + j] * T[f0 + j] - uf * J;
+                    Bp *= -uf;
+                }
+#pragma unroll
+                for (int s = 1; s < 32; s <<= 1) {
+                    const double Bq = __shfl_down_sync(0xffffffffu, Bp, s), Jq = __shfl_down_sync(0xffffffffu, J, s);
+                    if (lane + s < 32) { J = Bp * Jq + J; Bp = Bp * Bq; }
+                }
+                double carry = __shfl_down_sync(0xffffffffu, J, 1);
+                if (lane == 31) carry = 0.0;
+                J = carry;
+#pragma unroll 4
+                for (int j = Lc - 1; j >= 0; --j) {
+                    J = MINV[f0 + j] * T[f0 + j] - UB[f0 + j + 1] * J;
+                    T[f0 + j] = J;
                 }
             }
-        }
-        __syncwarp();
-      }  // t
+            __syncwarp();
+            // ---- P4: y = diag*x + w * B J
+            for (int fb = 0; fb < n; fb += 32) {
+                const int f = fb + lane;
+                if (f < n) {
+                    const long long e = line * n + f;
+                    const double JL = T[f], JR = T[f + 1];
+                    double out[3];
+                    out[0] = Y[f] + w * (JR - JL);
+                    if (M1 >= 2) out[1] = Y[RL + f] + ((K >= 1) ? w * (5.0 / 6.0) * (JL + JR) : 0.0);
+                    if (M1 >= 3) out[2] = Y[2 * RL + f] + ((K >= 2) ? w * (7.0 / 10.0) * (JR - JL) : 0.0);
+#pragma unroll
+                    for (int p = 0; p < M1; ++p) {
+                        double *yp = a.y + (size_t)md[p] * a.ne + e;
+                        *yp = a.first ? out[p] : (*yp + out[p]);
+                    }
+                }
+            }
+            __syncwarp();
+        }  // t
     }
     if (a.red_out) {
         double v[1] = {acc};
@@ -182,17 +187,26 @@ struct MarchGeom {
     long long ostride_face;  // face-array offset per orth index
 };
 
+// Loads are issued in batches of UNR line steps before the dependent recurrence runs, so every thread keeps
+// UNR*(M1+2) independent global loads in flight (the recurrence itself is a short DFMA chain).
+#ifndef NF_MARCH_MINB
+#define NF_MARCH_MINB 6
+#endif
+#ifndef NF_MARCH_UNR
+#define NF_MARCH_UNR 4
+#endif
 template <int K, int M1, bool SMEMZ>
-__global__ void __launch_bounds__(128) k_sweep_march(const SweepArgs a, const MarchGeom g)
+__global__ void __launch_bounds__(128, NF_MARCH_MINB) k_sweep_march(const SweepArgs a, const MarchGeom g)
 {
     if (a.done && *a.done) return;
     extern __shared__ double sm[];
+    constexpr int UNR = NF_MARCH_UNR;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, WPB = blockDim.x >> 5;
     const int n = g.n;
     const int nxb = (a.nx + 31) >> 5;
     const long long nitems = (long long)g.north * a.nt * nxb;
-    double *zb = SMEMZ ? (sm + (size_t)wib * (n + 1) * 32)
-                       : (a.zscratch + ((size_t)blockIdx.x * WPB + wib) * (size_t)(n + 1) * 32);
+    double *__restrict__ zb = SMEMZ ? (sm + (size_t)wib * (n + 1) * 32 + lane)
+                                    : (a.zscratch + ((size_t)blockIdx.x * WPB + wib) * (size_t)(n + 1) * 32 + lane);
     double acc = 0.0;
     for (long long item = (long long)blockIdx.x * WPB + wib; item < nitems; item += (long long)gridDim.x * WPB) {
         const int xb = (int)(item % nxb);
@@ -204,46 +218,79 @@ __global__ void __launch_bounds__(128) k_sweep_march(const SweepArgs a, const Ma
             const double w = a.w[t];
             const long long c0 = (long long)orth * g.ostride_cell + ix;
             const long long s0 = (long long)orth * g.ostride_face + ix;
-            const double *xp[3];
-            double *yp[3];
-#pragma unroll
-            for (int p = 0; p < M1; ++p) {
-                xp[p] = a.x + (size_t)a.mode[t][p] * a.ne + c0;
-                yp[p] = a.y + (size_t)a.mode[t][p] * a.ne + c0;
-            }
-            const double *um = a.u + s0, *mi = a.minv + s0;
-            // forward
+            const long long st = g.stride;
+            const double *__restrict__ xp0 = a.x + (size_t)a.mode[t][0] * a.ne + c0;
+            const double *__restrict__ xp1 = a.x + (size_t)a.mode[t][M1 >= 2 ? 1 : 0] * a.ne + c0;
+            const double *__restrict__ xp2 = a.x + (size_t)a.mode[t][M1 >= 3 ? 2 : 0] * a.ne + c0;
+            double *__restrict__ yp0 = a.y + (size_t)a.mode[t][0] * a.ne + c0;
+            double *__restrict__ yp1 = a.y + (size_t)a.mode[t][M1 >= 2 ? 1 : 0] * a.ne + c0;
+            double *__restrict__ yp2 = a.y + (size_t)a.mode[t][M1 >= 3 ? 2 : 0] * a.ne + c0;
+            const double *__restrict__ um = a.u + s0;
+            const double *__restrict__ mi = a.minv + s0;
+            // ---- forward
             double x0m = 0.0, tb0m = 0.0, tb1m = 0.0, z = 0.0, uprev = 0.0, q = 0.0;
-#pragma unroll 4
-            for (int f = 0; f <= n; ++f) {
-                double x0 = 0.0, tb0 = 0.0, tb1 = 0.0;
-                if (f < n) {
-                    const long long o = (long long)f * g.stride;
-                    x0 = xp[0][o];
-                    if (K >= 1 && M1 >= 2) tb0 = -(4.0 / 3.0) * xp[1][o];
-                    if (K >= 2 && M1 >= 3) tb1 = -(4.0 / 5.0) * xp[2][o];
+            for (int fb = 0; fb <= n; fb += UNR) {
+                double lx0[UNR], lx1[UNR], lx2[UNR], lu[UNR], lm[UNR];
+#pragma unroll
+                for (int j = 0; j < UNR; ++j) {
+                    const int f = fb + j;
+                    const long long o = (long long)f * st;
+                    lx0[j] = lx1[j] = lx2[j] = 0.0; lu[j] = lm[j] = 0.0;
+                    if (f < n) {
+                        lx0[j] = __ldg(xp0 + o);
+                        if (K >= 1 && M1 >= 2) lx1[j] = __ldg(xp1 + o);
+                        if (K >= 2 && M1 >= 3) lx2[j] = __ldg(xp2 + o);
+                    }
+                    if (f <= n) { lu[j] = __ldg(um + o); lm[j] = __ldg(mi + o); }
                 }
-                const double T = face_rhs<K, M1>(x0m, tb0m, tb1m, x0, tb0, tb1);
-                z = T - uprev * z;
-                const long long so = (long long)f * g.stride;
-                uprev = um[so];
-                q += z * z * mi[so];
-                zb[(size_t)f * 32 + lane] = z;
-                x0m = x0; tb0m = tb0; tb1m = tb1;
+#pragma unroll
+                for (int j = 0; j < UNR; ++j) {
+                    const int f = fb + j;
+                    if (f <= n) {
+                        const double tb0 = (K >= 1 && M1 >= 2) ? -(4.0 / 3.0) * lx1[j] : 0.0;
+                        const double tb1 = (K >= 2 && M1 >= 3) ? -(4.0 / 5.0) * lx2[j] : 0.0;
+                        const double T = face_rhs<K, M1>(x0m, tb0m, tb1m, lx0[j], tb0, tb1);
+                        z = T - uprev * z;
+                        uprev = lu[j];
+                        q += z * z * lm[j];
+                        zb[(size_t)f * 32] = z;
+                        x0m = lx0[j]; tb0m = tb0; tb1m = tb1;
+                    }
+                }
             }
             acc += w * q;
-            // backward
+            // ---- backward
             double Jn = 0.0;
-#pragma unroll 4
-            for (int f = n; f >= 0; --f) {
-                const long long so = (long long)f * g.stride;
-                const double J = mi[so] * zb[(size_t)f * 32 + lane] - um[so] * Jn;
-                if (f < n) {
-                    yp[0][so] += w * (Jn - J);
-                    if (K >= 1 && M1 >= 2) yp[1][so] += w * (5.0 / 6.0) * (J + Jn);
-                    if (K >= 2 && M1 >= 3) yp[2][so] += w * (7.0 / 10.0) * (Jn - J);
+            for (int fb = n; fb >= 0; fb -= UNR) {
+                double lz[UNR], lu[UNR], lm[UNR], ly0[UNR], ly1[UNR], ly2[UNR];
+#pragma unroll
+                for (int j = 0; j < UNR; ++j) {
+                    const int f = fb - j;
+                    const long long o = (long long)f * st;
+                    lz[j] = lu[j] = lm[j] = ly0[j] = ly1[j] = ly2[j] = 0.0;
+                    if (f >= 0) {
+                        lz[j] = zb[(size_t)f * 32]; lu[j] = __ldg(um + o); lm[j] = __ldg(mi + o);
+                        if (f < n) {
+                            ly0[j] = yp0[o];
+                            if (K >= 1 && M1 >= 2) ly1[j] = yp1[o];
+                            if (K >= 2 && M1 >= 3) ly2[j] = yp2[o];
+                        }
+                    }
                 }
-                Jn = J;
+#pragma unroll
+                for (int j = 0; j < UNR; ++j) {
+                    const int f = fb - j;
+                    if (f >= 0) {
+                        const long long o = (long long)f * st;
+                        const double J = lm[j] * lz[j] - lu[j] * Jn;
+                        if (f < n) {
+                            yp0[o] = ly0[j] + w * (Jn - J);
+                            if (K >= 1 && M1 >= 2) yp1[o] = ly1[j] + w * (5.0 / 6.0) * (J + Jn);
+                            if (K >= 2 && M1 >= 3) yp2[o] = ly2[j] + w * (7.0 / 10.0) * (Jn - J);
+                        }
+                        Jn = J;
+                    }
+                }
             }
         }
     }
