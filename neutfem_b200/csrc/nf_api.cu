@@ -161,11 +161,10 @@ static int launch_sweeps_t(nf_ctx *c, int g, const double *x, double *y, bool us
     SweepArgs a;
     if (pass_mask & 1) {   // x pass
         fill_sweep_args(c, a, g, 0, x, y, use_cg);
-        int Lc = (c->nx + 1 + 31) / 32;
-        Lc |= 1;
+        int Lc = (c->nx + 1 + kXT - 1) / kXT;
+        Lc |= 1;                                   // odd chunk stride: conflict-free shared-memory columns
         a.Lc = Lc;
-        const int RL = 32 * Lc;
-        const size_t per_warp = ((size_t)(3 + M1) * RL + 2) * sizeof(double);
+        const size_t smem = ((size_t)(5 + M1) * kXT * Lc + 2) * sizeof(double);
         static size_t maxdyn = 0;          // opt-in dynamic shared memory of this instantiation (static part excluded)
         if (maxdyn == 0) {
             cudaFuncAttributes fa;
@@ -174,13 +173,11 @@ static int launch_sweeps_t(nf_ctx *c, int g, const double *x, double *y, bool us
             CU(c, cudaFuncSetAttribute(k_sweep_x<K, M1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lim));
             maxdyn = lim;
         }
-        int WPB = 4;
-        while (WPB > 1 && per_warp * WPB > maxdyn / 2) WPB >>= 1;      // keep two CTAs per SM when possible
-        if (per_warp * WPB > maxdyn) NF_FAIL(c, NF_ERR_ARG, "nx=%d too large for the shared-memory line solver", c->nx);
-        const size_t smem = per_warp * WPB;
+        if (smem > maxdyn) NF_FAIL(c, NF_ERR_ARG, "nx=%d too large for the shared-memory line solver", c->nx);
         const long long nlines = (long long)c->ny * c->nz;
-        const int grid = (int)std::max<long long>(1, std::min<long long>(kRedBlocks, (nlines + WPB - 1) / WPB));
-        LAUNCH(c, (k_sweep_x<K, M1>), grid, WPB * 32, smem, a);
+        const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(16, (c->smem_optin) / (smem + 1024)));
+        const int grid = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(kRedBlocks, (long long)c->sm_count * per_sm), nlines));
+        LAUNCH(c, (k_sweep_x<K, M1>), grid, kXT, smem, a);
     }
     for (int d = 1; d < c->dim; ++d) {
         if (!(pass_mask & (1 << d))) continue;

@@ -29,32 +29,45 @@ __device__ __forceinline__ double face_rhs(double x0m, double tb0m, double tb1m,
     return T;
 }
 
+__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
+// x sweep: one CTA of 128 threads per grid line. The line (LDL^T factors, D, SigR*vol, the flux modes of the current
+// transverse pair) is staged in shared memory with cp.async (LDGSTS) so that a whole line of loads is in flight at
+// once; every thread owns a chunk of Lc consecutive faces for the two substitutions and the chunks are stitched
+// exactly by a scan of affine maps (warp shuffles + one shared-memory hop across the 4 warps).
+constexpr int kXT = 128;   // threads per line
+
 template <int K, int M1>
-__global__ void __launch_bounds__(128) k_sweep_x(const SweepArgs a)
+__global__ void __launch_bounds__(kXT) k_sweep_x(const SweepArgs a)
 {
     if (a.done && *a.done) return;
     extern __shared__ double sm[];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, WPB = blockDim.x >> 5;
-    const int n = a.nx, Lc = a.Lc, RL = 32 * Lc;
-    constexpr int NROW = 3 + M1;
-    // rows per warp: MINV[RL], UB[RL+1] (UB[1+f] = u_f, UB[0] = 0), T[RL], Y[M1][RL]; one pad double per warp
-    double *MINV = sm + (size_t)wib * (NROW * RL + 2);
-    double *UB = MINV + RL, *T = UB + RL + 2, *Y = T + RL;
+    __shared__ double wsA[4], wsB[4];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int n = a.nx, Lc = a.Lc, RL = kXT * Lc;
+    // rows: MINV[RL], UB[RL+2] (UB[1+f] = u_f, UB[0] = 0), DV[RL], SV[RL], T[RL], X[M1][RL]
+    double *MINV = sm, *UB = MINV + RL, *DV = UB + RL + 2, *SV = DV + RL, *T = SV + RL, *X = T + RL;
     const long long nlines = (long long)a.ny * a.nz;
     double acc = 0.0;
 
-    for (long long line = (long long)blockIdx.x * WPB + wib; line < nlines; line += (long long)gridDim.x * WPB) {
+    for (long long line = blockIdx.x; line < nlines; line += gridDim.x) {
         const int iy = (int)(line % a.ny), iz = (int)(line / a.ny);
-        __syncwarp();
-        {
-            const double *gm = a.minv + line * (n + 1), *gu = a.u + line * (n + 1);
-            for (int f = lane; f < RL; f += 32) {
-                MINV[f] = (f <= n) ? __ldg(gm + f) : 0.0;
-                UB[1 + f] = (f < n) ? __ldg(gu + f) : 0.0;
-            }
-            if (lane == 0) UB[0] = 0.0;
+        const long long e0 = line * n;
+        const double *gm = a.minv + line * (n + 1), *gu = a.u + line * (n + 1);
+        for (int f = tid; f < RL; f += kXT) {
+            if (f <= n) cp_async8(MINV + f, gm + f); else MINV[f] = 0.0;
+            if (f < n) { cp_async8(UB + 1 + f, gu + f); cp_async8(DV + f, a.D + e0 + f); cp_async8(SV + f, a.SigR + e0 + f); }
+            else { UB[1 + f] = 0.0; DV[f] = 0.0; SV[f] = 0.0; }
         }
-        // reciprocal transverse parts of f_d for this line (unused directions carry cb = 0)
+        if (tid == 0) UB[0] = 0.0;
         const double ify0 = 1.0 / (a.Fy[0][iy] * a.Fz[0][iz]);
         const double ify1 = 1.0 / (a.Fy[1][iy] * a.Fz[1][iz]);
         const double ify2 = 1.0 / (a.Fy[2][iy] * a.Fz[2][iz]);
@@ -67,44 +80,33 @@ __global__ void __launch_bounds__(128) k_sweep_x(const SweepArgs a)
                 md[p] = a.mode[t][p];
                 wc[p] = a.wC[md[p]]; c0[p] = a.cb[0][md[p]] * ify0; c1[p] = a.cb[1][md[p]] * ify1; c2[p] = a.cb[2][md[p]] * ify2;
             }
-            // ---- P1: load the line, form diag*x and the condensed face rhs
-            double cx0 = 0.0, ctb0 = 0.0, ctb1 = 0.0;   // values of cell f-1 carried across 32-blocks
-            for (int fb = 0; fb < RL; fb += 32) {
-                const int f = fb + lane;
-                const bool cell = f < n;
-                const long long e = line * n + f;
-                double xv[3] = {0.0, 0.0, 0.0};
-                if (cell) {
-                    const double Dv = __ldg(a.D + e), Sv = __ldg(a.SigR + e) * __ldg(a.vol + e);
-                    const double q0 = Dv * __ldg(a.iFx[0] + f), q1 = Dv * __ldg(a.iFx[1] + f), q2 = Dv * __ldg(a.iFx[2] + f);
+            // ---- A: stage the flux modes of this pair
+            for (int f = tid; f < RL; f += kXT) {
 #pragma unroll
-                    for (int p = 0; p < M1; ++p) {
-                        xv[p] = __ldg(a.x + (size_t)md[p] * a.ne + e);
-                        const double dg = Sv * wc[p] + q0 * c0[p] + q1 * c1[p] + q2 * c2[p];
-                        const double yv = dg * xv[p];
-                        Y[p * RL + f] = yv;
-                        acc += yv * xv[p];
-                    }
+                for (int p = 0; p < M1; ++p) {
+                    if (f < n) cp_async8(X + p * RL + f, a.x + (size_t)md[p] * a.ne + e0 + f);
+                    else X[p * RL + f] = 0.0;
                 }
-                const double tb0 = (K >= 1 && M1 >= 2) ? -(4.0 / 3.0) * xv[1] : 0.0;
-                const double tb1 = (K >= 2 && M1 >= 3) ? -(4.0 / 5.0) * xv[2] : 0.0;
-                double x0m = __shfl_up_sync(0xffffffffu, xv[0], 1);
-                double tb0m = 0.0, tb1m = 0.0;
-                if (K >= 1 && M1 >= 2) tb0m = __shfl_up_sync(0xffffffffu, tb0, 1);
-                if (K >= 2 && M1 >= 3) tb1m = __shfl_up_sync(0xffffffffu, tb1, 1);
-                if (lane == 0) { x0m = cx0; tb0m = ctb0; tb1m = ctb1; }
-                T[f] = (f <= n) ? face_rhs<K, M1>(x0m, tb0m, tb1m, xv[0], tb0, tb1) : 0.0;
-                cx0 = __shfl_sync(0xffffffffu, xv[0], 31);
-                if (K >= 1 && M1 >= 2) ctb0 = __shfl_sync(0xffffffffu, tb0, 31);
-                if (K >= 2 && M1 >= 3) ctb1 = __shfl_sync(0xffffffffu, tb1, 31);
             }
-            __syncwarp();
-
-            // ---- P2: forward substitution z_f = T_f - u_{f-1} z_{f-1}, chunk per lane + affine scan
-            const int f0 = lane * Lc;
+            cp_async_wait_all();
+            __syncthreads();
+            // ---- B: condensed face rhs
+            for (int f = tid; f < RL; f += kXT) {
+                double Tv = 0.0;
+                if (f <= n) {
+                    const double x0 = X[f], x0m = (f > 0) ? X[f - 1] : 0.0;
+                    double tb0 = 0.0, tb0m = 0.0, tb1 = 0.0, tb1m = 0.0;
+                    if (K >= 1 && M1 >= 2) { tb0 = -(4.0 / 3.0) * X[RL + f]; tb0m = (f > 0) ? -(4.0 / 3.0) * X[RL + f - 1] : 0.0; }
+                    if (K >= 2 && M1 >= 3) { tb1 = -(4.0 / 5.0) * X[2 * RL + f]; tb1m = (f > 0) ? -(4.0 / 5.0) * X[2 * RL + f - 1] : 0.0; }
+                    Tv = face_rhs<K, M1>(x0m, tb0m, tb1m, x0, tb0, tb1);
+                }
+                T[f] = Tv;
+            }
+            __syncthreads();
+            // ---- C: forward substitution z_f = T_f - u_{f-1} z_{f-1}
+            const int f0 = tid * Lc;
             {
                 double z = 0.0, A = 1.0;
-#pragma unroll 4
                 for (int j = 0; j < Lc; ++j) {
                     const double um = UB[f0 + j];
                     z = T[f0 + j] - um * z;
@@ -115,11 +117,14 @@ __global__ void __launch_bounds__(128) k_sweep_x(const SweepArgs a)
                     const double Ap = __shfl_up_sync(0xffffffffu, A, s), zp = __shfl_up_sync(0xffffffffu, z, s);
                     if (lane >= s) { z = A * zp + z; A = A * Ap; }
                 }
-                double carry = __shfl_up_sync(0xffffffffu, z, 1);
-                if (lane == 0) carry = 0.0;
-                z = carry;
+                if (lane == 31) { wsA[wid] = A; wsB[wid] = z; }
+                double Aex = __shfl_up_sync(0xffffffffu, A, 1), zex = __shfl_up_sync(0xffffffffu, z, 1);
+                if (lane == 0) { Aex = 1.0; zex = 0.0; }
+                __syncthreads();
+                double c = 0.0;
+                for (int ww = 0; ww < wid; ++ww) c = wsA[ww] * c + wsB[ww];
+                z = Aex * c + zex;
                 double q = 0.0;
-#pragma unroll 4
                 for (int j = 0; j < Lc; ++j) {
                     z = T[f0 + j] - UB[f0 + j] * z;
                     T[f0 + j] = z;
@@ -127,10 +132,10 @@ __global__ void __launch_bounds__(128) k_sweep_x(const SweepArgs a)
                 }
                 acc += w * q;
             }
-            // ---- P3: backward substitution J_f = z_f/m_f - u_f J_{f+1}
+            __syncthreads();   // wsA/wsB reuse below
+            // ---- D: backward substitution J_f = z_f/m_f - u_f J_{f+1}
             {
                 double J = 0.0, Bp = 1.0;
-#pragma unroll 4
                 for (int j = Lc - 1; j >= 0; --j) {
                     const double uf = UB[f0 + j + 1];
                     J = MINV[f0 + j] * T[f0 + j] - uf * J;
@@ -141,34 +146,40 @@ __global__ void __launch_bounds__(128) k_sweep_x(const SweepArgs a)
                     const double Bq = __shfl_down_sync(0xffffffffu, Bp, s), Jq = __shfl_down_sync(0xffffffffu, J, s);
                     if (lane + s < 32) { J = Bp * Jq + J; Bp = Bp * Bq; }
                 }
-                double carry = __shfl_down_sync(0xffffffffu, J, 1);
-                if (lane == 31) carry = 0.0;
-                J = carry;
-#pragma unroll 4
+                if (lane == 0) { wsA[wid] = Bp; wsB[wid] = J; }
+                double Bex = __shfl_down_sync(0xffffffffu, Bp, 1), Jex = __shfl_down_sync(0xffffffffu, J, 1);
+                if (lane == 31) { Bex = 1.0; Jex = 0.0; }
+                __syncthreads();
+                double c = 0.0;
+                for (int ww = 3; ww > wid; --ww) c = wsA[ww] * c + wsB[ww];
+                J = Bex * c + Jex;
                 for (int j = Lc - 1; j >= 0; --j) {
                     J = MINV[f0 + j] * T[f0 + j] - UB[f0 + j + 1] * J;
                     T[f0 + j] = J;
                 }
             }
-            __syncwarp();
-            // ---- P4: y = diag*x + w * B J
-            for (int fb = 0; fb < n; fb += 32) {
-                const int f = fb + lane;
-                if (f < n) {
-                    const long long e = line * n + f;
-                    const double JL = T[f], JR = T[f + 1];
-                    double out[3];
-                    out[0] = Y[f] + w * (JR - JL);
-                    if (M1 >= 2) out[1] = Y[RL + f] + ((K >= 1) ? w * (5.0 / 6.0) * (JL + JR) : 0.0);
-                    if (M1 >= 3) out[2] = Y[2 * RL + f] + ((K >= 2) ? w * (7.0 / 10.0) * (JR - JL) : 0.0);
+            __syncthreads();
+            // ---- E: y = diag*x + w * B J
+            for (int f = tid; f < n; f += kXT) {
+                const double JL = T[f], JR = T[f + 1];
+                const double Dv = DV[f], Sv = SV[f] * __ldg(a.vol + e0 + f);
+                const double q0 = Dv * __ldg(a.iFx[0] + f), q1 = Dv * __ldg(a.iFx[1] + f), q2 = Dv * __ldg(a.iFx[2] + f);
+                double sol[3];
+                sol[0] = w * (JR - JL);
+                sol[1] = (K >= 1) ? w * (5.0 / 6.0) * (JL + JR) : 0.0;
+                sol[2] = (K >= 2) ? w * (7.0 / 10.0) * (JR - JL) : 0.0;
 #pragma unroll
-                    for (int p = 0; p < M1; ++p) {
-                        double *yp = a.y + (size_t)md[p] * a.ne + e;
-                        *yp = a.first ? out[p] : (*yp + out[p]);
-                    }
+                for (int p = 0; p < M1; ++p) {
+                    const double xv = X[p * RL + f];
+                    const double dg = Sv * wc[p] + q0 * c0[p] + q1 * c1[p] + q2 * c2[p];
+                    const double yv = dg * xv;
+                    acc += yv * xv;
+                    double *yp = a.y + (size_t)md[p] * a.ne + e0 + f;
+                    const double o = yv + sol[p];
+                    *yp = a.first ? o : (*yp + o);
                 }
             }
-            __syncwarp();
+            __syncthreads();
         }  // t
     }
     if (a.red_out) {
