@@ -58,7 +58,12 @@ class Problem:
     def apply(self, solver):
         """Fill any object exposing the reference's binding surface (get_D()..., set_bc, BuildMatrices)."""
         for attr, t, v in self.bcs:
-            solver.set_bc(int(attr), t, float(v))
+            try:
+                solver.set_bc(int(attr), t, float(v))
+            except TypeError:       # the pybind11 module wants its BCType enum, like the reference's
+                import importlib
+                mod = importlib.import_module(type(solver).__module__)
+                solver.set_bc(int(attr), mod.BCType(int(t)), float(v))
         for getter, arr in (("get_D", self.D), ("get_SigR", self.SigR), ("get_NSF", self.NSF),
                             ("get_Chi", self.Chi), ("get_SigS", self.SigS)):
             view = getattr(solver, getter)()
