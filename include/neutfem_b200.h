@@ -130,9 +130,16 @@ NF_API int nf_get_diagonal_cache(nf_ctx *ctx, int g, double *s_inv);
 NF_API int nf_time_kernels(nf_ctx *ctx, int g, int reps, int fast, double *ms_out);
 
 /* ---- multi-GPU (z-slabs, one process per GPU) -------------------------------------------------------------
- * The reference is single-process; these have no counterpart there. nf_comm_unique_id fills a 128-byte NCCL id
- * on the caller (rank 0), the host distributes it (torch.distributed / MPI / files), every rank then calls
- * nf_create_slab + nf_comm_init. See DESIGN.md "z-slabs". */
+ * The reference is single-process; these have no counterpart there. Rank r owns the planes [z0, z1) of the global
+ * mesh (x/y/z breaks are the GLOBAL ones); its arrays (XS, flux) are the contiguous slices of the global arrays
+ * for those planes (element order is z-major, src/FEM.cpp:89-91). x and y sweeps are slab-local; the z-direction
+ * line systems are solved exactly by substructuring (one NCCL all-gather of 2 doubles per (x,y,mode) per apply) and
+ * the CG / k-eff scalars are all-reduced. nf_comm_unique_id fills a 128-byte NCCL id on rank 0; the host distributes
+ * it (torch.distributed / MPI / files); every rank then calls nf_comm_init before nf_build. Sizes returned by
+ * nf_get_sizes are local. The diagonal RT0-P0 path and nf_get_current are single-GPU only. */
+NF_API int nf_create_slab(nf_ctx **out, int rt_order, int p_order, int ng,
+                          const double *x_breaks, int n_x_breaks, const double *y_breaks, int n_y_breaks,
+                          const double *z_breaks, int n_z_breaks, int z0, int z1, int rank, int nranks, int device);
 NF_API int nf_comm_unique_id(char id[128]);
 NF_API int nf_comm_init(nf_ctx *ctx, const char id[128], int rank, int nranks);
 

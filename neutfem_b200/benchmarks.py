@@ -130,7 +130,7 @@ def problem_iaea3d(n: int = 2, nz_per_plane: int = 1) -> Problem:
     return Problem(f"iaea3d_{n}x{n}x{nz_per_plane}", 2, xb, yb, zb, D, R, F, C, S, bcs, d["kref"])
 
 
-def problem_iaea3d_synthetic(nx: int, ny: int, nz: int, void_as_reflector: bool = False) -> Problem:
+def problem_iaea3d_synthetic(nx: int, ny: int, nz: int, void_as_reflector: bool = False, z_range=None) -> Problem:
     """Synthetic refined IAEA-3D on exactly nx x ny x nz cells over the 380 cm cube-ish core:
     material(ix,iy,iz) = map[floor(19*iz/nz)][floor(19*iy/ny)][floor(19*ix/nx)] (SURVEY 8(d) alignment variant).
     void_as_reflector replaces the 1e15 'void' cells by reflector F4 (used only for conditioning studies)."""
@@ -142,6 +142,8 @@ def problem_iaea3d_synthetic(nx: int, ny: int, nz: int, void_as_reflector: bool 
     iz = (19 * np.arange(nz)) // nz
     iy = (19 * np.arange(ny)) // ny
     ix = (19 * np.arange(nx)) // nx
+    if z_range is not None:                      # only the planes [z0, z1) of a z-slab (breaks stay global)
+        iz = iz[z_range[0]:z_range[1]]
     ids = ids19[iz][:, iy][:, :, ix]
     xb = np.linspace(0.0, 380.0, nx + 1)
     yb = np.linspace(0.0, 380.0, ny + 1)

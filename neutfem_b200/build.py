@@ -35,13 +35,28 @@ def _sources(d, exts):
     return sorted(out)
 
 
+def nccl_paths():
+    """NCCL headers / library: the torch-bundled wheel (nvidia/nccl) first, the system one as fallback."""
+    try:
+        import nvidia.nccl as nn
+        base = os.path.dirname(nn.__file__) if getattr(nn, "__file__", None) else list(nn.__path__)[0]
+        inc, lib = os.path.join(base, "include"), os.path.join(base, "lib")
+        if os.path.exists(os.path.join(inc, "nccl.h")) and os.path.exists(os.path.join(lib, "libnccl.so.2")):
+            return inc, lib
+    except Exception:
+        pass
+    return "/usr/include", "/usr/lib/x86_64-linux-gnu"
+
+
 def build_cuda(force=False, verbose=False):
     os.makedirs(LIBDIR, exist_ok=True)
     deps = _sources(CSRC, (".cu", ".cuh")) + [os.path.join(ROOT, "include", "neutfem_b200.h")]
     if not (force or _newer(LIB, deps)):
         return LIB
+    inc, lib = nccl_paths()
     cmd = [NVCC, *ARCH, "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-fvisibility=hidden", "-shared",
-           "-o", LIB, os.path.join(CSRC, "nf_api.cu")]
+           f"-I{inc}", "-o", LIB, os.path.join(CSRC, "nf_api.cu"), f"-L{lib}", "-l:libnccl.so.2",
+           "-Xlinker", f"-rpath={lib}"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     subprocess.check_call(cmd)

@@ -27,6 +27,7 @@ EXPORTED = [
     "nf_build", "nf_build_diagonal_cache", "nf_set_flux", "nf_get_flux", "nf_get_flux_adjoint", "nf_reset_flux",
     "nf_get_current", "nf_solve_keff", "nf_solve_adjoint", "nf_solve_source", "nf_get_last_keff", "nf_schur_apply",
     "nf_schur_solve", "nf_current_from_flux", "nf_get_diagonal_cache", "nf_comm_unique_id", "nf_comm_init",
+    "nf_create_slab",
     "nf_version", "nf_kernel_launch_count", "nf_time_kernels",
 ]
 
@@ -60,6 +61,8 @@ def load():
     vp = ctypes.c_void_p
     L.nf_create.argtypes = [ctypes.POINTER(vp), ctypes.c_int, ctypes.c_int, ctypes.c_int, dp, ctypes.c_int, dp,
                             ctypes.c_int, dp, ctypes.c_int, ctypes.c_int]
+    L.nf_create_slab.argtypes = [ctypes.POINTER(vp), ctypes.c_int, ctypes.c_int, ctypes.c_int, dp, ctypes.c_int, dp,
+                                 ctypes.c_int, dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
     L.nf_destroy.argtypes = [vp]
     L.nf_last_error.argtypes = [vp]
     L.nf_last_error.restype = ctypes.c_char_p
@@ -102,13 +105,19 @@ def _f64(a):
 class Context:
     """One nf_ctx. Method names follow the C entry points (nf_ prefix dropped)."""
 
-    def __init__(self, rt_order, p_order, ng, x_breaks, y_breaks, z_breaks, device=-1):
+    def __init__(self, rt_order, p_order, ng, x_breaks, y_breaks, z_breaks, device=-1, slab=None):
+        """slab = (z0, z1, rank, nranks): z-slab context over the global breaks (nf_create_slab)."""
         L = load()
         self._L = L
         xb, yb, zb = _f64(x_breaks), _f64(y_breaks), _f64(z_breaks)
         h = ctypes.c_void_p()
-        rc = L.nf_create(ctypes.byref(h), int(rt_order), int(p_order), int(ng), _dp(xb), xb.size, _dp(yb), yb.size,
-                         _dp(zb), zb.size, int(device))
+        if slab is None:
+            rc = L.nf_create(ctypes.byref(h), int(rt_order), int(p_order), int(ng), _dp(xb), xb.size, _dp(yb), yb.size,
+                             _dp(zb), zb.size, int(device))
+        else:
+            z0, z1, rank, nranks = [int(v) for v in slab]
+            rc = L.nf_create_slab(ctypes.byref(h), int(rt_order), int(p_order), int(ng), _dp(xb), xb.size, _dp(yb), yb.size,
+                                  _dp(zb), zb.size, z0, z1, rank, nranks, int(device))
         if rc != 0:
             raise RuntimeError(f"nf_create failed ({rc}): {L.nf_last_error(None).decode()}")
         self._h = h
@@ -225,10 +234,21 @@ class Context:
         self._ck(self._L.nf_time_kernels(self._h, int(g), int(reps), int(fast), _dp(out)), "nf_time_kernels")
         return dict(sweep_x=out[0], sweep_y=out[1], sweep_z=out[2], cg_update=out[3], cg_pupdate=out[4], cg_iteration=out[5])
 
+    def comm_init(self, id_bytes, rank, nranks):
+        self._ck(self._L.nf_comm_init(self._h, id_bytes, int(rank), int(nranks)), "nf_comm_init")
+
     def diagonal_cache(self, g):
         out = np.empty(self.ne)
         self._ck(self._L.nf_get_diagonal_cache(self._h, int(g), _dp(out)), "nf_get_diagonal_cache")
         return out
+
+
+def comm_unique_id():
+    buf = ctypes.create_string_buffer(128)
+    rc = load().nf_comm_unique_id(buf)
+    if rc != 0:
+        raise RuntimeError(f"nf_comm_unique_id failed ({rc})")
+    return buf.raw
 
 
 def kernel_launch_count():

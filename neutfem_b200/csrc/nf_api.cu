@@ -11,6 +11,8 @@
 #include <string>
 #include <vector>
 
+#include <nccl.h>
+
 #include "../../include/neutfem_b200.h"
 #include "nf_common.cuh"
 #include "nf_sweeps.cuh"
@@ -56,7 +58,24 @@ struct nf_ctx {
     double wC[kMaxModes], cb[3][kMaxModes], wM[kMaxModes], wface[3][kMaxModes];
     std::string err;
     long long launches_call = 0;
+    // ---- z-slab (multi-GPU) mode: this context owns planes [z0, z0+nz) of a global mesh with nz_global planes
+    bool slab = false;
+    int rank = 0, nranks = 1, z0 = 0, nz_global = 0;
+    ncclComm_t comm = nullptr;
+    long long nxy = 0;
+    std::vector<double *> d_s0;            // [g] column 0 of the local z-line inverses
+    double *d_E = nullptr, *d_Eall = nullptr;      // [g][3][nxy], [g][nranks][3][nxy]
+    double *d_vG = nullptr, *d_vGall = nullptr;    // [2][nt][nxy], [nranks][2][nt][nxy]
 };
+
+#define NC(ctx, call)                                                                                      \
+    do {                                                                                                   \
+        ncclResult_t _r = (call);                                                                          \
+        if (_r != ncclSuccess) NF_FAIL(ctx, NF_ERR_NCCL, "%s failed: %s (%s:%d)", #call, ncclGetErrorString(_r), \
+                                       __FILE__, __LINE__);                                                \
+    } while (0)
+
+
 
 #define NF_FAIL(ctx, code, ...)                                  \
     do {                                                         \
@@ -78,6 +97,14 @@ struct nf_ctx {
         kern<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__); \
         ++g_launches; ++(ctx)->launches_call;                          \
     } while (0)
+
+// in-place sum over the ranks of n doubles living on the device (no-op on one rank)
+static int allreduce_sum(nf_ctx *c, double *dptr, int n)
+{
+    if (!c->slab) return NF_OK;
+    NC(c, ncclAllReduce(dptr, dptr, (size_t)n, ncclDouble, ncclSum, c->comm, c->stream));
+    return NF_OK;
+}
 
 static inline int ew_blocks(long long n) { return (int)std::max<long long>(1, std::min<long long>(kRedBlocks, (n + 255) / 256)); }
 
@@ -146,6 +173,10 @@ static void fill_sweep_args(nf_ctx *c, SweepArgs &a, int g, int d, const double 
     a.red_out = use_cg ? &c->d_cg->pAp[d] : nullptr;
     a.done = use_cg ? &c->d_cg->done : nullptr;
     a.ne = c->ne; a.nx = c->nx; a.ny = c->ny; a.nz = c->nz; a.dim = c->dim; a.nt = c->nt;
+    if (c->slab && d == 2) {
+        a.s0 = c->d_s0[g]; a.Eall = c->d_Eall + (size_t)g * c->nranks * 3 * c->nxy; a.vGall = c->d_vGall; a.vG = c->d_vG;
+        a.nxy = c->nxy; a.rank = c->rank; a.nranks = c->nranks;
+    }
     a.first = (d == 0);
     for (int t = 0; t < c->nt; ++t) {
         for (int p = 0; p < c->M1; ++p) a.mode[t][p] = c->tmode[d][t][p];
@@ -194,6 +225,26 @@ static int launch_sweeps_t(nf_ctx *c, int g, const double *x, double *y, bool us
         const int nxb = (c->nx + 31) / 32;
         const long long nitems = (long long)mg.north * c->nt * nxb;
         const int grid = (int)std::max<long long>(1, std::min<long long>(kRedBlocks, (nitems + WPB - 1) / WPB));
+        if (c->slab && d == 2 && c->nranks > 1) {
+            // forward (local) -> all-gather of the interface values -> backward with the reduced interface solve
+            const size_t need = (size_t)nitems * (mg.n + 1) * 32 * sizeof(double);
+            if (need > c->zscratch_bytes) {
+                CU(c, cudaStreamSynchronize(c->stream));
+                if (c->d_zscratch) cudaFree(c->d_zscratch);
+                c->d_zscratch = nullptr; c->zscratch_bytes = 0;
+                CU(c, cudaMalloc((void **)&c->d_zscratch, need));
+                c->zscratch_bytes = need;
+            }
+            a.zscratch = c->d_zscratch;
+            double *slot = a.red_out;
+            LAUNCH(c, (k_march_slab_fwd<K, M1>), grid, WPB * 32, 0, a, mg);
+            NC(c, ncclAllGather(c->d_vG, c->d_vGall, (size_t)2 * c->nt * c->nxy, ncclDouble, c->comm, c->stream));
+            // the backward kernel adds its share of x^T S x into the spare slot
+            a.red_out = slot ? &c->d_cg->pAp[3] : nullptr;
+            a.red_part = c->d_part + (size_t)3 * kRedBlocks; a.ticket = c->d_ticket + 3;
+            LAUNCH(c, (k_march_slab_bwd<K, M1>), grid, WPB * 32, 0, a, mg);
+            continue;
+        }
         const size_t zs = (size_t)(mg.n + 1) * 32 * sizeof(double) * WPB;
         if (zs <= 96 * 1024) {
             static bool conf = false;
@@ -246,6 +297,10 @@ static int dirichlet_flags(const nf_ctx *c, int *fl)
             auto it = c->bc_types.find(attr);
             fl[2 * d + up] = (it != c->bc_types.end() && it->second == NF_BC_DIRICHLET) ? 1 : 0;
         }
+    if (c->slab) {      // interior slab interfaces are not boundaries
+        if (c->rank > 0) fl[4] = 0;
+        if (c->rank < c->nranks - 1) fl[5] = 0;
+    }
     return 0;
 }
 
@@ -264,8 +319,8 @@ int64_t nf_kernel_launch_count(void) { return (int64_t)g_launches.load(); }
 
 const char *nf_last_error(const nf_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
-int nf_create(nf_ctx **out, int rt_order, int p_order, int ng, const double *xb, int nxb, const double *yb, int nyb,
-              const double *zb, int nzb, int device)
+static int create_impl(nf_ctx **out, int rt_order, int p_order, int ng, const double *xb, int nxb, const double *yb, int nyb,
+                       const double *zb, int nzb, int device, int force_dim)
 {
     if (!out) return NF_ERR_ARG;
     *out = nullptr;
@@ -289,6 +344,7 @@ int nf_create(nf_ctx **out, int rt_order, int p_order, int ng, const double *xb,
     c->ny = (yb && nyb > 1) ? nyb - 1 : 1;
     c->nz = (zb && nzb > 1) ? nzb - 1 : 1;
     c->dim = (c->nz > 1) ? 3 : (c->ny > 1 ? 2 : 1);
+    if (force_dim == 3) c->dim = 3;
     c->hx.resize(c->nx); c->hy.assign(c->ny, 1.0); c->hz.assign(c->nz, 1.0);
     for (int i = 0; i < c->nx; ++i) c->hx[i] = xb[i + 1] - xb[i];
     if (c->dim >= 2) for (int i = 0; i < c->ny; ++i) c->hy[i] = yb[i + 1] - yb[i];
@@ -395,6 +451,36 @@ int nf_create(nf_ctx **out, int rt_order, int p_order, int ng, const double *xb,
     return NF_OK;
 }
 
+int nf_create(nf_ctx **out, int rt_order, int p_order, int ng, const double *xb, int nxb, const double *yb, int nyb,
+              const double *zb, int nzb, int device)
+{
+    return create_impl(out, rt_order, p_order, ng, xb, nxb, yb, nyb, zb, nzb, device, 0);
+}
+
+int nf_create_slab(nf_ctx **out, int rt_order, int p_order, int ng, const double *xb, int nxb, const double *yb, int nyb,
+                   const double *zb, int nzb, int z0, int z1, int rank, int nranks, int device)
+{
+    if (!out || !zb || nzb < 2 || z0 < 0 || z1 <= z0 || z1 > nzb - 1 || rank < 0 || rank >= nranks || nranks > kMaxRanks || !yb || nyb < 2) {
+        g_create_error = "nf_create_slab: bad arguments (3-D meshes only, 1 <= planes per rank, nranks <= 16)";
+        return NF_ERR_ARG;
+    }
+    int r = create_impl(out, rt_order, p_order, ng, xb, nxb, yb, nyb, zb + z0, z1 - z0 + 1, device, 3);
+    if (r != NF_OK) return r;
+    nf_ctx *c = *out;
+    c->rank = rank; c->nranks = nranks; c->z0 = z0; c->nz_global = nzb - 1; c->nxy = (long long)c->nx * c->ny;
+    c->slab = nranks > 1;
+    if (c->slab) {
+        auto bad = [&](int code) { g_create_error = c->err; nf_destroy(c); *out = nullptr; return code; };
+        c->d_s0.assign(ng, nullptr);
+        for (int g = 0; g < ng; ++g) if (dalloc(c, &c->d_s0[g], (size_t)c->nfaces[2]) != NF_OK) return bad(NF_ERR_CUDA);
+        if (dalloc(c, &c->d_E, (size_t)ng * 3 * c->nxy) != NF_OK) return bad(NF_ERR_CUDA);
+        if (dalloc(c, &c->d_Eall, (size_t)ng * nranks * 3 * c->nxy) != NF_OK) return bad(NF_ERR_CUDA);
+        if (dalloc(c, &c->d_vG, (size_t)2 * c->nt * c->nxy) != NF_OK) return bad(NF_ERR_CUDA);
+        if (dalloc(c, &c->d_vGall, (size_t)nranks * 2 * c->nt * c->nxy) != NF_OK) return bad(NF_ERR_CUDA);
+    }
+    return NF_OK;
+}
+
 int nf_destroy(nf_ctx *c)
 {
     if (!c) return NF_OK;
@@ -406,6 +492,9 @@ int nf_destroy(nf_ctx *c)
     for (double *p : ptrs) if (p) cudaFree(p);
     for (int d = 0; d < 3; ++d) for (int ax = 0; ax < 3; ++ax) if (c->d_F[d][ax]) cudaFree(c->d_F[d][ax]);
     for (int d = 0; d < 3; ++d) if (c->d_iFx[d]) cudaFree(c->d_iFx[d]);
+    for (double *p : c->d_s0) if (p) cudaFree(p);
+    for (double *p : {c->d_E, c->d_Eall, c->d_vG, c->d_vGall}) if (p) cudaFree(p);
+    if (c->comm) ncclCommDestroy(c->comm);
     for (double *p : c->d_minv) if (p) cudaFree(p);
     for (double *p : c->d_u) if (p) cudaFree(p);
     if (c->d_cg) cudaFree(c->d_cg);
@@ -482,11 +571,19 @@ int nf_build(nf_ctx *c)
             a.minv = c->d_minv[g * 3 + d]; a.u = c->d_u[g * 3 + d];
             a.nx = c->nx; a.ny = c->ny; a.nz = c->nz; a.dim = c->dim; a.dir = d; a.K = c->K;
             a.dir_lo = fl[2 * d]; a.dir_hi = fl[2 * d + 1];
+            a.s0 = nullptr; a.E = nullptr; a.nxy = c->nxy;
+            if (c->slab && d == 2) { a.s0 = c->d_s0[g]; a.E = c->d_E + (size_t)g * 3 * c->nxy; }
             const int n = (d == 0) ? c->nx : (d == 1 ? c->ny : c->nz);
             const long long nlines = c->ne / n;
             LAUNCH(c, k_factor_lines, (int)((nlines + 127) / 128), 128, 0, a);
         }
     CU(c, cudaGetLastError());
+    if (c->slab) {
+        if (!c->comm) NF_FAIL(c, NF_ERR_STATE, "nf_build: z-slab context without communicator (call nf_comm_init)");
+        for (int g = 0; g < c->ng; ++g)
+            NC(c, ncclAllGather(c->d_E + (size_t)g * 3 * c->nxy, c->d_Eall + (size_t)g * c->nranks * 3 * c->nxy,
+                                (size_t)3 * c->nxy, ncclDouble, c->comm, c->stream));
+    }
     CU(c, cudaStreamSynchronize(c->stream));
     c->built = true; c->diag_valid = false; c->jac_valid = false;
     return NF_OK;
@@ -503,6 +600,7 @@ int nf_build_diagonal_cache(nf_ctx *c)
     if (!c) return NF_ERR_ARG;
     if (c->K != 0 || c->M != 0) return NF_OK;                    // "non applicable (ordre > 0)", NeutFEM.cpp:485-488
     if (!c->built) NF_FAIL(c, NF_ERR_STATE, "nf_build_diagonal_cache: call nf_build first");
+    if (c->slab) NF_FAIL(c, NF_ERR_STATE, "the diagonal RT0-P0 path is not sharded (replicas only, DESIGN.md)");
     if (c->diag_valid) return NF_OK;
     CU(c, cudaSetDevice(c->dev));
     if (!c->d_sinv) { int r = dalloc(c, &c->d_sinv, (size_t)c->ng * c->ne); if (r) return r; }
@@ -618,15 +716,20 @@ static int solve_group(nf_ctx *c, int g, const double *b, double *x, int *iters_
     if (direct) { tol = std::min(tol, 1e-13); maxit = std::max(maxit, (int)std::min<long long>(20000, 4 * n + 100)); }
     if (fast || direct) { int r = build_jacobi(c); if (r) return r; }
     const bool pcg = fast || direct;
+    const int fin = c->slab ? 0 : 1;        // scalar recurrences inside the reducing kernel unless ranks must be summed first
     const double *jac = pcg ? c->d_jac + (size_t)g * c->nphi : nullptr;
     CU(c, cudaEventRecord(c->ev2, c->stream));
     if (!pcg) {
-        LAUNCH(c, k_cg_init, blocks, 256, 0, b, x, c->d_r, c->d_p, n, tol, c->d_cg, c->d_part + 4 * kRedBlocks, c->d_ticket + 4);
+        LAUNCH(c, k_cg_init, blocks, 256, 0, b, x, c->d_r, c->d_p, n, tol, c->d_cg, c->d_part + 4 * kRedBlocks, c->d_ticket + 4, fin);
     } else {
         if (!fast) LAUNCH(c, k_fill, blocks, 256, 0, x, n, 0.0);      // "direct": x0 = 0
         { int r = apply_schur(c, g, x, c->d_Ap, false); if (r) return r; }
         LAUNCH(c, k_pcg_init, blocks, 256, 0, b, c->d_Ap, jac, c->d_r, c->d_p, n, tol, c->d_cg, c->d_part + 4 * kRedBlocks,
-               c->d_ticket + 4);
+               c->d_ticket + 4, fin);
+    }
+    if (!fin) {
+        { int r = allreduce_sum(c, c->d_cg->tmp, 3); if (r) return r; }
+        LAUNCH(c, k_cg_finalize, 1, 1, 0, c->d_cg, 0, tol, pcg ? 1 : 0);
     }
     // poll the device-side done flag every few iterations; iterations after convergence are no-ops on the device
     const double est_us = (double)n * 160.0 / 6.0e6 + 15.0;
@@ -637,13 +740,15 @@ static int solve_group(nf_ctx *c, int g, const double *b, double *x, int *iters_
         const int chunk = std::min(poll, maxit - k);
         for (int j = 0; j < chunk; ++j) {
             { int r = apply_schur(c, g, c->d_p, c->d_Ap, true); if (r) return r; }
-            if (!pcg) {
-                LAUNCH(c, k_cg_update, blocks, 256, 0, c->d_p, c->d_Ap, x, c->d_r, n, c->d_cg, c->d_part + 4 * kRedBlocks, c->d_ticket + 4);
-                LAUNCH(c, k_cg_pupdate, blocks, 256, 0, c->d_r, c->d_p, n, c->d_cg);
-            } else {
-                LAUNCH(c, k_pcg_update, blocks, 256, 0, c->d_p, c->d_Ap, jac, x, c->d_r, n, c->d_cg, c->d_part + 4 * kRedBlocks, c->d_ticket + 4);
-                LAUNCH(c, k_pcg_pupdate, blocks, 256, 0, c->d_r, jac, c->d_p, n, c->d_cg);
+            if (!fin) { int r = allreduce_sum(c, c->d_cg->pAp, 4); if (r) return r; }
+            if (!pcg) LAUNCH(c, k_cg_update, blocks, 256, 0, c->d_p, c->d_Ap, x, c->d_r, n, c->d_cg, c->d_part + 4 * kRedBlocks, c->d_ticket + 4, fin);
+            else LAUNCH(c, k_pcg_update, blocks, 256, 0, c->d_p, c->d_Ap, jac, x, c->d_r, n, c->d_cg, c->d_part + 4 * kRedBlocks, c->d_ticket + 4, fin);
+            if (!fin) {
+                { int r = allreduce_sum(c, c->d_cg->tmp, 2); if (r) return r; }
+                LAUNCH(c, k_cg_finalize, 1, 1, 0, c->d_cg, 1, tol, pcg ? 1 : 0);
             }
+            if (!pcg) LAUNCH(c, k_cg_pupdate, blocks, 256, 0, c->d_r, c->d_p, n, c->d_cg);
+            else LAUNCH(c, k_pcg_pupdate, blocks, 256, 0, c->d_r, jac, c->d_p, n, c->d_cg);
         }
         k += chunk;
         CU(c, cudaMemcpyAsync(c->h_cg, c->d_cg, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
@@ -663,7 +768,7 @@ static int solve_group(nf_ctx *c, int g, const double *b, double *x, int *iters_
     if (iters_out) *iters_out = iters;
     if (res_out) *res_out = res;
     if (st) {
-        st->cg_iterations += iters; st->cg_dof_iterations += (long long)iters * n; st->group_solves += 1;
+        st->cg_iterations += iters; st->cg_dof_iterations += (long long)iters * n; st->group_solves += 1;   // n = local DOFs
         st->ms_schur_cg += ms; st->last_cg_residual = res;
     }
     return NF_OK;
@@ -717,6 +822,7 @@ static int power_iteration(nf_ctx *c, bool adjoint, int use_diag, int accel, dou
             }
         }
         LAUNCH(c, k_outer_post, blocks, 256, 0, oa, c->d_old, adjoint ? 1 : 0, c->d_part + 5 * kRedBlocks, c->d_ticket + 5, c->d_scal + 1);
+        { int r = allreduce_sum(c, c->d_scal, 4); if (r) return r; }
         CU(c, cudaMemcpyAsync(c->h_scal, c->d_scal, 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         CU(c, cudaStreamSynchronize(c->stream));
         const double prod_old = c->h_scal[0], prod_new = c->h_scal[1], sol_sq = c->h_scal[2], diff_sq = c->h_scal[3];
@@ -786,7 +892,8 @@ int nf_solve_adjoint(nf_ctx *c, int normalize_to_direct, int use_direct_keff, do
     const bool fixed = use_direct_keff && c->has_valid;
     if (fixed) k = c->last_keff;
     const long long ntot = (long long)c->ng * c->nphi;
-    LAUNCH(c, k_fill, ew_blocks(ntot), 256, 0, c->d_phi_adj, ntot, 1.0 / std::sqrt((double)ntot));    // NeutFEM.cpp:1894-1895
+    const double ntot_global = (double)ntot * (c->slab ? (double)c->nz_global / (double)c->nz : 1.0);
+    LAUNCH(c, k_fill, ew_blocks(ntot), 256, 0, c->d_phi_adj, ntot, 1.0 / std::sqrt(ntot_global));    // NeutFEM.cpp:1894-1895
     // Chebyshev only in power-iteration mode and from it >= 5 (NeutFEM.cpp:1990-1992)
     const int accel = use_direct_keff ? NF_ACCEL_NONE : NF_ACCEL_CHEBYSHEV;
     int r = power_iteration(c, true, 0, accel, k, fixed, !use_direct_keff, 5, &k, &st);
@@ -794,6 +901,7 @@ int nf_solve_adjoint(nf_ctx *c, int normalize_to_direct, int use_direct_keff, do
     if (normalize_to_direct && c->has_valid) {                   // bi-orthogonal normalisation, NeutFEM.cpp:2020-2066
         LAUNCH(c, k_biorth, ew_blocks(c->nphi), 256, 0, c->d_phi, c->d_phi_adj, c->d_vol, c->ne, c->nloc, c->ng,
                c->d_part + 5 * kRedBlocks, c->d_ticket + 5, c->d_scal + 4, WVec(c->wC, c->dim));
+        { int r2 = allreduce_sum(c, c->d_scal + 4, 1); if (r2) return r2; }
         CU(c, cudaMemcpyAsync(c->h_scal + 4, c->d_scal + 4, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         CU(c, cudaStreamSynchronize(c->stream));
         const double ip = c->h_scal[4];
@@ -841,6 +949,7 @@ int nf_solve_source(nf_ctx *c, double *amplification, nf_stats *stats)
             }
             LAUNCH(c, k_flux_integral, blocks, 256, 0, c->d_phi, c->d_old, c->d_vol, c->ne, c->nloc, c->ng,
                    c->d_part + 5 * kRedBlocks, c->d_ticket + 5, c->d_scal + 5);
+            { int r2 = allreduce_sum(c, c->d_scal + 5, 3); if (r2) return r2; }
             CU(c, cudaMemcpyAsync(c->h_scal + 5, c->d_scal + 5, 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
             CU(c, cudaStreamSynchronize(c->stream));
             const double integral = c->h_scal[5], nsq = c->h_scal[6], dsq = c->h_scal[7];
@@ -922,6 +1031,7 @@ int nf_current_from_flux(nf_ctx *c, int g, const double *phi, double *J)
 {
     if (!c || !phi || !J || g < 0 || g >= c->ng) return NF_ERR_ARG;
     if (!c->built) NF_FAIL(c, NF_ERR_STATE, "nf_current_from_flux: call nf_build first");
+    if (c->slab) NF_FAIL(c, NF_ERR_STATE, "nf_current_from_flux: not available on z-slab contexts");
     CU(c, cudaSetDevice(c->dev));
     if (!c->d_J) { int r = dalloc(c, &c->d_J, (size_t)c->nJ); if (r) return r; }
     const size_t n = (size_t)c->nphi;
@@ -937,6 +1047,7 @@ int nf_get_current(nf_ctx *c, double *J, int adjoint)
 {
     if (!c || !J) return NF_ERR_ARG;
     if (!c->built) NF_FAIL(c, NF_ERR_STATE, "nf_get_current: call nf_build first");
+    if (c->slab) NF_FAIL(c, NF_ERR_STATE, "nf_get_current: not available on z-slab contexts");
     CU(c, cudaSetDevice(c->dev));
     if (!c->d_J) { int r = dalloc(c, &c->d_J, (size_t)c->nJ); if (r) return r; }
     if (adjoint) { int r = ensure_adjoint(c); if (r) return r; }
@@ -972,13 +1083,17 @@ int nf_time_kernels(nf_ctx *c, int g, int reps, int fast, double *ms_out)
     if (fast) { int r = build_jacobi(c); if (r) return r; }
     const double *jac = fast ? c->d_jac + (size_t)g * c->nphi : nullptr;
     LAUNCH(c, k_fill, blocks, 256, 0, c->d_rhs, n, 1.0);
-    LAUNCH(c, k_cg_init, blocks, 256, 0, c->d_rhs, c->d_tot, c->d_r, c->d_p, n, 0.0, c->d_cg, c->d_part + 4 * kRedBlocks, c->d_ticket + 4);
+    const int fin = c->slab ? 0 : 1;
+    LAUNCH(c, k_cg_init, blocks, 256, 0, c->d_rhs, c->d_tot, c->d_r, c->d_p, n, 0.0, c->d_cg, c->d_part + 4 * kRedBlocks, c->d_ticket + 4, fin);
+    if (!fin) { { int r = allreduce_sum(c, c->d_cg->tmp, 3); if (r) return r; } LAUNCH(c, k_cg_finalize, 1, 1, 0, c->d_cg, 0, 0.0, 0); }
     for (int i = 0; i < 8; ++i) ms_out[i] = 0.0;
     auto iteration = [&](int mask, bool upd, bool pupd) -> int {
         if (mask) { int r = apply_schur(c, g, c->d_p, c->d_Ap, true, mask); if (r) return r; }
         if (upd) {
-            if (!fast) LAUNCH(c, k_cg_update, blocks, 256, 0, c->d_p, c->d_Ap, c->d_tot, c->d_r, n, c->d_cg, c->d_part + 4 * kRedBlocks, c->d_ticket + 4);
-            else LAUNCH(c, k_pcg_update, blocks, 256, 0, c->d_p, c->d_Ap, jac, c->d_tot, c->d_r, n, c->d_cg, c->d_part + 4 * kRedBlocks, c->d_ticket + 4);
+            if (!fin) { int r = allreduce_sum(c, c->d_cg->pAp, 4); if (r) return r; }
+            if (!fast) LAUNCH(c, k_cg_update, blocks, 256, 0, c->d_p, c->d_Ap, c->d_tot, c->d_r, n, c->d_cg, c->d_part + 4 * kRedBlocks, c->d_ticket + 4, fin);
+            else LAUNCH(c, k_pcg_update, blocks, 256, 0, c->d_p, c->d_Ap, jac, c->d_tot, c->d_r, n, c->d_cg, c->d_part + 4 * kRedBlocks, c->d_ticket + 4, fin);
+            if (!fin) { { int r = allreduce_sum(c, c->d_cg->tmp, 2); if (r) return r; } LAUNCH(c, k_cg_finalize, 1, 1, 0, c->d_cg, 1, 0.0, fast ? 1 : 0); }
         }
         if (pupd) {
             if (!fast) LAUNCH(c, k_cg_pupdate, blocks, 256, 0, c->d_r, c->d_p, n, c->d_cg);
@@ -1004,16 +1119,25 @@ int nf_time_kernels(nf_ctx *c, int g, int reps, int fast, double *ms_out)
 
 int nf_comm_unique_id(char id[128])
 {
-    (void)id;
-    return NF_ERR_STATE;   // multi-GPU slabs: see nf_slab.cu (round-1: single GPU per context)
+    static_assert(sizeof(ncclUniqueId) <= 128, "NCCL id does not fit the ABI buffer");
+    if (!id) return NF_ERR_ARG;
+    ncclUniqueId u;
+    if (ncclGetUniqueId(&u) != ncclSuccess) return NF_ERR_NCCL;
+    memset(id, 0, 128);
+    memcpy(id, &u, sizeof(u));
+    return NF_OK;
 }
 
 int nf_comm_init(nf_ctx *c, const char id[128], int rank, int nranks)
 {
-    (void)id; (void)rank;
-    if (!c) return NF_ERR_ARG;
+    if (!c || !id) return NF_ERR_ARG;
     if (nranks == 1) return NF_OK;
-    NF_FAIL(c, NF_ERR_STATE, "nf_comm_init: z-slab decomposition is not available in this build");
+    if (!c->slab || rank != c->rank || nranks != c->nranks) NF_FAIL(c, NF_ERR_ARG, "nf_comm_init: context was not created by nf_create_slab with this rank/nranks");
+    CU(c, cudaSetDevice(c->dev));
+    ncclUniqueId u;
+    memcpy(&u, id, sizeof(u));
+    NC(c, ncclCommInitRank(&c->comm, nranks, u, rank));
+    return NF_OK;
 }
 
 }  // extern "C"

@@ -34,6 +34,13 @@ struct SweepArgs {
     const double *Fx[3], *Fy[3], *Fz[3];   // 1-D factors of f_d(e) = Fx[d][ix]*Fy[d][iy]*Fz[d][iz]
     const double *iFx[3];                  // 1/Fx[d][ix]
     double *zscratch;     // forward-sweep intermediates for long strided lines
+    // z-slab (multi-GPU) mode of the z sweep
+    const double *s0;     // column 0 of (A^r)^-1 per z line, face-indexed
+    const double *Eall;   // [nranks][3][nxy]: (G00, G0n, Gnn) of every rank's local inverse
+    const double *vGall;  // [nranks][2][nt][nxy]: local solutions at the interface faces, all ranks
+    double *vG;           // [2][nt][nxy]: this rank's
+    long long nxy;
+    int rank, nranks;
     double *red_part;     // [kRedBlocks] partial sums of this pass
     unsigned *ticket;
     double *red_out;      // scalar: x^T (this pass) x

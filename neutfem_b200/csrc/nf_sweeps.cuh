@@ -312,6 +312,197 @@ __global__ void __launch_bounds__(128, NF_MARCH_MINB) k_sweep_march(const SweepA
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// z sweep in z-slab (multi-GPU) mode: exact substructuring of the global z line systems (tests/slab_model.py is the
+// numpy model). Forward kernel: local forward substitution (z_f kept in global scratch), v_Gamma = local solution at
+// the two interface faces (v_n = z_n/m_n; v_0 = sum_f G_{0f} T_f with the precomputed column s0), local part of
+// x^T S x. [ncclAllGather of v_Gamma]. Backward kernel: every thread solves the (P-1)-interface reduced system of
+// its line redundantly, then J_f = v_f + s0_f lam_0 + sn_f lam_n while marching back (sn by its own recurrence).
+constexpr int kMaxRanks = 16;
+
+template <int K, int M1>
+__global__ void __launch_bounds__(128, NF_MARCH_MINB) k_march_slab_fwd(const SweepArgs a, const MarchGeom g)
+{
+    if (a.done && *a.done) return;
+    constexpr int UNR = NF_MARCH_UNR;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, WPB = blockDim.x >> 5;
+    const int n = g.n;
+    const int nxb = (a.nx + 31) >> 5;
+    const long long nitems = (long long)g.north * a.nt * nxb;
+    double acc = 0.0;
+    for (long long item = (long long)blockIdx.x * WPB + wib; item < nitems; item += (long long)gridDim.x * WPB) {
+        const int xb = (int)(item % nxb);
+        const long long r = item / nxb;
+        const int t = (int)(r % a.nt);
+        const int orth = (int)(r / a.nt);
+        const int ix = xb * 32 + lane;
+        if (ix < a.nx) {
+            double *__restrict__ zb = a.zscratch + (size_t)item * (size_t)(n + 1) * 32 + lane;
+            const double w = a.w[t];
+            const long long c0 = (long long)orth * g.ostride_cell + ix;
+            const long long s0o = (long long)orth * g.ostride_face + ix;
+            const long long st = g.stride;
+            const double *__restrict__ xp0 = a.x + (size_t)a.mode[t][0] * a.ne + c0;
+            const double *__restrict__ xp1 = a.x + (size_t)a.mode[t][M1 >= 2 ? 1 : 0] * a.ne + c0;
+            const double *__restrict__ xp2 = a.x + (size_t)a.mode[t][M1 >= 3 ? 2 : 0] * a.ne + c0;
+            const double *__restrict__ um = a.u + s0o;
+            const double *__restrict__ mi = a.minv + s0o;
+            const double *__restrict__ sp = a.s0 + s0o;
+            double x0m = 0.0, tb0m = 0.0, tb1m = 0.0, z = 0.0, uprev = 0.0, q = 0.0, v0 = 0.0, vn = 0.0;
+            for (int fb = 0; fb <= n; fb += UNR) {
+                double lx0[UNR], lx1[UNR], lx2[UNR], lu[UNR], lm[UNR], ls[UNR];
+#pragma unroll
+                for (int j = 0; j < UNR; ++j) {
+                    const int f = fb + j;
+                    const long long o = (long long)f * st;
+                    lx0[j] = lx1[j] = lx2[j] = 0.0; lu[j] = lm[j] = ls[j] = 0.0;
+                    if (f < n) {
+                        lx0[j] = __ldg(xp0 + o);
+                        if (K >= 1 && M1 >= 2) lx1[j] = __ldg(xp1 + o);
+                        if (K >= 2 && M1 >= 3) lx2[j] = __ldg(xp2 + o);
+                    }
+                    if (f <= n) { lu[j] = __ldg(um + o); lm[j] = __ldg(mi + o); ls[j] = __ldg(sp + o); }
+                }
+#pragma unroll
+                for (int j = 0; j < UNR; ++j) {
+                    const int f = fb + j;
+                    if (f <= n) {
+                        const double tb0 = (K >= 1 && M1 >= 2) ? -(4.0 / 3.0) * lx1[j] : 0.0;
+                        const double tb1 = (K >= 2 && M1 >= 3) ? -(4.0 / 5.0) * lx2[j] : 0.0;
+                        const double T = face_rhs<K, M1>(x0m, tb0m, tb1m, lx0[j], tb0, tb1);
+                        v0 += ls[j] * T;
+                        z = T - uprev * z;
+                        uprev = lu[j];
+                        q += z * z * lm[j];
+                        zb[(size_t)f * 32] = z;
+                        if (f == n) vn = z * lm[j];
+                        x0m = lx0[j]; tb0m = tb0; tb1m = tb1;
+                    }
+                }
+            }
+            acc += w * q;
+            const long long lxy = (long long)orth * a.nx + ix;
+            a.vG[((size_t)0 * a.nt + t) * a.nxy + lxy] = v0;
+            a.vG[((size_t)1 * a.nt + t) * a.nxy + lxy] = vn;
+        }
+    }
+    if (a.red_out) {
+        double v[1] = {acc};
+        grid_reduce<1>(v, a.red_part, a.ticket, a.red_out);
+    }
+}
+
+template <int K, int M1>
+__global__ void __launch_bounds__(128, NF_MARCH_MINB) k_march_slab_bwd(const SweepArgs a, const MarchGeom g)
+{
+    if (a.done && *a.done) return;
+    constexpr int UNR = NF_MARCH_UNR;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, WPB = blockDim.x >> 5;
+    const int n = g.n, P = a.nranks, me = a.rank;
+    const int nxb = (a.nx + 31) >> 5;
+    const long long nitems = (long long)g.north * a.nt * nxb;
+    double acc = 0.0;
+    for (long long item = (long long)blockIdx.x * WPB + wib; item < nitems; item += (long long)gridDim.x * WPB) {
+        const int xb = (int)(item % nxb);
+        const long long r = item / nxb;
+        const int t = (int)(r % a.nt);
+        const int orth = (int)(r / a.nt);
+        const int ix = xb * 32 + lane;
+        if (ix < a.nx) {
+            const double *__restrict__ zb = a.zscratch + (size_t)item * (size_t)(n + 1) * 32 + lane;
+            const double w = a.w[t];
+            const long long lxy = (long long)orth * a.nx + ix;
+            // ---- reduced interface system (interfaces i = 0..P-2 between rank i and i+1)
+            double dg[kMaxRanks], of[kMaxRanks], gg[kMaxRanks];
+            for (int i = 0; i < P; ++i) { dg[i] = 0.0; of[i] = 0.0; gg[i] = 0.0; }
+            double myG00 = 1.0, myG0n = 0.0, myGnn = 1.0, myv0 = 0.0, myvn = 0.0;
+            for (int rr = 0; rr < P; ++rr) {
+                const double G00 = __ldg(a.Eall + ((size_t)rr * 3 + 0) * a.nxy + lxy);
+                const double G0n = __ldg(a.Eall + ((size_t)rr * 3 + 1) * a.nxy + lxy);
+                const double Gnn = __ldg(a.Eall + ((size_t)rr * 3 + 2) * a.nxy + lxy);
+                const double v0 = __ldg(a.vGall + (((size_t)rr * 2 + 0) * a.nt + t) * a.nxy + lxy);
+                const double vn = __ldg(a.vGall + (((size_t)rr * 2 + 1) * a.nt + t) * a.nxy + lxy);
+                if (rr == me) { myG00 = G00; myG0n = G0n; myGnn = Gnn; myv0 = v0; myvn = vn; }
+                const int lo = rr - 1, hi = rr;
+                if (rr == 0) { dg[hi] += 1.0 / Gnn; gg[hi] += vn / Gnn; }
+                else if (rr == P - 1) { dg[lo] += 1.0 / G00; gg[lo] += v0 / G00; }
+                else {
+                    const double idet = 1.0 / (G00 * Gnn - G0n * G0n);
+                    const double S00 = Gnn * idet, S0n = -G0n * idet, Snn = G00 * idet;
+                    dg[lo] += S00; dg[hi] += Snn; of[lo] += S0n;
+                    gg[lo] += S00 * v0 + S0n * vn; gg[hi] += S0n * v0 + Snn * vn;
+                }
+            }
+            const int m = P - 1;
+            for (int i = 1; i < m; ++i) {               // Thomas on (dg, of, gg)
+                const double l = of[i - 1] / dg[i - 1];
+                dg[i] -= l * of[i - 1];
+                gg[i] -= l * gg[i - 1];
+            }
+            gg[m - 1] /= dg[m - 1];
+            for (int i = m - 2; i >= 0; --i) gg[i] = (gg[i] - of[i] * gg[i + 1]) / dg[i];
+            double lam0 = 0.0, lamn = 0.0;
+            if (me == 0) lamn = (gg[0] - myvn) / myGnn;
+            else if (me == P - 1) lam0 = (gg[P - 2] - myv0) / myG00;
+            else {
+                const double idet = 1.0 / (myG00 * myGnn - myG0n * myG0n);
+                const double d0 = gg[me - 1] - myv0, dn = gg[me] - myvn;
+                lam0 = (myGnn * d0 - myG0n * dn) * idet;
+                lamn = (-myG0n * d0 + myG00 * dn) * idet;
+            }
+            acc += w * (myv0 * lam0 + myvn * lamn);
+            // ---- backward with the interface corrections
+            const long long c0 = (long long)orth * g.ostride_cell + ix;
+            const long long s0o = (long long)orth * g.ostride_face + ix;
+            const long long st = g.stride;
+            double *__restrict__ yp0 = a.y + (size_t)a.mode[t][0] * a.ne + c0;
+            double *__restrict__ yp1 = a.y + (size_t)a.mode[t][M1 >= 2 ? 1 : 0] * a.ne + c0;
+            double *__restrict__ yp2 = a.y + (size_t)a.mode[t][M1 >= 3 ? 2 : 0] * a.ne + c0;
+            const double *__restrict__ um = a.u + s0o;
+            const double *__restrict__ mi = a.minv + s0o;
+            const double *__restrict__ sp = a.s0 + s0o;
+            double vnx = 0.0, snx = 0.0, Jn = 0.0;
+            for (int fb = n; fb >= 0; fb -= UNR) {
+                double lz[UNR], lu[UNR], lm[UNR], ls[UNR], ly0[UNR], ly1[UNR], ly2[UNR];
+#pragma unroll
+                for (int j = 0; j < UNR; ++j) {
+                    const int f = fb - j;
+                    const long long o = (long long)f * st;
+                    lz[j] = lu[j] = lm[j] = ls[j] = ly0[j] = ly1[j] = ly2[j] = 0.0;
+                    if (f >= 0) {
+                        lz[j] = zb[(size_t)f * 32]; lu[j] = __ldg(um + o); lm[j] = __ldg(mi + o); ls[j] = __ldg(sp + o);
+                        if (f < n) {
+                            ly0[j] = yp0[o];
+                            if (K >= 1 && M1 >= 2) ly1[j] = yp1[o];
+                            if (K >= 2 && M1 >= 3) ly2[j] = yp2[o];
+                        }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < UNR; ++j) {
+                    const int f = fb - j;
+                    if (f >= 0) {
+                        const long long o = (long long)f * st;
+                        const double v = lm[j] * lz[j] - lu[j] * vnx;
+                        const double sn = (f == n) ? lm[j] : -lu[j] * snx;
+                        const double J = v + ls[j] * lam0 + sn * lamn;
+                        if (f < n) {
+                            yp0[o] = ly0[j] + w * (Jn - J);
+                            if (K >= 1 && M1 >= 2) yp1[o] = ly1[j] + w * (5.0 / 6.0) * (J + Jn);
+                            if (K >= 2 && M1 >= 3) yp2[o] = ly2[j] + w * (7.0 / 10.0) * (Jn - J);
+                        }
+                        vnx = v; snx = sn; Jn = J;
+                    }
+                }
+            }
+        }
+    }
+    if (a.red_out) {
+        double v[1] = {acc};
+        grid_reduce<1>(v, a.red_part, a.ticket, a.red_out);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // LDL^T factors of the condensed line matrices of A_g for one direction (build step; replaces the
 // Eigen::SparseLU::compute(A_g) of SchurSolver::SetMatrices, src/solvers.cpp:163, and ApplyDirichletToA,
 // src/NeutFEM.cpp:1328-1456). One thread per line.
@@ -322,6 +513,9 @@ struct FactorArgs {
     double *minv, *u;
     int nx, ny, nz, dim, dir, K;
     int dir_lo, dir_hi;     // Dirichlet flags of the two sides
+    double *s0;             // slab mode (z only): column 0 of the local inverse, face-indexed
+    double *E;              // slab mode: [3][nxy] = (G00, G0n, Gnn)
+    long long nxy;
 };
 
 __global__ void k_factor_lines(const FactorArgs a)
@@ -374,6 +568,22 @@ __global__ void k_factor_lines(const FactorArgs a)
         a.minv[s0 + f * fs] = mi;
         a.u[s0 + f * fs] = o * mi;
         uprev = o * mi; offprev = o; cprev = c;
+    }
+    if (a.s0) {     // G[:,0] = L^-T D^-1 L^-1 e_0 of the local (Neumann-type) line matrix, and its corner entries
+        double pf = 1.0;
+        for (int f = 0; f <= n; ++f) {
+            a.s0[s0 + f * fs] = pf * a.minv[s0 + f * fs];
+            pf = -a.u[s0 + f * fs] * pf;
+        }
+        double sprev = 0.0;
+        for (int f = n; f >= 0; --f) {
+            const double sv = a.s0[s0 + f * fs] - a.u[s0 + f * fs] * sprev;
+            a.s0[s0 + f * fs] = sv;
+            sprev = sv;
+        }
+        a.E[0 * a.nxy + L] = a.s0[s0];
+        a.E[1 * a.nxy + L] = a.s0[s0 + (long long)n * fs];
+        a.E[2 * a.nxy + L] = a.minv[s0 + (long long)n * fs];
     }
 }
 

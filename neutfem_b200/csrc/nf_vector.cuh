@@ -16,6 +16,7 @@ struct CgState {
     double tol_sq;      // tol^2 ||b||^2
     double bnorm_sq;
     double rr_true;     // ||r||^2 (for the stopping test)
+    double tmp[4];      // raw local sums of the last reduction (all-reduced across ranks in z-slab mode)
     int done;
     int iters;
     int breakdown;
@@ -23,6 +24,38 @@ struct CgState {
 };
 
 __device__ __forceinline__ double thr14(double v) { return (fabs(v) > 1e-14) ? v : 0.0; }
+
+// Scalar part of the CG recurrences (solvers.cpp:587-589, 615-631). Runs in the last block of the reducing kernel on
+// one GPU, or in k_cg_finalize after the NCCL all-reduce of st->tmp in z-slab mode.
+__device__ inline void cg_init_fin(CgState *st, double tol, int pcg)
+{
+    if (!pcg) {
+        st->rr = st->bnorm_sq = st->rr_true = st->tmp[0];
+        st->tol_sq = tol * tol * st->tmp[0];
+        st->done = 0;
+    } else {
+        st->rr = st->tmp[0]; st->bnorm_sq = st->tmp[1]; st->rr_true = st->tmp[2];
+        st->tol_sq = tol * tol * st->tmp[1];
+        st->done = (st->tmp[2] < st->tol_sq || st->tmp[1] == 0.0) ? 1 : 0;
+    }
+    st->pAp[0] = st->pAp[1] = st->pAp[2] = st->pAp[3] = 0.0;
+    st->beta = 0.0; st->iters = 0; st->breakdown = 0;
+}
+
+__device__ inline void cg_update_fin(CgState *st, int pcg)
+{
+    const double num = st->tmp[0], rr_true = pcg ? st->tmp[1] : st->tmp[0];
+    st->iters += 1;
+    st->rr_true = rr_true;
+    if (rr_true < st->tol_sq) st->done = 1;
+    else { st->beta = num / st->rr; st->rr = num; }
+}
+
+__global__ void k_cg_finalize(CgState *st, int which, double tol, int pcg)
+{
+    if (which == 0) cg_init_fin(st, tol, pcg);
+    else if (!st->done) cg_update_fin(st, pcg);
+}
 
 // ---- layout ---------------------------------------------------------------------------------------------------
 // reference element-major [e*nloc + mode] <-> mode-major [mode*ne + e], ngv vectors back to back
@@ -60,7 +93,7 @@ __global__ void k_fill(double *v, long long n, double val)
 // x = 0, r = p = b, rr = ||b||^2, tol_sq = tol^2 ||b||^2      (solvers.cpp:583-589)
 __global__ void __launch_bounds__(256) k_cg_init(const double *__restrict__ b, double *__restrict__ x,
                                                  double *__restrict__ r, double *__restrict__ p, long long n,
-                                                 double tol, CgState *st, double *part, unsigned *ticket)
+                                                 double tol, CgState *st, double *part, unsigned *ticket, int fin)
 {
     double acc = 0.0;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -71,17 +104,15 @@ __global__ void __launch_bounds__(256) k_cg_init(const double *__restrict__ b, d
     double v[1] = {acc};
     __shared__ double out[1];
     if (grid_reduce<1>(v, part, ticket, out) && threadIdx.x == 0) {
-        st->rr = out[0]; st->bnorm_sq = out[0]; st->rr_true = out[0];
-        st->tol_sq = tol * tol * out[0];
-        st->pAp[0] = st->pAp[1] = st->pAp[2] = st->pAp[3] = 0.0;
-        st->beta = 0.0; st->done = 0; st->iters = 0; st->breakdown = 0;
+        st->tmp[0] = out[0];
+        if (fin) cg_init_fin(st, tol, 0);
     }
 }
 
 // alpha = rr / p.Ap ; x += alpha p ; r -= alpha Ap ; rr_new = ||r||^2 ; stop / beta    (solvers.cpp:601-631)
 __global__ void __launch_bounds__(256) k_cg_update(const double *__restrict__ p, const double *__restrict__ Ap,
                                                    double *__restrict__ x, double *__restrict__ r, long long n,
-                                                   CgState *st, double *part, unsigned *ticket)
+                                                   CgState *st, double *part, unsigned *ticket, int fin)
 {
     if (st->done) return;
     const double pAp = (st->pAp[0] + st->pAp[1]) + (st->pAp[2] + st->pAp[3]);
@@ -103,11 +134,8 @@ __global__ void __launch_bounds__(256) k_cg_update(const double *__restrict__ p,
     double v[1] = {acc};
     __shared__ double out[1];
     if (grid_reduce<1>(v, part, ticket, out) && threadIdx.x == 0) {
-        const double rr_new = out[0];
-        st->iters += 1;
-        st->rr_true = rr_new;
-        if (rr_new < st->tol_sq) st->done = 1;
-        else { st->beta = rr_new / rr; st->rr = rr_new; }
+        st->tmp[0] = out[0];
+        if (fin) cg_update_fin(st, 0);
     }
 }
 
@@ -125,7 +153,7 @@ __global__ void __launch_bounds__(256) k_cg_pupdate(const double *__restrict__ r
 __global__ void __launch_bounds__(256) k_pcg_init(const double *__restrict__ b, const double *__restrict__ Sx,
                                                   const double *__restrict__ minv, double *__restrict__ r,
                                                   double *__restrict__ p, long long n, double tol, CgState *st,
-                                                  double *part, unsigned *ticket)
+                                                  double *part, unsigned *ticket, int fin)
 {
     double acc[3] = {0.0, 0.0, 0.0};
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -135,18 +163,15 @@ __global__ void __launch_bounds__(256) k_pcg_init(const double *__restrict__ b, 
     }
     __shared__ double out[3];
     if (grid_reduce<3>(acc, part, ticket, out) && threadIdx.x == 0) {
-        st->rr = out[0]; st->bnorm_sq = out[1]; st->rr_true = out[2];
-        st->tol_sq = tol * tol * out[1];
-        st->pAp[0] = st->pAp[1] = st->pAp[2] = st->pAp[3] = 0.0;
-        st->beta = 0.0; st->iters = 0; st->breakdown = 0;
-        st->done = (out[2] < st->tol_sq || out[1] == 0.0) ? 1 : 0;
+        st->tmp[0] = out[0]; st->tmp[1] = out[1]; st->tmp[2] = out[2];
+        if (fin) cg_init_fin(st, tol, 1);
     }
 }
 
 __global__ void __launch_bounds__(256) k_pcg_update(const double *__restrict__ p, const double *__restrict__ Ap,
                                                     const double *__restrict__ minv, double *__restrict__ x,
                                                     double *__restrict__ r, long long n, CgState *st, double *part,
-                                                    unsigned *ticket)
+                                                    unsigned *ticket, int fin)
 {
     if (st->done) return;
     const double pAp = (st->pAp[0] + st->pAp[1]) + (st->pAp[2] + st->pAp[3]);
@@ -167,10 +192,8 @@ __global__ void __launch_bounds__(256) k_pcg_update(const double *__restrict__ p
     }
     __shared__ double out[2];
     if (grid_reduce<2>(acc, part, ticket, out) && threadIdx.x == 0) {
-        st->iters += 1;
-        st->rr_true = out[1];
-        if (out[1] < st->tol_sq) st->done = 1;
-        else { st->beta = out[0] / rz; st->rr = out[0]; }
+        st->tmp[0] = out[0]; st->tmp[1] = out[1];
+        if (fin) cg_update_fin(st, 1);
     }
 }
 
