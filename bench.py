@@ -186,11 +186,15 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        raise RuntimeError("z-slab multi-GPU path not available in this build")
 
     mesh = tuple(args.mesh)
     fast = args.mode == "fast"
-    p = bm.problem_iaea3d_synthetic(*mesh)
+    if world > 1:
+        from neutfem_b200.slab import SlabSolver, partition_planes
+        z0, z1 = partition_planes(mesh[2], world)[rank]
+        p = bm.problem_iaea3d_synthetic(*mesh, z_range=(z0, z1))       # this rank's planes only, global breaks
+    else:
+        p = bm.problem_iaea3d_synthetic(*mesh)
     # inputs live in pinned host memory (e2e copies start there)
     host = {}
     keep = []
@@ -198,9 +202,34 @@ def run_ours(args):
         v, t = pinned(getattr(p, name))
         host[name] = v
         keep.append(t)
-    ctx = cabi.Context(args.rt, args.p, p.ng, p.x_breaks, p.y_breaks, p.z_breaks, device=local_rank)
+    if world > 1:
+        slab = SlabSolver(args.rt, args.p, p.ng, p.x_breaks, p.y_breaks, p.z_breaks, rank, world, local_rank)
+        ctx = slab.ctx
+    else:
+        ctx = cabi.Context(args.rt, args.p, p.ng, p.x_breaks, p.y_breaks, p.z_breaks, device=local_rank)
     for a, t, v in p.bcs:
         ctx.set_bc(a, t, v)
+
+    def gsum(v):
+        if world == 1:
+            return v
+        t = torch.tensor([float(v)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return t.item()
+
+    def gmax(v):
+        if world == 1:
+            return v
+        t = torch.tensor([float(v)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
     K, W = args.steps, args.warmup
     solver = dict(solver_type=cabi.BICGSTAB, tol_keff=1e-14, tol_flux=args.tol_flux, max_inner=1000,
                   mode=cabi.MODE_FAST if fast else cabi.MODE_PARITY)
@@ -215,34 +244,35 @@ def run_ours(args):
     ctx.set_solver(max_outer=K, **solver)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    torch.cuda.synchronize()
+    barrier()
     launches0 = cabi.kernel_launch_count()
     k_dev, st = ctx.solve_keff(False)
-    torch.cuda.synchronize()
+    barrier()
     clocks = sampler.stop()
     launches = cabi.kernel_launch_count() - launches0
-    ms = st["ms_total"]
-    value = st["cg_dof_iterations"] / (ms * 1e-3) / 1e9
+    ms = gmax(st["ms_total"])                      # CUDA events on each rank's stream, max over ranks
+    dof_its = gsum(st["cg_dof_iterations"])        # whole-job count (ranks hold disjoint DOFs)
+    value = dof_its / (ms * 1e-3) / 1e9
     # ---- end to end through the C ABI with host buffers
     ctx.reset_flux()
     h2d = sum(v.nbytes for v in host.values())
-    flux_host = np.empty(ctx.ng * ctx.n_Phi)
-    torch.cuda.synchronize()
+    barrier()
     t0 = time.perf_counter()
     ctx.upload_xs(**host)
     ctx.build()
     k_e2e, st2 = ctx.solve_keff(False)
     flux = ctx.get_flux()
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    d2h = flux.nbytes + 32 * K
-    e2e = st2["cg_dof_iterations"] / dt / 1e9
+    barrier()
+    dt = gmax(time.perf_counter() - t0)
+    d2h = gsum(flux.nbytes + 32 * K)
+    h2d = gsum(h2d)
+    e2e = gsum(st2["cg_dof_iterations"]) / dt / 1e9
     # ---- roofline of the CG iteration from live CUDA-event kernel timings
     kt = ctx.time_kernels(0, 5, fast)
     hbm, how = peaks()
     nl = ctx.n_phi_loc
-    alg_bytes = (88.0 + 16.0 / nl) * ctx.n_Phi
-    achieved = alg_bytes / (kt["cg_iteration"] * 1e-3) / 1e9
+    alg_bytes = (88.0 + 16.0 / nl) * ctx.n_Phi              # per GPU: local DOFs over the local iteration time
+    achieved = alg_bytes / (gmax(kt["cg_iteration"]) * 1e-3) / 1e9
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / max(K, 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
@@ -252,18 +282,21 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"], "samples": clocks["samples"]},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
-                     "peak_source": how, "kernel": "one Schur-CG iteration = k_sweep_x + k_sweep_march(y) + k_sweep_march(z) + k_(p)cg_update + k_(p)cg_pupdate",
+                     "peak_source": how, "per": "GPU", "kernel": "one Schur-CG iteration = k_sweep_x + k_sweep_march(y) + k_sweep_march(z) + k_(p)cg_update + k_(p)cg_pupdate",
                      "algorithmic_bytes_per_dof": 88.0 + 16.0 / nl, "dofs_per_launch": ctx.n_Phi,
                      "ms_per_launch": kt["cg_iteration"],
                      "kernels_ms": {k: v for k, v in kt.items()}},
         "keff_after_K": k_dev, "outer_iterations": st["outer_iterations"], "cg_iterations": st["cg_iterations"],
-        "n_phi_per_group": ctx.n_Phi, "ms_schur_cg": st["ms_schur_cg"],
+        "n_phi_per_group": int(gsum(ctx.n_Phi)), "ms_schur_cg": st["ms_schur_cg"],
     }
     if rank == 0 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args)
     ctx.close()
     if rank == 0:
         print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     return 0
 
 
