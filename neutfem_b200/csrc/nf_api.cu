@@ -18,6 +18,7 @@
 #include "nf_sweeps.cuh"
 #include "nf_vector.cuh"
 #include "nf_current.cuh"
+#include "nf_fused.cuh"
 
 using namespace nf;
 
@@ -66,6 +67,13 @@ struct nf_ctx {
     std::vector<double *> d_s0;            // [g] column 0 of the local z-line inverses
     double *d_E = nullptr, *d_Eall = nullptr;      // [g][3][nxy], [g][nranks][3][nxy]
     double *d_vG = nullptr, *d_vGall = nullptr;    // [2][nt][nxy], [nranks][2][nt][nxy]
+    // ---- fused two-kernel CG iteration (nf_fused.cuh), 3-D single-GPU contexts
+    int fused = -1;                        // -1: not yet decided, 0: unavailable / disabled, 1: ready
+    int fLW = 4, fLcX = 1, fRLX = 0, fPS = 0, fLcY = 1, fRLY = 0, fnX = 0, fnY = 0, fnitems = 0, fgrid = 0;
+    size_t fsmem = 0;
+    double *d_zs = nullptr, *d_W = nullptr, *d_fpart = nullptr;
+    int *d_fq = nullptr;                   // [0] queue head, [1] error flag, [2] ticket, [4..4+nz) plane counters
+    int2 *d_items = nullptr;
 };
 
 #define NC(ctx, call)                                                                                      \
@@ -284,6 +292,162 @@ static int apply_schur(nf_ctx *c, int g, const double *x, double *y, bool use_cg
     NF_FAIL(c, NF_ERR_STATE, "unsupported order RT%d-P%d", c->K, c->M);
 }
 
+
+// ---- fused two-kernel CG iteration (nf_fused.cuh) ---------------------------------------------------------------------
+static int env_int(const char *name, int def)
+{
+    const char *v = getenv(name);
+    return (v && *v) ? atoi(v) : def;
+}
+
+template <int K, int M1, int LW>
+static int fused_prepare_t(nf_ctx *c, size_t smem, int *per_sm)
+{
+    CU(c, cudaFuncSetAttribute(k_plane_fwd<K, M1, LW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, k_plane_fwd<K, M1, LW>, kFT, smem));
+    return NF_OK;
+}
+
+template <int K, int M1>
+static int fused_prepare_lw(nf_ctx *c, size_t smem, int *per_sm)
+{
+    switch (c->fLW) {
+    case 2: return fused_prepare_t<K, M1, 2>(c, smem, per_sm);
+    case 4: return fused_prepare_t<K, M1, 4>(c, smem, per_sm);
+    case 8: return fused_prepare_t<K, M1, 8>(c, smem, per_sm);
+    }
+    NF_FAIL(c, NF_ERR_STATE, "fused path: unsupported y tile width %d", c->fLW);
+}
+
+#define NF_ORDER_SWITCH(c, CALL)                                              \
+    switch ((c)->K * 4 + (c)->M1) {                                           \
+    case 0 * 4 + 1: return CALL(0, 1);                                        \
+    case 1 * 4 + 1: return CALL(1, 1);                                        \
+    case 1 * 4 + 2: return CALL(1, 2);                                        \
+    case 2 * 4 + 1: return CALL(2, 1);                                        \
+    case 2 * 4 + 2: return CALL(2, 2);                                        \
+    case 2 * 4 + 3: return CALL(2, 3);                                        \
+    }                                                                         \
+    NF_FAIL(c, NF_ERR_STATE, "unsupported order RT%d-P%d", (c)->K, (c)->M)
+
+static int fused_prepare(nf_ctx *c, size_t smem, int *per_sm)
+{
+#define CALL(KK, MM) fused_prepare_lw<KK, MM>(c, smem, per_sm)
+    NF_ORDER_SWITCH(c, CALL);
+#undef CALL
+}
+
+// Decide once per context whether the fused path applies (3-D, single GPU, lines fit in shared memory) and build its
+// work-item queue: round r holds the X items of plane r and the Y items of plane r-delay, the Y items starting `lag`
+// X items into the round so that they (almost) never find their plane incomplete.
+static int fused_setup(nf_ctx *c)
+{
+    if (c->fused >= 0) return NF_OK;
+    c->fused = 0;
+    if (c->dim != 3 || c->slab || env_int("NF_FUSED", 1) == 0) return NF_OK;
+    int LW = env_int("NF_FUSED_LW", 4);
+    if (LW != 2 && LW != 4 && LW != 8) LW = 4;
+    c->fLW = LW;
+    auto chunk = [](int n, int cpl, int &Lc, int &RL) { Lc = (n + 1 + cpl - 1) / cpl; Lc |= 1; RL = cpl * Lc; };
+    chunk(c->nx, kFT, c->fLcX, c->fRLX);
+    chunk(c->ny, kFT / LW, c->fLcY, c->fRLY);
+    c->fPS = (c->nx + 2) & ~1;
+    const size_t smemX = ((size_t)3 * c->fRLX + 2 + (size_t)(3 + c->nloc) * c->fPS) * sizeof(double);
+    const size_t smemY = (((size_t)3 * c->fRLY + 1) * LW + (size_t)c->M1 * (c->ny + 1) * LW) * sizeof(double);
+    const size_t smem = (std::max(smemX, smemY) + 15) & ~(size_t)15;
+    if (smem + 4096 > c->smem_optin) return NF_OK;               // lines too long for shared memory: separate kernels
+    int per_sm = 0;
+    { int r = fused_prepare(c, smem, &per_sm); if (r) return r; }
+    if (per_sm < 1) return NF_OK;
+    const int want = env_int("NF_FUSED_CTAS", 0);
+    if (want > 0) per_sm = std::min(per_sm, want);
+    c->fsmem = smem;
+    c->fgrid = per_sm * c->sm_count;
+    const int nX = c->ny, nY = (c->nx + LW - 1) / LW, nz = c->nz;
+    c->fnX = nX; c->fnY = nY;
+    const int delay = env_int("NF_FUSED_DELAY", 1) ? 1 : 0;
+    int lag = env_int("NF_FUSED_LAG", nX / 2);
+    lag = std::max(0, std::min(lag, nX));
+    std::vector<int2> items;
+    items.reserve((size_t)nz * (nX + nY));
+    for (int r = 0; r < nz + delay; ++r) {
+        const int xs = (r < nz) ? nX : 0, yp = r - delay, ys = (yp >= 0 && yp < nz) ? nY : 0;
+        const int first = delay ? std::min(lag, xs) : xs;
+        int xi = 0, yi = 0;
+        for (; xi < first; ++xi) items.push_back(make_int2(r * 2, xi));
+        const int remx = xs - first;
+        while (xi < xs || yi < ys) {         // proportional merge of the remaining X items with the Y items
+            const bool takeY = (yi < ys) && (xi >= xs || (long long)yi * remx <= (long long)(xi - first) * ys);
+            if (takeY) { items.push_back(make_int2(yp * 2 + 1, yi)); ++yi; }
+            else { items.push_back(make_int2(r * 2, xi)); ++xi; }
+        }
+    }
+    c->fnitems = (int)items.size();
+    const size_t nxy = (size_t)c->nx * c->ny;
+    { int r = dalloc(c, &c->d_zs, (size_t)(nz + 1) * c->nt * nxy); if (r) return r; }
+    { int r = dalloc(c, &c->d_W, (size_t)2 * c->nt * nxy); if (r) return r; }
+    { int r = dalloc(c, &c->d_fpart, (size_t)c->fnitems); if (r) return r; }
+    { int r = dalloc(c, &c->d_fq, (size_t)nz + 8); if (r) return r; }
+    { int r = dalloc(c, &c->d_items, items.size()); if (r) return r; }
+    CU(c, cudaMemsetAsync(c->d_fq, 0, ((size_t)nz + 8) * sizeof(int), c->stream));
+    CU(c, cudaMemcpyAsync(c->d_items, items.data(), items.size() * sizeof(int2), cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    c->fused = 1;
+    return NF_OK;
+}
+
+static void fill_fused_args(nf_ctx *c, FusedArgs &a, int g, double *x, const double *jac)
+{
+    memset(&a, 0, sizeof(a));
+    a.r = c->d_r; a.rw = c->d_r; a.jac = jac; a.p = c->d_p; a.yp = c->d_Ap; a.x = x;
+    for (int d = 0; d < 3; ++d) {
+        a.minv[d] = c->d_minv[g * 3 + d]; a.u[d] = c->d_u[g * 3 + d];
+        a.Fy[d] = c->d_F[d][1]; a.Fz[d] = c->d_F[d][2]; a.iFx[d] = c->d_iFx[d];
+    }
+    a.D = c->d_D + (size_t)g * c->ne; a.SigR = c->d_SigR + (size_t)g * c->ne; a.vol = c->d_vol;
+    a.zs = c->d_zs; a.W = c->d_W; a.st = c->d_cg;
+    a.qhead = c->d_fq; a.err = &c->d_cg->pad; a.ticket = (unsigned *)(c->d_fq + 2); a.xdone = c->d_fq + 4;
+    a.items = c->d_items; a.part = c->d_fpart;
+    a.red_part = c->d_part + (size_t)4 * kRedBlocks; a.ticket2 = c->d_ticket + 4;
+    a.ne = c->ne; a.nxy = (long long)c->nx * c->ny; a.nitems = c->fnitems;
+    a.nx = c->nx; a.ny = c->ny; a.nz = c->nz; a.nt = c->nt; a.nloc = c->nloc;
+    a.LcX = c->fLcX; a.RLX = c->fRLX; a.PS = c->fPS; a.LcY = c->fLcY; a.RLY = c->fRLY; a.nX = c->fnX; a.nY = c->fnY;
+    a.pcg = jac ? 1 : 0; a.fin = 1;
+    for (int d = 0; d < 3; ++d)
+        for (int t = 0; t < c->nt; ++t)
+            for (int p = 0; p < c->M1; ++p) a.mode[d][t][p] = c->tmode[d][t][p];
+    for (int t = 0; t < c->nt; ++t) a.w[t] = c->tw[0][t];
+    memcpy(a.wC, c->wC, sizeof(a.wC));
+    memcpy(a.cb, c->cb, sizeof(a.cb));
+}
+
+// which: bit 0 = k_plane_fwd (direction update + x, y sweeps + z forward), bit 1 = k_zback_update
+template <int K, int M1>
+static int fused_launch_t(nf_ctx *c, const FusedArgs &a, int which)
+{
+    if (which & 1) {
+        switch (c->fLW) {
+        case 2: LAUNCH(c, (k_plane_fwd<K, M1, 2>), c->fgrid, kFT, c->fsmem, a); break;
+        case 4: LAUNCH(c, (k_plane_fwd<K, M1, 4>), c->fgrid, kFT, c->fsmem, a); break;
+        case 8: LAUNCH(c, (k_plane_fwd<K, M1, 8>), c->fgrid, kFT, c->fsmem, a); break;
+        }
+    }
+    if (which & 2) {
+        const long long nitems = (long long)c->ny * c->nt * ((c->nx + 31) / 32);
+        const int grid = (int)std::max<long long>(1, std::min<long long>(kRedBlocks, (nitems + 3) / 4));
+        LAUNCH(c, (k_zback_update<K, M1>), grid, 128, 0, a);
+    }
+    CU(c, cudaGetLastError());
+    return NF_OK;
+}
+
+static int fused_launch(nf_ctx *c, const FusedArgs &a, int which)
+{
+#define CALL(KK, MM) fused_launch_t<KK, MM>(c, a, which)
+    NF_ORDER_SWITCH(c, CALL);
+#undef CALL
+}
+
 static int dirichlet_flags(const nf_ctx *c, int *fl)
 {
     // side -> attribute map of the reference (NeutFEM::GetBoundaryAttribute, src/NeutFEM.cpp:2338-2347)
@@ -493,7 +657,9 @@ int nf_destroy(nf_ctx *c)
     for (int d = 0; d < 3; ++d) for (int ax = 0; ax < 3; ++ax) if (c->d_F[d][ax]) cudaFree(c->d_F[d][ax]);
     for (int d = 0; d < 3; ++d) if (c->d_iFx[d]) cudaFree(c->d_iFx[d]);
     for (double *p : c->d_s0) if (p) cudaFree(p);
-    for (double *p : {c->d_E, c->d_Eall, c->d_vG, c->d_vGall}) if (p) cudaFree(p);
+    for (double *p : {c->d_E, c->d_Eall, c->d_vG, c->d_vGall, c->d_zs, c->d_W, c->d_fpart}) if (p) cudaFree(p);
+    if (c->d_fq) cudaFree(c->d_fq);
+    if (c->d_items) cudaFree(c->d_items);
     if (c->comm) ncclCommDestroy(c->comm);
     for (double *p : c->d_minv) if (p) cudaFree(p);
     for (double *p : c->d_u) if (p) cudaFree(p);
@@ -731,6 +897,10 @@ static int solve_group(nf_ctx *c, int g, const double *b, double *x, int *iters_
         { int r = allreduce_sum(c, c->d_cg->tmp, 3); if (r) return r; }
         LAUNCH(c, k_cg_finalize, 1, 1, 0, c->d_cg, 0, tol, pcg ? 1 : 0);
     }
+    { int r = fused_setup(c); if (r) return r; }
+    const bool fused = (c->fused == 1);
+    FusedArgs fa;
+    if (fused) fill_fused_args(c, fa, g, x, jac);
     // poll the device-side done flag every few iterations; iterations after convergence are no-ops on the device
     const double est_us = (double)n * 160.0 / 6.0e6 + 15.0;
     int poll = (int)std::max(1.0, std::min(16.0, 200.0 / est_us));
@@ -739,6 +909,11 @@ static int solve_group(nf_ctx *c, int g, const double *b, double *x, int *iters_
     while (k < maxit && !done) {
         const int chunk = std::min(poll, maxit - k);
         for (int j = 0; j < chunk; ++j) {
+            if (fused) {          // two kernels: direction update + forward sweeps | z back substitution + update
+                int r = fused_launch(c, fa, 3);
+                if (r) return r;
+                continue;
+            }
             { int r = apply_schur(c, g, c->d_p, c->d_Ap, true); if (r) return r; }
             if (!fin) { int r = allreduce_sum(c, c->d_cg->pAp, 4); if (r) return r; }
             if (!pcg) LAUNCH(c, k_cg_update, blocks, 256, 0, c->d_p, c->d_Ap, x, c->d_r, n, c->d_cg, c->d_part + 4 * kRedBlocks, c->d_ticket + 4, fin);
@@ -763,6 +938,7 @@ static int solve_group(nf_ctx *c, int g, const double *b, double *x, int *iters_
     CU(c, cudaEventSynchronize(c->ev3));
     float ms = 0.f;
     cudaEventElapsedTime(&ms, c->ev2, c->ev3);
+    if (c->h_cg->pad) NF_FAIL(c, NF_ERR_STATE, "fused CG kernel: a work-item dependency timed out (internal error)");
     const int iters = c->h_cg->iters;
     const double res = (c->h_cg->bnorm_sq > 0) ? std::sqrt(c->h_cg->rr_true / c->h_cg->bnorm_sq) : 0.0;
     if (iters_out) *iters_out = iters;
@@ -1073,8 +1249,10 @@ int nf_get_diagonal_cache(nf_ctx *c, int g, double *s_inv)
 int nf_time_kernels(nf_ctx *c, int g, int reps, int fast, double *ms_out)
 {
     // Average device time per launch of each hot-path kernel, CUDA events on the context stream, operands resident
-    // in HBM. ms_out[0..2] = x / y / z sweep, [3] = CG update, [4] = CG direction update, [5] = one full CG
-    // iteration (the five launches back to back). Destroys the CG work vectors, not the flux.
+    // in HBM. ms_out[0..2] = x / y / z sweep, [3] = CG update, [4] = CG direction update of the separate-kernel
+    // path, [8] = one CG iteration of that path (five launches); [6] = k_plane_fwd, [7] = k_zback_update of the fused
+    // path (0 if it does not apply), [5] = one CG iteration of the path the solver really uses. ms_out holds 10
+    // doubles. Destroys the CG work vectors, not the flux.
     if (!c || !ms_out || g < 0 || g >= c->ng || reps < 1) return NF_ERR_ARG;
     if (!c->built) NF_FAIL(c, NF_ERR_STATE, "nf_time_kernels: call nf_build first");
     CU(c, cudaSetDevice(c->dev));
@@ -1086,7 +1264,7 @@ int nf_time_kernels(nf_ctx *c, int g, int reps, int fast, double *ms_out)
     const int fin = c->slab ? 0 : 1;
     LAUNCH(c, k_cg_init, blocks, 256, 0, c->d_rhs, c->d_tot, c->d_r, c->d_p, n, 0.0, c->d_cg, c->d_part + 4 * kRedBlocks, c->d_ticket + 4, fin);
     if (!fin) { { int r = allreduce_sum(c, c->d_cg->tmp, 3); if (r) return r; } LAUNCH(c, k_cg_finalize, 1, 1, 0, c->d_cg, 0, 0.0, 0); }
-    for (int i = 0; i < 8; ++i) ms_out[i] = 0.0;
+    for (int i = 0; i < 10; ++i) ms_out[i] = 0.0;
     auto iteration = [&](int mask, bool upd, bool pupd) -> int {
         if (mask) { int r = apply_schur(c, g, c->d_p, c->d_Ap, true, mask); if (r) return r; }
         if (upd) {
@@ -1113,6 +1291,27 @@ int nf_time_kernels(nf_ctx *c, int g, int reps, int fast, double *ms_out)
         float ms = 0.f;
         cudaEventElapsedTime(&ms, c->ev2, c->ev3);
         ms_out[w] = ms / reps;
+    }
+    ms_out[8] = ms_out[5];                       // the separate-kernel iteration
+    { int r = fused_setup(c); if (r) return r; }
+    if (c->fused == 1) {                          // product path on 3-D single-GPU contexts: two fused kernels
+        FusedArgs fa;
+        fill_fused_args(c, fa, g, c->d_tot, jac);
+        { int r = fused_launch(c, fa, 3); if (r) return r; }     // warm-up
+        const int which[3] = {1, 2, 3};
+        const int slot[3] = {6, 7, 5};
+        for (int w = 0; w < 3; ++w) {
+            CU(c, cudaEventRecord(c->ev2, c->stream));
+            for (int i = 0; i < reps; ++i) { int r = fused_launch(c, fa, which[w]); if (r) return r; }
+            CU(c, cudaEventRecord(c->ev3, c->stream));
+            CU(c, cudaEventSynchronize(c->ev3));
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, c->ev2, c->ev3);
+            ms_out[slot[w]] = ms / reps;
+        }
+        CU(c, cudaMemcpyAsync(c->h_cg, c->d_cg, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+        if (c->h_cg->pad) NF_FAIL(c, NF_ERR_STATE, "fused CG kernel: a work-item dependency timed out (internal error)");
     }
     return NF_OK;
 }

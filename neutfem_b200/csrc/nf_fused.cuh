@@ -1,0 +1,556 @@
+// nf_fused.cuh -- the Schur-CG iteration of a 3-D mesh as TWO kernels that stream HBM a minimal number of times.
+//
+// Reference: SchurSolver::SolveSchurImplicit / SchurProduct (src/solvers.cpp:577-636, 535-547): per iteration
+//   Ap = (C + B A^-1 B^T) p ; alpha = rr / p.Ap ; x += alpha p ; r -= alpha Ap ; beta ; p = r + beta p.
+// The separate-kernel path (nf_sweeps.cuh + nf_vector.cuh) moves ~180 B per flux DOF for that. Here:
+//
+//   k_plane_fwd    walks the mesh plane by plane in z (a persistent grid that draws work items from an ordered
+//                  queue). X items own one x line of one plane: they form p = M^-1 r + beta p (the direction update
+//                  of the PREVIOUS iteration, fused), solve the x-direction line systems in shared memory, write
+//                  yp = diag*p + (x part), and advance the z-direction forward substitution by one plane (the carry
+//                  W lives in a two-plane ring that never leaves L2). Y items own a few adjacent y lines of one
+//                  plane: they wait until every X item of that plane has signalled, read p and yp back from L2 (the
+//                  plane was written moments ago) and add the y part. HBM sees r, M^-1, p_old, the line factors and
+//                  the cross-sections once, and p, yp, zs (z-forward intermediates) written once.
+//                  p^T S p is accumulated on the fly from the quadratic form (diag*p^2 + w z^2/m), per work item, and
+//                  summed in item order by the last CTA (deterministic).
+//   k_zback_update marches the z-direction back substitution downwards with one thread per (x, y, transverse pair),
+//                  completes Ap = yp + (z part) in registers and applies x += alpha p, r -= alpha Ap, r.z / r.r in the
+//                  same pass. Ap is never written.
+//
+// Dependencies between work items are counters in global memory (release: __syncthreads + __threadfence + atomicAdd,
+// acquire: ld.acquire + __syncthreads); data that crosses CTAs inside the launch is read with L2-only loads. The
+// queue is drawn in order, every item only depends on items earlier in the queue, and a CTA never holds more than
+// one item, so the scheme cannot deadlock whatever the number of resident CTAs.
+#pragma once
+#include "nf_common.cuh"
+#include "nf_sweeps.cuh"
+#include "nf_vector.cuh"
+
+namespace nf {
+
+constexpr int kFT = 256;        // threads per CTA of k_plane_fwd
+constexpr int kFW = kFT / 32;
+constexpr int kFMaxLW = 8;      // y lines per Y item (template parameter LW) is at most this
+
+struct FusedArgs {
+    const double *r;        // residual (SoA)                    [pass 1: read, pass 2: read+write through rw]
+    const double *jac;      // Jacobi M^-1 (SoA) or nullptr (parity mode: M = I)
+    double *p;              // search direction, updated in place by pass 1
+    double *yp;             // partial S p (everything but the z part)
+    double *x, *rw;         // pass 2: solution and residual (rw == r)
+    const double *minv[3], *u[3];
+    const double *D, *SigR, *vol;
+    const double *Fy[3], *Fz[3], *iFx[3];
+    double *zs;             // [(nz+1)][nt][ny][nx] z-forward intermediates
+    double *W;              // [2][nt][ny][nx] carry of the z-forward recurrence (ring over planes)
+    CgState *st;
+    int *qhead, *xdone, *err;
+    const int2 *items;      // .x = plane*2 + (1 if Y item), .y = line / x-block index
+    double *part;           // [nitems] per-item partials of p^T S p
+    unsigned *ticket;
+    double *red_part;       // pass 2 block partials
+    unsigned *ticket2;
+    long long ne, nxy;
+    int nitems;
+    int nx, ny, nz, nt, nloc;
+    int LcX, RLX, PS;       // x lines: chunk length per thread, padded line length, row length of P
+    int LcY, RLY;           // y lines
+    int nX, nY;             // items per plane
+    int pcg, fin;
+    int mode[3][kMaxT][3];
+    double w[kMaxT];        // transverse Legendre weight of pair t (the same table for the three directions)
+    double wC[kMaxModes];
+    double cb[3][kMaxModes];
+};
+
+__device__ __forceinline__ void cp_async16_cg(double *smem_dst, const double *gsrc)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gsrc) : "memory");
+}
+
+__device__ __forceinline__ int ld_acquire_gpu(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// block-wide wait until *cnt >= target (bounded: a lost signal raises *err instead of hanging the GPU)
+__device__ __forceinline__ void wait_count(const int *cnt, int target, int *err)
+{
+    if (threadIdx.x == 0) {
+        unsigned spins = 0;
+        while (ld_acquire_gpu(cnt) < target) {
+            __nanosleep(200);
+            if (*(volatile int *)err) break;                       // somebody already gave up: drain the queue quickly
+            if (++spins > (1u << 22)) { atomicExch(err, 1); break; }
+        }
+    }
+    __syncthreads();
+}
+
+// Solves the condensed tridiagonal systems of LW lines held in shared memory, layout [face][line] (index f*LW + l).
+// T: in rhs T_f, out J_f. MINV[f] = 1/m_f, UB[f] = u_{f-1} (row 0 = 0, so UB[f + 1 row] = u_f). Every thread owns
+// Lc consecutive faces of one line; the chunks are stitched exactly with a scan of affine maps (warp shuffles, then
+// one shared-memory hop across the warps). Rows past the end of a line hold zeros. Returns this thread's share of
+// sum_f z_f^2 / m_f. Ends with a __syncthreads().
+template <int LW>
+__device__ __forceinline__ double tile_solve(double *__restrict__ T, const double *__restrict__ MINV,
+                                             const double *__restrict__ UB, const int Lc, double *wsA, double *wsB)
+{
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int l = tid % LW, k = tid / LW;
+    const int i0 = k * Lc * LW + l;
+    double q = 0.0;
+    {   // forward substitution z_f = T_f - u_{f-1} z_{f-1}
+        double z = 0.0, A = 1.0;
+        for (int j = 0; j < Lc; ++j) {
+            const double um = UB[i0 + j * LW];
+            z = T[i0 + j * LW] - um * z;
+            A *= -um;
+        }
+#pragma unroll
+        for (int s = LW; s < 32; s <<= 1) {
+            const double Ap = __shfl_up_sync(0xffffffffu, A, s), zp = __shfl_up_sync(0xffffffffu, z, s);
+            if (lane >= s) { z = A * zp + z; A = A * Ap; }
+        }
+        if (lane >= 32 - LW) { wsA[wid * LW + l] = A; wsB[wid * LW + l] = z; }
+        double Aex = __shfl_up_sync(0xffffffffu, A, LW), zex = __shfl_up_sync(0xffffffffu, z, LW);
+        if (lane < LW) { Aex = 1.0; zex = 0.0; }
+        __syncthreads();
+        double c = 0.0;
+        for (int ww = 0; ww < wid; ++ww) c = wsA[ww * LW + l] * c + wsB[ww * LW + l];
+        z = Aex * c + zex;
+        for (int j = 0; j < Lc; ++j) {
+            const int i = i0 + j * LW;
+            z = T[i] - UB[i] * z;
+            T[i] = z;
+            q += z * z * MINV[i];
+        }
+    }
+    __syncthreads();
+    {   // backward substitution J_f = z_f/m_f - u_f J_{f+1}
+        double J = 0.0, Bp = 1.0;
+        for (int j = Lc - 1; j >= 0; --j) {
+            const int i = i0 + j * LW;
+            const double uf = UB[i + LW];
+            J = MINV[i] * T[i] - uf * J;
+            Bp *= -uf;
+        }
+#pragma unroll
+        for (int s = LW; s < 32; s <<= 1) {
+            const double Bq = __shfl_down_sync(0xffffffffu, Bp, s), Jq = __shfl_down_sync(0xffffffffu, J, s);
+            if (lane + s < 32) { J = Bp * Jq + J; Bp = Bp * Bq; }
+        }
+        if (lane < LW) { wsA[wid * LW + l] = Bp; wsB[wid * LW + l] = J; }
+        double Bex = __shfl_down_sync(0xffffffffu, Bp, LW), Jex = __shfl_down_sync(0xffffffffu, J, LW);
+        if (lane >= 32 - LW) { Bex = 1.0; Jex = 0.0; }
+        __syncthreads();
+        double c = 0.0;
+        for (int ww = kFW - 1; ww > wid; --ww) c = wsA[ww * LW + l] * c + wsB[ww * LW + l];
+        J = Bex * c + Jex;
+        for (int j = Lc - 1; j >= 0; --j) {
+            const int i = i0 + j * LW;
+            J = MINV[i] * T[i] - UB[i + LW] * J;
+            T[i] = J;
+        }
+    }
+    __syncthreads();
+    return q;
+}
+
+// contribution of one cell to the face rhs of its two faces: T_f = lo(cell f-1) - hi(cell f)  (cf. face_rhs)
+template <int K, int M1>
+__device__ __forceinline__ void cell_lo_hi(double x0, double x1, double x2, double &lo, double &hi)
+{
+    lo = x0; hi = x0;
+    if (K >= 1 && M1 >= 2) { const double tb0 = -(4.0 / 3.0) * x1; lo -= 0.625 * tb0; hi += 0.625 * tb0; }
+    if (K >= 2 && M1 >= 3) { const double tb1 = -(4.0 / 5.0) * x2; lo -= 0.875 * tb1; hi -= 0.875 * tb1; }
+}
+
+// ---- X item: one x line (iy, iz), all modes ------------------------------------------------------------------------
+template <int K, int M1>
+__device__ __forceinline__ void fused_x_item(const FusedArgs &a, const int iz, const int iy, const double beta,
+                                             double *sm, double *wsA, double *wsB, double &acc)
+{
+    const int tid = threadIdx.x;
+    const int n = a.nx, RL = a.RLX, Lc = a.LcX, PS = a.PS, nloc = a.nloc, nt = a.nt;
+    double *MINV = sm;             // [RL]
+    double *UB = MINV + RL;        // [RL + 2]  UB[1 + f] = u_f
+    double *T = UB + RL + 2;       // [RL]
+    double *DV = T + RL;           // [PS]
+    double *SV = DV + PS;          // [PS]
+    double *VV = SV + PS;          // [PS]
+    double *P = VV + PS;           // [nloc][PS]
+    const long long line = (long long)iz * a.ny + iy;
+    const long long e0 = line * n;
+    {
+        const double *gm = a.minv[0] + line * (n + 1), *gu = a.u[0] + line * (n + 1);
+        for (int f = tid; f < RL; f += kFT) {
+            if (f <= n) cp_async8(MINV + f, gm + f); else MINV[f] = 0.0;
+            if (f < n) {
+                cp_async8(UB + 1 + f, gu + f); cp_async8(DV + f, a.D + e0 + f);
+                cp_async8(SV + f, a.SigR + e0 + f); cp_async8(VV + f, a.vol + e0 + f);
+            } else UB[1 + f] = 0.0;
+            T[f] = 0.0;
+        }
+        if (tid == 0) UB[0] = 0.0;
+    }
+    // ---- direction update p = M^-1 r + beta p for every mode of the line (k_(p)cg_pupdate of the separate path)
+    {
+        constexpr int MB = 4;
+        const bool pcg = a.pcg != 0, hasb = (beta != 0.0);
+        for (int f = tid; f < n; f += kFT) {
+            for (int m0 = 0; m0 < nloc; m0 += MB) {
+                double rv[MB], jv[MB], po[MB];
+#pragma unroll
+                for (int j = 0; j < MB; ++j) {
+                    rv[j] = 0.0; jv[j] = 1.0; po[j] = 0.0;
+                    if (m0 + j < nloc) {
+                        const size_t o = (size_t)(m0 + j) * a.ne + e0 + f;
+                        rv[j] = __ldg(a.r + o);
+                        if (pcg) jv[j] = __ldg(a.jac + o);
+                        if (hasb) po[j] = a.p[o];
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < MB; ++j) {
+                    if (m0 + j < nloc) {
+                        const size_t o = (size_t)(m0 + j) * a.ne + e0 + f;
+                        const double pn = jv[j] * rv[j] + beta * po[j];
+                        P[(m0 + j) * PS + f] = pn;
+                        a.p[o] = pn;
+                    }
+                }
+            }
+        }
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    const double ify0 = 1.0 / (a.Fy[0][iy] * a.Fz[0][iz]);
+    const double ify1 = 1.0 / (a.Fy[1][iy] * a.Fz[1][iz]);
+    const double ify2 = 1.0 / (a.Fy[2][iy] * a.Fz[2][iz]);
+    // ---- x-direction line systems, one transverse pair at a time
+    for (int t = 0; t < nt; ++t) {
+        const double w = a.w[t];
+        int md[3];
+        double wc[3], c0[3], c1[3], c2[3];
+#pragma unroll
+        for (int p = 0; p < M1; ++p) {
+            md[p] = a.mode[0][t][p];
+            wc[p] = a.wC[md[p]]; c0[p] = a.cb[0][md[p]] * ify0; c1[p] = a.cb[1][md[p]] * ify1; c2[p] = a.cb[2][md[p]] * ify2;
+        }
+        const double *P0 = P + md[0] * PS, *P1 = P + md[M1 >= 2 ? 1 : 0] * PS, *P2 = P + md[M1 >= 3 ? 2 : 0] * PS;
+        for (int f = tid; f <= n; f += kFT) {
+            double lom = 0.0, hi = 0.0, dum;
+            if (f > 0) cell_lo_hi<K, M1>(P0[f - 1], P1[f - 1], P2[f - 1], lom, dum);
+            if (f < n) cell_lo_hi<K, M1>(P0[f], P1[f], P2[f], dum, hi);
+            T[f] = lom - hi;
+        }
+        __syncthreads();
+        acc += w * tile_solve<1>(T, MINV, UB, Lc, wsA, wsB);
+        for (int f = tid; f < n; f += kFT) {
+            const double JL = T[f], JR = T[f + 1];
+            const double Dv = DV[f], Sv = SV[f] * VV[f];
+            const double q0 = Dv * __ldg(a.iFx[0] + f), q1 = Dv * __ldg(a.iFx[1] + f), q2 = Dv * __ldg(a.iFx[2] + f);
+            double sol[3];
+            sol[0] = w * (JR - JL);
+            sol[1] = (K >= 1) ? w * (5.0 / 6.0) * (JL + JR) : 0.0;
+            sol[2] = (K >= 2) ? w * (7.0 / 10.0) * (JR - JL) : 0.0;
+#pragma unroll
+            for (int p = 0; p < M1; ++p) {
+                const double xv = P[md[p] * PS + f];
+                const double dg = Sv * wc[p] + q0 * c0[p] + q1 * c1[p] + q2 * c2[p];
+                const double yv = dg * xv;
+                acc += yv * xv;
+                a.yp[(size_t)md[p] * a.ne + e0 + f] = yv + sol[p];
+            }
+        }
+        __syncthreads();
+    }
+    // ---- z-direction forward substitution, one plane step:  z_iz = W_{iz-1} - hi(iz),  W_iz = lo(iz) - u_iz z_iz
+    if (iz > 0) wait_count(a.xdone + (iz - 1), a.nX, a.err);
+    {
+        const long long cxy = (long long)iy * n;
+        const double *uz = a.u[2] + (long long)iz * a.nxy + cxy;
+        const double *mz = a.minv[2] + (long long)iz * a.nxy + cxy;
+        const double *mzn = a.minv[2] + (long long)(iz + 1) * a.nxy + cxy;
+        const double *Wprev = a.W + (size_t)((iz + 1) & 1) * nt * a.nxy + cxy;
+        double *Wcur = a.W + (size_t)(iz & 1) * nt * a.nxy + cxy;
+        double *zcur = a.zs + (size_t)iz * nt * a.nxy + cxy;
+        double *zlast = a.zs + (size_t)a.nz * nt * a.nxy + cxy;
+        const bool last = (iz == a.nz - 1);
+        for (int i = tid; i < nt * n; i += kFT) {
+            const int t = i / n, ix = i - t * n;
+            const int m0 = a.mode[2][t][0], m1 = a.mode[2][t][M1 >= 2 ? 1 : 0], m2 = a.mode[2][t][M1 >= 3 ? 2 : 0];
+            double lo, hi;
+            cell_lo_hi<K, M1>(P[m0 * PS + ix], P[m1 * PS + ix], P[m2 * PS + ix], lo, hi);
+            const double wp = (iz > 0) ? __ldcg(Wprev + (size_t)t * a.nxy + ix) : 0.0;
+            const double z = wp - hi;
+            const double uu = __ldg(uz + ix), mm = __ldg(mz + ix);
+            double q = z * z * mm;
+            zcur[(size_t)t * a.nxy + ix] = z;
+            const double Wv = lo - uu * z;
+            if (last) { zlast[(size_t)t * a.nxy + ix] = Wv; q += Wv * Wv * __ldg(mzn + ix); }
+            else Wcur[(size_t)t * a.nxy + ix] = Wv;
+            acc += a.w[t] * q;
+        }
+    }
+}
+
+// ---- Y item: LW adjacent y lines (x block xb) of plane iz, all transverse pairs ----------------------------------------
+template <int K, int M1, int LW>
+__device__ __forceinline__ void fused_y_item(const FusedArgs &a, const int iz, const int xb, double *sm, double *wsA,
+                                             double *wsB, double &acc)
+{
+    const int tid = threadIdx.x;
+    const int n = a.ny, nx = a.nx, RL = a.RLY, Lc = a.LcY, nt = a.nt;
+    const int ix0 = xb * LW;
+    const int ncol = min(LW, nx - ix0);
+    double *MINV = sm;                   // [RL][LW]
+    double *UB = MINV + RL * LW;         // [RL + 1][LW]
+    double *T = UB + (RL + 1) * LW;      // [RL][LW]
+    double *PT = T + RL * LW;            // [M1][n + 1][LW]   (row n = 0)
+    const int PTS = (n + 1) * LW;
+    const bool al16 = (LW % 2 == 0) && ((nx & 1) == 0) && (ncol == LW);
+    {   // line factors (constant during the solve: cached loads)
+        const double *gm = a.minv[1] + (size_t)iz * (n + 1) * nx + ix0;
+        const double *gu = a.u[1] + (size_t)iz * (n + 1) * nx + ix0;
+        for (int e = tid; e < RL * LW; e += kFT) {
+            const int f = e / LW, l = e - f * LW;
+            if (f <= n && l < ncol) { cp_async8(MINV + e, gm + (size_t)f * nx + l); cp_async8(UB + LW + e, gu + (size_t)f * nx + l); }
+            else { MINV[e] = 0.0; UB[LW + e] = 0.0; }
+            T[e] = 0.0;
+        }
+        if (tid < LW) UB[tid] = 0.0;
+    }
+    wait_count(a.xdone + iz, a.nX, a.err);      // p and yp of this plane are complete
+    const size_t cell0 = (size_t)iz * n * nx + ix0;
+    for (int t = 0; t < nt; ++t) {
+        const double w = a.w[t];
+        int md[3];
+#pragma unroll
+        for (int p = 0; p < M1; ++p) md[p] = a.mode[1][t][p];
+        // ---- stage p of this pair (written by other CTAs during this launch: L2-only loads)
+#pragma unroll
+        for (int p = 0; p < M1; ++p) {
+            const double *gp = a.p + (size_t)md[p] * a.ne + cell0;
+            double *dst = PT + p * PTS;
+            if (al16) {
+                for (int e = tid * 2; e < n * LW; e += kFT * 2) {
+                    const int f = e / LW, l = e - f * LW;
+                    cp_async16_cg(dst + e, gp + (size_t)f * nx + l);
+                }
+            } else {
+                for (int e = tid; e < n * LW; e += kFT) {
+                    const int f = e / LW, l = e - f * LW;
+                    dst[e] = (l < ncol) ? __ldcg(gp + (size_t)f * nx + l) : 0.0;
+                }
+            }
+            if (tid < LW) dst[n * LW + tid] = 0.0;
+        }
+        cp_async_wait_all();
+        __syncthreads();
+        {
+            const double *P0 = PT, *P1 = PT + (M1 >= 2 ? 1 : 0) * PTS, *P2 = PT + (M1 >= 3 ? 2 : 0) * PTS;
+            for (int e = tid; e < (n + 1) * LW; e += kFT) {
+                double lom = 0.0, hi = 0.0, dum;
+                if (e >= LW) cell_lo_hi<K, M1>(P0[e - LW], P1[e - LW], P2[e - LW], lom, dum);
+                if (e < n * LW) cell_lo_hi<K, M1>(P0[e], P1[e], P2[e], dum, hi);
+                T[e] = lom - hi;
+            }
+        }
+        __syncthreads();
+        acc += w * tile_solve<LW>(T, MINV, UB, Lc, wsA, wsB);
+        // ---- yp += w B J   (read-modify-write in L2)
+        constexpr int UB4 = 4;
+        for (int eb = tid; eb < n * LW; eb += kFT * UB4) {
+            double yv[UB4][3];
+            size_t go[UB4];
+            bool ok[UB4];
+#pragma unroll
+            for (int j = 0; j < UB4; ++j) {
+                const int e = eb + j * kFT;
+                const int f = e / LW, l = e - f * LW;
+                ok[j] = (e < n * LW) && (l < ncol);
+                go[j] = cell0 + (size_t)f * nx + l;
+                if (ok[j]) {
+#pragma unroll
+                    for (int p = 0; p < M1; ++p) yv[j][p] = __ldcg(a.yp + (size_t)md[p] * a.ne + go[j]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < UB4; ++j) {
+                if (ok[j]) {
+                    const int e = eb + j * kFT;
+                    const double JL = T[e], JR = T[e + LW];
+                    double sol[3];
+                    sol[0] = w * (JR - JL);
+                    sol[1] = (K >= 1) ? w * (5.0 / 6.0) * (JL + JR) : 0.0;
+                    sol[2] = (K >= 2) ? w * (7.0 / 10.0) * (JR - JL) : 0.0;
+#pragma unroll
+                    for (int p = 0; p < M1; ++p) a.yp[(size_t)md[p] * a.ne + go[j]] = yv[j][p] + sol[p];
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <int K, int M1, int LW>
+__global__ void __launch_bounds__(kFT, 2) k_plane_fwd(const FusedArgs a)
+{
+    if (a.st->done) return;
+    extern __shared__ __align__(16) double sm[];
+    __shared__ double wsA[kFW * kFMaxLW], wsB[kFW * kFMaxLW];
+    __shared__ double s_red[kFW];
+    __shared__ int s_item, s_last;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const double beta = a.st->beta;
+    for (;;) {
+        if (tid == 0) s_item = atomicAdd(a.qhead, 1);
+        __syncthreads();
+        const int item = s_item;
+        if (item >= a.nitems) break;
+        const int2 it = a.items[item];
+        const int plane = it.x >> 1;
+        const bool isY = (it.x & 1) != 0;
+        double acc = 0.0;
+        if (isY) fused_y_item<K, M1, LW>(a, plane, it.y, sm, wsA, wsB, acc);
+        else fused_x_item<K, M1>(a, plane, it.y, beta, sm, wsA, wsB, acc);
+        acc = warp_sum(acc);
+        if (lane == 0) s_red[wid] = acc;
+        __syncthreads();                      // also: every global store of the item has been issued
+        if (tid == 0) {
+            double s = 0.0;
+#pragma unroll
+            for (int ww = 0; ww < kFW; ++ww) s += s_red[ww];
+            a.part[plane * (a.nX + a.nY) + (isY ? a.nX : 0) + it.y] = s;      // canonical slot: queue order does not matter
+            if (!isY) { __threadfence(); atomicAdd(a.xdone + plane, 1); }
+        }
+        __syncthreads();
+    }
+    // ---- the last CTA to run dry sums the per-item partials in item order and re-arms the queue
+    if (tid == 0) {
+        __threadfence();
+        const unsigned tk = atomicAdd(a.ticket, 1u);
+        s_last = (tk == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    double s = 0.0;
+    for (int i = tid; i < a.nitems; i += kFT) s += __ldcg(a.part + i);
+    s = warp_sum(s);
+    if (lane == 0) s_red[wid] = s;
+    for (int i = tid; i < a.nz; i += kFT) a.xdone[i] = 0;
+    __syncthreads();
+    if (tid == 0) {
+        double tot = 0.0;
+#pragma unroll
+        for (int ww = 0; ww < kFW; ++ww) tot += s_red[ww];
+        a.st->pAp[0] = tot; a.st->pAp[1] = 0.0; a.st->pAp[2] = 0.0; a.st->pAp[3] = 0.0;
+        *a.qhead = 0;
+        *a.ticket = 0u;
+        __threadfence();
+    }
+}
+
+// ---- pass 2: z back substitution + CG update ----------------------------------------------------------------------------
+// One thread per (ix, iy, transverse pair of the z direction), marching from the top plane down. For every cell:
+// Ap = yp + w B_z J ; x += alpha p ; r -= alpha Ap ; accumulates r.M^-1 r and r.r (solvers.cpp:601-631).
+#ifndef NF_ZB_UNR
+#define NF_ZB_UNR 2
+#endif
+template <int K, int M1>
+__global__ void __launch_bounds__(128, 4) k_zback_update(const FusedArgs a)
+{
+    CgState *st = a.st;
+    if (st->done) return;
+    const double pAp = (st->pAp[0] + st->pAp[1]) + (st->pAp[2] + st->pAp[3]);
+    if (fabs(pAp) < (a.pcg ? 1e-300 : 1e-30)) {        // breakdown guard, solvers.cpp:605
+        __syncthreads();
+        if (blockIdx.x == 0 && threadIdx.x == 0) { st->breakdown = 1; st->done = 1; }
+        return;
+    }
+    constexpr int UNR = NF_ZB_UNR;
+    const double alpha = st->rr / pAp;
+    const bool pcg = a.pcg != 0;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, WPB = blockDim.x >> 5;
+    const int nz = a.nz, nt = a.nt;
+    const int nxb = (a.nx + 31) >> 5;
+    const long long nitems = (long long)a.ny * nt * nxb;
+    const long long sxy = a.nxy;
+    double acc[2] = {0.0, 0.0};
+    for (long long item = (long long)blockIdx.x * WPB + wib; item < nitems; item += (long long)gridDim.x * WPB) {
+        const int xb = (int)(item % nxb);
+        const long long rr = item / nxb;
+        const int t = (int)(rr % nt);
+        const int iy = (int)(rr / nt);
+        const int ix = xb * 32 + lane;
+        if (ix >= a.nx) continue;
+        const double w = a.w[t];
+        const long long c0 = (long long)iy * a.nx + ix;
+        const double *__restrict__ zp = a.zs + (size_t)t * sxy + c0;       // + f * nt * sxy
+        const double *__restrict__ um = a.u[2] + c0;                       // + f * sxy
+        const double *__restrict__ mi = a.minv[2] + c0;
+        size_t mo[3];
+#pragma unroll
+        for (int p = 0; p < 3; ++p) mo[p] = (size_t)a.mode[2][t][p < M1 ? p : 0] * a.ne + c0;
+        double Jn = 0.0;
+        for (int fb = nz; fb >= 0; fb -= UNR) {
+            double lz[UNR], lu[UNR], lm[UNR], ly[UNR][3], lp[UNR][3], lx[UNR][3], lr[UNR][3], lj[UNR][3];
+#pragma unroll
+            for (int j = 0; j < UNR; ++j) {
+                const int f = fb - j;
+                lz[j] = lu[j] = lm[j] = 0.0;
+                if (f >= 0) {
+                    lz[j] = __ldg(zp + (size_t)f * nt * sxy); lu[j] = __ldg(um + (size_t)f * sxy); lm[j] = __ldg(mi + (size_t)f * sxy);
+                    if (f < nz) {
+#pragma unroll
+                        for (int p = 0; p < M1; ++p) {
+                            const size_t o = mo[p] + (size_t)f * sxy;
+                            ly[j][p] = __ldg(a.yp + o); lp[j][p] = __ldg(a.p + o);
+                            lx[j][p] = a.x[o]; lr[j][p] = a.rw[o];
+                            lj[j][p] = pcg ? __ldg(a.jac + o) : 1.0;
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < UNR; ++j) {
+                const int f = fb - j;
+                if (f >= 0) {
+                    const double J = lm[j] * lz[j] - lu[j] * Jn;
+                    if (f < nz) {
+                        double sol[3];
+                        sol[0] = w * (Jn - J);
+                        sol[1] = (K >= 1) ? w * (5.0 / 6.0) * (J + Jn) : 0.0;
+                        sol[2] = (K >= 2) ? w * (7.0 / 10.0) * (Jn - J) : 0.0;
+#pragma unroll
+                        for (int p = 0; p < M1; ++p) {
+                            const size_t o = mo[p] + (size_t)f * sxy;
+                            const double Apv = ly[j][p] + sol[p];
+                            a.x[o] = lx[j][p] + alpha * lp[j][p];
+                            const double rv = lr[j][p] - alpha * Apv;
+                            a.rw[o] = rv;
+                            acc[0] += rv * rv * lj[j][p];
+                            acc[1] += rv * rv;
+                        }
+                    }
+                    Jn = J;
+                }
+            }
+        }
+    }
+    __shared__ double out[2];
+    if (grid_reduce<2>(acc, a.red_part, a.ticket2, out) && threadIdx.x == 0) {
+        if (pcg) { st->tmp[0] = out[0]; st->tmp[1] = out[1]; }
+        else { st->tmp[0] = out[1]; }
+        if (a.fin) cg_update_fin(st, a.pcg);
+    }
+}
+
+}  // namespace nf
