@@ -69,10 +69,10 @@ struct nf_ctx {
     double *d_vG = nullptr, *d_vGall = nullptr;    // [2][nt][nxy], [nranks][2][nt][nxy]
     // ---- fused two-kernel CG iteration (nf_fused.cuh), 3-D single-GPU contexts
     int fused = -1;                        // -1: not yet decided, 0: unavailable / disabled, 1: ready
-    int fLW = 4, fLcX = 1, fRLX = 0, fPS = 0, fLcY = 1, fRLY = 0, fnX = 0, fnY = 0, fnitems = 0, fgrid = 0;
+    int fLW = 4, fLcX = 1, fTS = 0, fPS = 0, fLcY = 1, fnX = 0, fnY = 0, fnitems = 0, fgrid = 0;
     size_t fsmem = 0;
     double *d_zs = nullptr, *d_W = nullptr, *d_fpart = nullptr;
-    int *d_fq = nullptr;                   // [0] queue head, [1] error flag, [2] ticket, [4..4+nz) plane counters
+    int *d_fq = nullptr;                   // [0] queue head, [2] ticket, [4..4+nz) plane counters, then ny row counters
     int2 *d_items = nullptr;
 };
 
@@ -344,16 +344,24 @@ static int fused_setup(nf_ctx *c)
 {
     if (c->fused >= 0) return NF_OK;
     c->fused = 0;
-    if (c->dim != 3 || c->slab || env_int("NF_FUSED", 1) == 0) return NF_OK;
+    const int want_mode = env_int("NF_FUSED", 1);
+    if (c->dim != 3 || c->slab || want_mode == 0) return NF_OK;
+    if (want_mode == 2) {                 // hybrid: separate x / y sweeps + k_zfwd + k_zback_update
+        const size_t nxy2 = (size_t)c->nx * c->ny;
+        { int r = dalloc(c, &c->d_zs, (size_t)(c->nz + 1) * c->nt * nxy2); if (r) return r; }
+        c->fused = 2;
+        return NF_OK;
+    }
     int LW = env_int("NF_FUSED_LW", 4);
     if (LW != 2 && LW != 4 && LW != 8) LW = 4;
     c->fLW = LW;
-    auto chunk = [](int n, int cpl, int &Lc, int &RL) { Lc = (n + 1 + cpl - 1) / cpl; Lc |= 1; RL = cpl * Lc; };
-    chunk(c->nx, kFT, c->fLcX, c->fRLX);
-    chunk(c->ny, kFT / LW, c->fLcY, c->fRLY);
-    c->fPS = (c->nx + 2) & ~1;
-    const size_t smemX = ((size_t)3 * c->fRLX + 2 + (size_t)(3 + c->nloc) * c->fPS) * sizeof(double);
-    const size_t smemY = (((size_t)3 * c->fRLY + 1) * LW + (size_t)c->M1 * (c->ny + 1) * LW) * sizeof(double);
+    const int GX = (c->M1 == 1) ? 1 : 4;           // transverse pairs of an x line solved side by side
+    c->fLcX = ((c->nx + 1 + kFT / GX - 1) / (kFT / GX)) | 1;
+    c->fLcY = ((c->ny + 1 + kFT / LW - 1) / (kFT / LW)) | 1;
+    c->fTS = (c->nx + 3) & ~1;
+    c->fPS = (c->nx + 1) & ~1;
+    const size_t smemX = ((size_t)(2 + GX) * c->fTS + (size_t)(3 + c->nloc) * c->fPS) * sizeof(double);
+    const size_t smemY = (size_t)4 * (c->ny + 2) * LW * sizeof(double);
     const size_t smem = (std::max(smemX, smemY) + 15) & ~(size_t)15;
     if (smem + 4096 > c->smem_optin) return NF_OK;               // lines too long for shared memory: separate kernels
     int per_sm = 0;
@@ -363,7 +371,7 @@ static int fused_setup(nf_ctx *c)
     if (want > 0) per_sm = std::min(per_sm, want);
     c->fsmem = smem;
     c->fgrid = per_sm * c->sm_count;
-    const int nX = c->ny, nY = (c->nx + LW - 1) / LW, nz = c->nz;
+    const int nX = c->ny, nY = ((c->nx + LW - 1) / LW) * c->nt, nz = c->nz;
     c->fnX = nX; c->fnY = nY;
     const int delay = env_int("NF_FUSED_DELAY", 1) ? 1 : 0;
     int lag = env_int("NF_FUSED_LAG", nX / 2);
@@ -387,9 +395,9 @@ static int fused_setup(nf_ctx *c)
     { int r = dalloc(c, &c->d_zs, (size_t)(nz + 1) * c->nt * nxy); if (r) return r; }
     { int r = dalloc(c, &c->d_W, (size_t)2 * c->nt * nxy); if (r) return r; }
     { int r = dalloc(c, &c->d_fpart, (size_t)c->fnitems); if (r) return r; }
-    { int r = dalloc(c, &c->d_fq, (size_t)nz + 8); if (r) return r; }
+    { int r = dalloc(c, &c->d_fq, (size_t)nz + c->ny + 8); if (r) return r; }
     { int r = dalloc(c, &c->d_items, items.size()); if (r) return r; }
-    CU(c, cudaMemsetAsync(c->d_fq, 0, ((size_t)nz + 8) * sizeof(int), c->stream));
+    CU(c, cudaMemsetAsync(c->d_fq, 0, ((size_t)nz + c->ny + 8) * sizeof(int), c->stream));
     CU(c, cudaMemcpyAsync(c->d_items, items.data(), items.size() * sizeof(int2), cudaMemcpyHostToDevice, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
     c->fused = 1;
@@ -407,11 +415,12 @@ static void fill_fused_args(nf_ctx *c, FusedArgs &a, int g, double *x, const dou
     a.D = c->d_D + (size_t)g * c->ne; a.SigR = c->d_SigR + (size_t)g * c->ne; a.vol = c->d_vol;
     a.zs = c->d_zs; a.W = c->d_W; a.st = c->d_cg;
     a.qhead = c->d_fq; a.err = &c->d_cg->pad; a.ticket = (unsigned *)(c->d_fq + 2); a.xdone = c->d_fq + 4;
+    a.rowdone = c->d_fq + 4 + c->nz;
     a.items = c->d_items; a.part = c->d_fpart;
     a.red_part = c->d_part + (size_t)4 * kRedBlocks; a.ticket2 = c->d_ticket + 4;
     a.ne = c->ne; a.nxy = (long long)c->nx * c->ny; a.nitems = c->fnitems;
     a.nx = c->nx; a.ny = c->ny; a.nz = c->nz; a.nt = c->nt; a.nloc = c->nloc;
-    a.LcX = c->fLcX; a.RLX = c->fRLX; a.PS = c->fPS; a.LcY = c->fLcY; a.RLY = c->fRLY; a.nX = c->fnX; a.nY = c->fnY;
+    a.LcX = c->fLcX; a.TS = c->fTS; a.PS = c->fPS; a.LcY = c->fLcY; a.nX = c->fnX; a.nY = c->fnY;
     a.pcg = jac ? 1 : 0; a.fin = 1;
     for (int d = 0; d < 3; ++d)
         for (int t = 0; t < c->nt; ++t)
@@ -431,6 +440,11 @@ static int fused_launch_t(nf_ctx *c, const FusedArgs &a, int which)
         case 4: LAUNCH(c, (k_plane_fwd<K, M1, 4>), c->fgrid, kFT, c->fsmem, a); break;
         case 8: LAUNCH(c, (k_plane_fwd<K, M1, 8>), c->fgrid, kFT, c->fsmem, a); break;
         }
+    }
+    if (which & 4) {
+        const long long nitems = (long long)c->ny * c->nt * ((c->nx + 31) / 32);
+        const int grid = (int)std::max<long long>(1, std::min<long long>(kRedBlocks, (nitems + 3) / 4));
+        LAUNCH(c, (k_zfwd<K, M1>), grid, 128, 0, a, c->d_part + (size_t)2 * kRedBlocks, c->d_ticket + 2, &c->d_cg->pAp[2]);
     }
     if (which & 2) {
         const long long nitems = (long long)c->ny * c->nt * ((c->nx + 31) / 32);
@@ -898,9 +912,9 @@ static int solve_group(nf_ctx *c, int g, const double *b, double *x, int *iters_
         LAUNCH(c, k_cg_finalize, 1, 1, 0, c->d_cg, 0, tol, pcg ? 1 : 0);
     }
     { int r = fused_setup(c); if (r) return r; }
-    const bool fused = (c->fused == 1);
+    const bool fused = (c->fused == 1), hybrid = (c->fused == 2);
     FusedArgs fa;
-    if (fused) fill_fused_args(c, fa, g, x, jac);
+    if (fused || hybrid) fill_fused_args(c, fa, g, x, jac);
     // poll the device-side done flag every few iterations; iterations after convergence are no-ops on the device
     const double est_us = (double)n * 160.0 / 6.0e6 + 15.0;
     int poll = (int)std::max(1.0, std::min(16.0, 200.0 / est_us));
@@ -912,6 +926,13 @@ static int solve_group(nf_ctx *c, int g, const double *b, double *x, int *iters_
             if (fused) {          // two kernels: direction update + forward sweeps | z back substitution + update
                 int r = fused_launch(c, fa, 3);
                 if (r) return r;
+                continue;
+            }
+            if (hybrid) {         // direction update, x and y sweeps as separate kernels, then z forward | z back + update
+                if (!pcg) LAUNCH(c, k_cg_pupdate, blocks, 256, 0, c->d_r, c->d_p, n, c->d_cg);
+                else LAUNCH(c, k_pcg_pupdate, blocks, 256, 0, c->d_r, jac, c->d_p, n, c->d_cg);
+                { int r = apply_schur(c, g, c->d_p, c->d_Ap, true, 3); if (r) return r; }
+                { int r = fused_launch(c, fa, 4 | 2); if (r) return r; }
                 continue;
             }
             { int r = apply_schur(c, g, c->d_p, c->d_Ap, true); if (r) return r; }
@@ -1294,6 +1315,30 @@ int nf_time_kernels(nf_ctx *c, int g, int reps, int fast, double *ms_out)
     }
     ms_out[8] = ms_out[5];                       // the separate-kernel iteration
     { int r = fused_setup(c); if (r) return r; }
+    if (c->fused == 2) {                          // hybrid path: separate direction update, x, y sweeps + k_zfwd + k_zback_update
+        FusedArgs fa;
+        fill_fused_args(c, fa, g, c->d_tot, jac);
+        auto hyb = [&](int what) -> int {          // 1: pupdate + x + y, 4: z forward, 2: z back + update
+            if (what & 1) {
+                if (!fast) LAUNCH(c, k_cg_pupdate, blocks, 256, 0, c->d_r, c->d_p, n, c->d_cg);
+                else LAUNCH(c, k_pcg_pupdate, blocks, 256, 0, c->d_r, jac, c->d_p, n, c->d_cg);
+                int r = apply_schur(c, g, c->d_p, c->d_Ap, true, 3); if (r) return r;
+            }
+            return fused_launch(c, fa, what & 6);
+        };
+        { int r = hyb(7); if (r) return r; }
+        const int which[3] = {4, 2, 7};
+        const int slot[3] = {6, 7, 5};
+        for (int w = 0; w < 3; ++w) {
+            CU(c, cudaEventRecord(c->ev2, c->stream));
+            for (int i = 0; i < reps; ++i) { int r = hyb(which[w]); if (r) return r; }
+            CU(c, cudaEventRecord(c->ev3, c->stream));
+            CU(c, cudaEventSynchronize(c->ev3));
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, c->ev2, c->ev3);
+            ms_out[slot[w]] = ms / reps;
+        }
+    }
     if (c->fused == 1) {                          // product path on 3-D single-GPU contexts: two fused kernels
         FusedArgs fa;
         fill_fused_args(c, fa, g, c->d_tot, jac);

@@ -1,0 +1,97 @@
+"""
+Frozen vectors (tests/golden/golden_v1.npz, made by tools/make_golden.py from the CPU oracle in the build container).
+CPU: the oracle still reproduces them (guards the checker against drift). GPU: the CUDA path reproduces them through
+the C ABI without any CPU solve at run time. Tolerances: operators 1e-12 relative; k 1e-6, flux 1e-5 (north_star).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import make_gpu, make_oracle, random_problem, relerr
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+G = np.load(os.path.join(HERE, "golden", "golden_v1.npz"))
+
+OPERATOR_CASES = [   # must match tools/make_golden.py
+    ("op1d_rt2p2", 101, 1, (17, 1, 1), 2, 2, "mixed"),
+    ("op2d_rt1p1", 102, 2, (9, 7, 1), 1, 1, "mixed"),
+    ("op2d_rt2p1", 103, 2, (6, 5, 1), 2, 1, "all"),
+    ("op3d_rt0p0", 104, 3, (5, 4, 3), 0, 0, "mixed"),
+    ("op3d_rt1p1", 105, 3, (5, 4, 3), 1, 1, "all"),
+    ("op3d_rt2p2", 106, 3, (3, 3, 2), 2, 2, "none"),
+]
+
+
+def _cfgs():
+    from neutfem_b200 import benchmarks as bm
+    from oracle.neutfem_oracle import BICGSTAB, CG_DIAG
+    return {
+        "cfg1_iaea2d_rt0p0": (lambda: bm.problem_2d("iaea2d", 2), 0, 0, BICGSTAB, (1e-9, 1e-9, 800, 5000), False),
+        "cfg2_iaea3d_diag": (lambda: bm.problem_iaea3d(2, 1), 0, 0, BICGSTAB, (1e-10, 1e-10, 1000, 1000), True),
+        "cfg3_biblis_rt1p1": (lambda: bm.problem_2d("biblis2d", 2), 1, 1, CG_DIAG, (1e-9, 1e-9, 800, 5000), False),
+        "cfg4_koeberg_rt2p2": (lambda: bm.problem_2d("koeberg2d", 1), 2, 2, BICGSTAB, (1e-9, 1e-9, 800, 8000), False),
+    }
+
+
+@pytest.mark.parametrize("name,seed,dim,n,rt,pp,bc", OPERATOR_CASES)
+def test_oracle_reproduces_golden_operators(name, seed, dim, n, rt, pp, bc):
+    p = random_problem(seed, dim, n, ng=2, bc=bc)
+    o = make_oracle(p, rt, pp)
+    x = G[name + "_x"]
+    assert tuple(G[name + "_sizes"]) == (o.fes.n_Phi, o.fes.n_J)
+    assert np.array_equal(x, np.random.default_rng(seed).uniform(0.5, 1.5, o.fes.n_Phi))
+    assert relerr(o.schur_product(0, x), G[name + "_Sx_g0"]) < 1e-13
+    assert relerr(o.schur_product(1, x), G[name + "_Sx_g1"]) < 1e-13
+    assert relerr(o.current_from_flux(0, x), G[name + "_J_g0"]) < 1e-13
+
+
+def test_oracle_reproduces_golden_config2():
+    """IAEA-3D diagonal path (configs[1]): cheap enough for the CPU suite."""
+    from oracle.neutfem_oracle import OracleNeutFEM
+    mk, rt, pp, solver, tol, diag = _cfgs()["cfg2_iaea3d_diag"]
+    p = mk()
+    o = OracleNeutFEM(rt, pp, p.ng, p.x_breaks, p.y_breaks, p.z_breaks)
+    o.set_linear_solver(solver)
+    o.set_tol(tol[0], tol[1], tol[1], tol[2], tol[3])
+    p.apply(o)
+    o.BuildMatrices()
+    k = o.SolveKeff(use_diagonal_solver=diag)
+    assert abs(k - G["cfg2_iaea3d_diag_k"][0]) < 1e-12
+    assert o.stats.outer_iterations == int(G["cfg2_iaea3d_diag_outer"][0])
+    assert relerr(np.array(o.Sol_Phi)[::37], G["cfg2_iaea3d_diag_phi_sample"]) < 1e-12
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,seed,dim,n,rt,pp,bc", OPERATOR_CASES)
+def test_gpu_reproduces_golden_operators(name, seed, dim, n, rt, pp, bc):
+    p = random_problem(seed, dim, n, ng=2, bc=bc)
+    c = make_gpu(p, rt, pp)
+    x = G[name + "_x"]
+    assert tuple(G[name + "_sizes"]) == (c.n_Phi, c.n_J)
+    assert relerr(c.schur_apply(0, x), G[name + "_Sx_g0"]) < 1e-12
+    assert relerr(c.schur_apply(1, x), G[name + "_Sx_g1"]) < 1e-12
+    assert relerr(c.current_from_flux(0, x), G[name + "_J_g0"]) < 1e-12
+    c.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["cfg1_iaea2d_rt0p0", "cfg2_iaea3d_diag", "cfg3_biblis_rt1p1", "cfg4_koeberg_rt2p2"])
+def test_gpu_reproduces_golden_keff(name):
+    from neutfem_b200 import cabi
+    mk, rt, pp, solver, tol, diag = _cfgs()[name]
+    p = mk()
+    c = cabi.Context(rt, pp, p.ng, p.x_breaks, p.y_breaks, p.z_breaks)
+    c.set_solver(solver_type=solver, tol_keff=tol[0], tol_flux=tol[1], max_outer=tol[2], max_inner=tol[3])
+    for a, t, v in p.bcs:
+        c.set_bc(a, t, v)
+    c.upload_xs(D=p.D, SigR=p.SigR, NSF=p.NSF, Chi=p.Chi, SigS=p.SigS)
+    c.build()
+    k, st = c.solve_keff(diag)
+    k_ref = float(G[name + "_k"][0])
+    assert abs(k - k_ref) / k_ref < 1e-6
+    assert st["outer_iterations"] == int(G[name + "_outer"][0])
+    phi = c.get_flux()
+    assert abs(np.linalg.norm(phi) - G[name + "_phi_norm"][0]) / G[name + "_phi_norm"][0] < 1e-5
+    assert relerr(phi[::37], G[name + "_phi_sample"]) < 1e-5
+    c.close()

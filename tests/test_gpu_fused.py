@@ -23,7 +23,7 @@ CASES = [
 
 class fused_env:
     def __init__(self, on, lw=4, lag=None, delay=None):
-        self.vals = {"NF_FUSED": "1" if on else "0", "NF_FUSED_LW": str(lw)}
+        self.vals = {"NF_FUSED": str(int(on)), "NF_FUSED_LW": str(lw)}
         if lag is not None:
             self.vals["NF_FUSED_LAG"] = str(lag)
         if delay is not None:
@@ -69,6 +69,21 @@ def test_fused_equals_separate_kernels(n, rt, pp, mode):
         assert abs(it1 - it0) <= 2, (lw, it0, it1)
         assert res1 < 1e-10
         assert relerr(phi1, phi0) < 1e-8, lw
+
+
+@pytest.mark.parametrize("n,rt,pp", CASES[:6])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_hybrid_equals_separate_kernels(n, rt, pp, mode):
+    """NF_FUSED=2: separate direction update / x / y kernels + k_zfwd + k_zback_update."""
+    p = random_problem(33, 3, n, ng=1, bc="mixed")
+    nloc = (min(rt, pp) + 1) ** 3
+    rhs = np.random.default_rng(6).uniform(0.0, 1.0, n[0] * n[1] * n[2] * nloc)
+    phi0, it0, res0, kt0 = _solve(p, rt, pp, mode, rhs, 0)
+    phi1, it1, res1, kt1 = _solve(p, rt, pp, mode, rhs, 2)
+    assert kt1["zback_update"] > 0.0 and kt0["zback_update"] == 0.0
+    assert abs(it1 - it0) <= 2
+    assert res1 < 1e-10
+    assert relerr(phi1, phi0) < 1e-8
 
 
 @pytest.mark.parametrize("lag,delay", [(0, 1), (3, 1), (0, 0), (1000, 1)])
