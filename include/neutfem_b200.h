@@ -124,11 +124,12 @@ NF_API int nf_current_from_flux(nf_ctx *ctx, int g, const double *phi, double *J
 /* 1/S_ee of the diagonal RT0-P0 path for group g, [NE] */
 NF_API int nf_get_diagonal_cache(nf_ctx *ctx, int g, double *s_inv);
 
-/* Average device time (ms) per launch of the hot-path kernels, CUDA events on the library's stream. ms_out holds 10
+/* Average device time (ms) per launch of the hot-path kernels, CUDA events on the library's stream. ms_out holds 16
  * doubles: [0..2] x/y/z sweep, [3] CG update, [4] CG direction update and [8] one CG iteration of the
- * separate-kernel path; [6] k_plane_fwd, [7] k_zback_update of the fused path (3-D single-GPU contexts, else 0);
- * [5] one CG iteration of the path the solver uses. fast != 0 times the Jacobi-PCG variants. Measurement hook for
- * bench.py's roofline; no reference counterpart. */
+ * separate-kernel path; [6] forward kernel (k_plane_fwd / k_zfwd), [7] k_zback_update, [9] k_xrow, [10] k_ycol of the
+ * 3-D single-GPU paths (else 0); [5] one CG iteration of the path the solver uses; [12] id of that path
+ * (0 separate kernels, 1 plane-ordered fused, 2 hybrid, 3 rows). fast != 0 times the Jacobi-PCG variants.
+ * Measurement hook for bench.py's roofline; no reference counterpart. */
 NF_API int nf_time_kernels(nf_ctx *ctx, int g, int reps, int fast, double *ms_out);
 
 /* ---- multi-GPU (z-slabs, one process per GPU) -------------------------------------------------------------

@@ -19,6 +19,7 @@
 #include "nf_vector.cuh"
 #include "nf_current.cuh"
 #include "nf_fused.cuh"
+#include "nf_rows.cuh"
 
 using namespace nf;
 
@@ -72,6 +73,7 @@ struct nf_ctx {
     int fLW = 4, fLcX = 1, fTS = 0, fPS = 0, fLcY = 1, fnX = 0, fnY = 0, fnitems = 0, fgrid = 0;
     size_t fsmem = 0;
     double *d_zs = nullptr, *d_W = nullptr, *d_fpart = nullptr;
+    RowGeom rg; int xrow_grid = 0, ycol_grid = 0;   // register-resident x-row / y-column kernels (nf_rows.cuh)
     int *d_fq = nullptr;                   // [0] queue head, [2] ticket, [4..4+nz) plane counters, then ny row counters
     int2 *d_items = nullptr;
 };
@@ -337,6 +339,93 @@ static int fused_prepare(nf_ctx *c, size_t smem, int *per_sm)
 #undef CALL
 }
 
+// ---- register-resident x-row / y-column kernels (nf_rows.cuh) ----------------------------------------------------------
+// Chunking of the lines: every thread owns <= kLC faces; the x lines use 8 / 16 / 32 lanes per (line, pair), the y lines
+// 8 / 16 / 32 chunks spread over the warps of a CTA. Returns false when a line is too long (> 32 * kLC - 1 cells).
+static bool rows_geometry(const nf_ctx *c, RowGeom &g)
+{
+    memset(&g, 0, sizeof(g));
+    const int nfx = c->nx + 1, nfy = c->ny + 1;
+    if (nfx > 32 * kLC || nfy > 32 * kLC) return false;
+    g.Cx = (nfx <= 8 * kLC) ? 8 : (nfx <= 16 * kLC ? 16 : 32);
+    g.LcX = (nfx + g.Cx - 1) / g.Cx;
+    g.PWx = 32 / g.Cx;
+    g.NFx = g.Cx * g.LcX;
+    int pp = g.NFx + 1;
+    while ((c->M1 * pp) % 16 != 8) ++pp;          // pair slots of a half-warp land in disjoint bank halves
+    g.pitchP = pp;
+    int pj = g.NFx + 2;
+    while (pj % 16 != 8) ++pj;
+    g.pitchJ = pj;
+    g.xsmemW = (2 * (g.NFx + 2) + g.PWx * c->M1 * g.pitchP + g.PWx * g.pitchJ + 1) & ~1;
+    g.Cy = (nfy <= 8 * kLC) ? 8 : (nfy <= 16 * kLC ? 16 : 32);
+    g.warpsY = (g.Cy == 8) ? 4 : 8;               // 16 columns per item (8 for the longest lines)
+    g.LcY = (nfy + g.Cy - 1) / g.Cy;
+    g.colsY = 32 * g.warpsY / g.Cy;
+    return true;
+}
+
+template <int K, int M1, int NCL>
+static int rows_prepare_x(nf_ctx *c)
+{
+    const size_t smem = (size_t)kXW * c->rg.xsmemW * sizeof(double);
+    if (smem + 2048 > c->smem_optin) { c->xrow_grid = 0; return NF_OK; }
+    CU(c, cudaFuncSetAttribute(k_xrow<K, M1, NCL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_xrow<K, M1, NCL>, 32 * kXW, smem));
+    const long long nrows = (long long)c->ny * c->nz;
+    c->xrow_grid = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(kRedBlocks, (long long)per_sm * c->sm_count), (nrows + kXW - 1) / kXW));
+    return NF_OK;
+}
+
+template <int K, int M1>
+static int rows_prepare_t(nf_ctx *c)
+{
+    const int ncl = (c->nx + 31) / 32;
+    int r = (ncl <= 8) ? rows_prepare_x<K, M1, 8>(c) : (ncl <= 16 ? rows_prepare_x<K, M1, 16>(c) : rows_prepare_x<K, M1, 33>(c));
+    if (r) return r;
+    int per_sm = 0;
+    const size_t ysmem = (size_t)(c->rg.LcY + 5) * 32 * c->rg.warpsY * sizeof(double);
+    CU(c, cudaFuncSetAttribute(k_ycol<K, M1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ysmem));
+    CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ycol<K, M1>, 32 * c->rg.warpsY, ysmem));
+    const long long nitems = (long long)c->nz * ((c->nx + c->rg.colsY - 1) / c->rg.colsY) * c->nt;
+    c->ycol_grid = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(kRedBlocks, (long long)std::max(per_sm, 1) * c->sm_count), nitems));
+    return NF_OK;
+}
+
+static int rows_prepare(nf_ctx *c)
+{
+#define CALL(KK, MM) rows_prepare_t<KK, MM>(c)
+    NF_ORDER_SWITCH(c, CALL);
+#undef CALL
+}
+
+// which: bit 0 = k_xrow (direction update + x part), bit 1 = k_ycol (y part)
+template <int K, int M1>
+static int rows_launch_t(nf_ctx *c, const FusedArgs &a, int which)
+{
+    if (which & 1) {
+        const int ncl = (c->nx + 31) / 32;
+        const size_t smem = (size_t)kXW * c->rg.xsmemW * sizeof(double);
+        double *part = c->d_part + (size_t)0 * kRedBlocks;
+        if (ncl <= 8) LAUNCH(c, (k_xrow<K, M1, 8>), c->xrow_grid, 32 * kXW, smem, a, c->rg, part, c->d_ticket + 0, &c->d_cg->pAp[0]);
+        else if (ncl <= 16) LAUNCH(c, (k_xrow<K, M1, 16>), c->xrow_grid, 32 * kXW, smem, a, c->rg, part, c->d_ticket + 0, &c->d_cg->pAp[0]);
+        else LAUNCH(c, (k_xrow<K, M1, 33>), c->xrow_grid, 32 * kXW, smem, a, c->rg, part, c->d_ticket + 0, &c->d_cg->pAp[0]);
+    }
+    if (which & 2)
+        LAUNCH(c, (k_ycol<K, M1>), c->ycol_grid, 32 * c->rg.warpsY, (size_t)(c->rg.LcY + 5) * 32 * c->rg.warpsY * sizeof(double), a, c->rg,
+               c->d_part + (size_t)1 * kRedBlocks, c->d_ticket + 1, &c->d_cg->pAp[1]);
+    CU(c, cudaGetLastError());
+    return NF_OK;
+}
+
+static int rows_launch(nf_ctx *c, const FusedArgs &a, int which)
+{
+#define CALL(KK, MM) rows_launch_t<KK, MM>(c, a, which)
+    NF_ORDER_SWITCH(c, CALL);
+#undef CALL
+}
+
 // Decide once per context whether the fused path applies (3-D, single GPU, lines fit in shared memory) and build its
 // work-item queue: round r holds the X items of plane r and the Y items of plane r-delay, the Y items starting `lag`
 // X items into the round so that they (almost) never find their plane incomplete.
@@ -346,6 +435,18 @@ static int fused_setup(nf_ctx *c)
     c->fused = 0;
     const int want_mode = env_int("NF_FUSED", 1);
     if (c->dim != 3 || c->slab || want_mode == 0) return NF_OK;
+    if (want_mode == 3) {                 // rows: k_xrow (direction update + x) + k_ycol + k_zfwd + k_zback_update
+        if (rows_geometry(c, c->rg)) {
+            { int r = rows_prepare(c); if (r) return r; }
+            if (c->xrow_grid > 0) {
+                const size_t nxy2 = (size_t)c->nx * c->ny;
+                { int r = dalloc(c, &c->d_zs, (size_t)(c->nz + 1) * c->nt * nxy2); if (r) return r; }
+                c->fused = 3;
+                return NF_OK;
+            }
+        }
+        return NF_OK;                     // lines too long for the register-resident solvers: separate kernels
+    }
     if (want_mode == 2) {                 // hybrid: separate x / y sweeps + k_zfwd + k_zback_update
         const size_t nxy2 = (size_t)c->nx * c->ny;
         { int r = dalloc(c, &c->d_zs, (size_t)(c->nz + 1) * c->nt * nxy2); if (r) return r; }
@@ -557,7 +658,9 @@ static int create_impl(nf_ctx **out, int rt_order, int p_order, int ng, const do
     CK(dalloc(c, &c->d_phi, G * np)); CK(dalloc(c, &c->d_old, G * np));
     CK(dalloc(c, &c->d_h0, G * np)); CK(dalloc(c, &c->d_h1, G * np)); CK(dalloc(c, &c->d_tmp, G * np));
     CK(dalloc(c, &c->d_tot, np)); CK(dalloc(c, &c->d_rhs, np)); CK(dalloc(c, &c->d_r, np));
-    CK(dalloc(c, &c->d_p, np)); CK(dalloc(c, &c->d_Ap, np));
+    const size_t rowpad = (size_t)kRowPad * c->nx;           // the y-column kernels read (and mask) a few rows past the end
+    CK(dalloc(c, &c->d_p, np + rowpad)); CK(dalloc(c, &c->d_Ap, np + rowpad));
+    CKU(cudaMemset(c->d_p + np, 0, rowpad * sizeof(double))); CKU(cudaMemset(c->d_Ap + np, 0, rowpad * sizeof(double)));
     CK(dalloc(c, &c->d_cg, 1)); CK(dalloc(c, &c->d_part, (size_t)8 * kRedBlocks)); CK(dalloc(c, &c->d_ticket, 16));
     CK(dalloc(c, &c->d_scal, 16));
     CKU(cudaMemset(c->d_ticket, 0, 16 * sizeof(unsigned)));
@@ -567,8 +670,10 @@ static int create_impl(nf_ctx **out, int rt_order, int p_order, int ng, const do
     c->d_minv.assign(G * 3, nullptr); c->d_u.assign(G * 3, nullptr);
     for (size_t g = 0; g < G; ++g)
         for (int d = 0; d < c->dim; ++d) {
-            CK(dalloc(c, &c->d_minv[g * 3 + d], (size_t)c->nfaces[d]));
-            CK(dalloc(c, &c->d_u[g * 3 + d], (size_t)c->nfaces[d]));
+            CK(dalloc(c, &c->d_minv[g * 3 + d], (size_t)c->nfaces[d] + rowpad));
+            CK(dalloc(c, &c->d_u[g * 3 + d], (size_t)c->nfaces[d] + rowpad));
+            CKU(cudaMemset(c->d_minv[g * 3 + d] + c->nfaces[d], 0, rowpad * sizeof(double)));
+            CKU(cudaMemset(c->d_u[g * 3 + d] + c->nfaces[d], 0, rowpad * sizeof(double)));
         }
     // geometry factors f_d(e) = Fx[d][ix]*Fy[d][iy]*Fz[d][iz]   (Piola factors, src/FEM.cpp:794-813)
     {
@@ -912,9 +1017,9 @@ static int solve_group(nf_ctx *c, int g, const double *b, double *x, int *iters_
         LAUNCH(c, k_cg_finalize, 1, 1, 0, c->d_cg, 0, tol, pcg ? 1 : 0);
     }
     { int r = fused_setup(c); if (r) return r; }
-    const bool fused = (c->fused == 1), hybrid = (c->fused == 2);
+    const bool fused = (c->fused == 1), hybrid = (c->fused == 2), rows = (c->fused == 3);
     FusedArgs fa;
-    if (fused || hybrid) fill_fused_args(c, fa, g, x, jac);
+    if (fused || hybrid || rows) fill_fused_args(c, fa, g, x, jac);
     // poll the device-side done flag every few iterations; iterations after convergence are no-ops on the device
     const double est_us = (double)n * 160.0 / 6.0e6 + 15.0;
     int poll = (int)std::max(1.0, std::min(16.0, 200.0 / est_us));
@@ -926,6 +1031,11 @@ static int solve_group(nf_ctx *c, int g, const double *b, double *x, int *iters_
             if (fused) {          // two kernels: direction update + forward sweeps | z back substitution + update
                 int r = fused_launch(c, fa, 3);
                 if (r) return r;
+                continue;
+            }
+            if (rows) {           // direction update + x rows | y columns | z forward | z back + update
+                { int r = rows_launch(c, fa, 3); if (r) return r; }
+                { int r = fused_launch(c, fa, 4 | 2); if (r) return r; }
                 continue;
             }
             if (hybrid) {         // direction update, x and y sweeps as separate kernels, then z forward | z back + update
@@ -1272,8 +1382,9 @@ int nf_time_kernels(nf_ctx *c, int g, int reps, int fast, double *ms_out)
     // Average device time per launch of each hot-path kernel, CUDA events on the context stream, operands resident
     // in HBM. ms_out[0..2] = x / y / z sweep, [3] = CG update, [4] = CG direction update of the separate-kernel
     // path, [8] = one CG iteration of that path (five launches); [6] = k_plane_fwd, [7] = k_zback_update of the fused
-    // path (0 if it does not apply), [5] = one CG iteration of the path the solver really uses. ms_out holds 10
-    // doubles. Destroys the CG work vectors, not the flux.
+    // path (0 if it does not apply), [5] = one CG iteration of the path the solver really uses, [9] = k_xrow,
+    // [10] = k_ycol of the rows path, [12] = id of the path in use. ms_out holds 16 doubles. Destroys the CG work
+    // vectors, not the flux.
     if (!c || !ms_out || g < 0 || g >= c->ng || reps < 1) return NF_ERR_ARG;
     if (!c->built) NF_FAIL(c, NF_ERR_STATE, "nf_time_kernels: call nf_build first");
     CU(c, cudaSetDevice(c->dev));
@@ -1285,7 +1396,7 @@ int nf_time_kernels(nf_ctx *c, int g, int reps, int fast, double *ms_out)
     const int fin = c->slab ? 0 : 1;
     LAUNCH(c, k_cg_init, blocks, 256, 0, c->d_rhs, c->d_tot, c->d_r, c->d_p, n, 0.0, c->d_cg, c->d_part + 4 * kRedBlocks, c->d_ticket + 4, fin);
     if (!fin) { { int r = allreduce_sum(c, c->d_cg->tmp, 3); if (r) return r; } LAUNCH(c, k_cg_finalize, 1, 1, 0, c->d_cg, 0, 0.0, 0); }
-    for (int i = 0; i < 10; ++i) ms_out[i] = 0.0;
+    for (int i = 0; i < 16; ++i) ms_out[i] = 0.0;
     auto iteration = [&](int mask, bool upd, bool pupd) -> int {
         if (mask) { int r = apply_schur(c, g, c->d_p, c->d_Ap, true, mask); if (r) return r; }
         if (upd) {
@@ -1332,6 +1443,28 @@ int nf_time_kernels(nf_ctx *c, int g, int reps, int fast, double *ms_out)
         for (int w = 0; w < 3; ++w) {
             CU(c, cudaEventRecord(c->ev2, c->stream));
             for (int i = 0; i < reps; ++i) { int r = hyb(which[w]); if (r) return r; }
+            CU(c, cudaEventRecord(c->ev3, c->stream));
+            CU(c, cudaEventSynchronize(c->ev3));
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, c->ev2, c->ev3);
+            ms_out[slot[w]] = ms / reps;
+        }
+    }
+    ms_out[12] = (double)c->fused;
+    if (c->fused == 3) {                          // rows path: k_xrow | k_ycol | k_zfwd | k_zback_update
+        FusedArgs fa;
+        fill_fused_args(c, fa, g, c->d_tot, jac);
+        auto rowsit = [&](int what) -> int {       // 1: x rows, 8: y columns, 4: z forward, 2: z back + update
+            if (what & 1) { int r = rows_launch(c, fa, 1); if (r) return r; }
+            if (what & 8) { int r = rows_launch(c, fa, 2); if (r) return r; }
+            return (what & 6) ? fused_launch(c, fa, what & 6) : NF_OK;
+        };
+        { int r = rowsit(15); if (r) return r; }
+        const int which[5] = {1, 8, 4, 2, 15};
+        const int slot[5] = {9, 10, 6, 7, 5};
+        for (int w = 0; w < 5; ++w) {
+            CU(c, cudaEventRecord(c->ev2, c->stream));
+            for (int i = 0; i < reps; ++i) { int r = rowsit(which[w]); if (r) return r; }
             CU(c, cudaEventRecord(c->ev3, c->stream));
             CU(c, cudaEventSynchronize(c->ev3));
             float ms = 0.f;

@@ -86,6 +86,24 @@ def test_hybrid_equals_separate_kernels(n, rt, pp, mode):
     assert relerr(phi1, phi0) < 1e-8
 
 
+ROW_CASES = CASES + [((270, 5, 3), 1, 1), ((6, 300, 3), 1, 1), ((40, 37, 5), 2, 2), ((530, 4, 2), 1, 0)]
+
+
+@pytest.mark.parametrize("n,rt,pp", ROW_CASES)
+@pytest.mark.parametrize("mode", [0, 1])
+def test_rows_equals_separate_kernels(n, rt, pp, mode):
+    """NF_FUSED=3: register-resident x rows (direction update fused) / y columns + k_zfwd + k_zback_update."""
+    p = random_problem(35, 3, n, ng=1, bc="mixed")
+    nloc = (min(rt, pp) + 1) ** 3
+    rhs = np.random.default_rng(8).uniform(0.0, 1.0, n[0] * n[1] * n[2] * nloc)
+    phi0, it0, res0, kt0 = _solve(p, rt, pp, mode, rhs, 0)
+    phi1, it1, res1, kt1 = _solve(p, rt, pp, mode, rhs, 3)
+    assert kt1["path"] == 3.0 and kt1["xrow"] > 0.0 and kt1["ycol"] > 0.0
+    assert abs(it1 - it0) <= 2
+    assert res1 < 1e-10
+    assert relerr(phi1, phi0) < 1e-8
+
+
 @pytest.mark.parametrize("lag,delay", [(0, 1), (3, 1), (0, 0), (1000, 1)])
 def test_fused_queue_orders(lag, delay):
     """Any admissible ordering of the work queue gives the same numbers (per-item partial sums, fixed order)."""
