@@ -37,6 +37,7 @@ struct nf_ctx {
     double *d_iFx[3] = {nullptr, nullptr, nullptr};   // 1/F[dir][x axis]
     double *d_D = nullptr, *d_SigR = nullptr, *d_NSF = nullptr, *d_Chi = nullptr, *d_SigS = nullptr, *d_SRC = nullptr;
     std::vector<double *> d_minv, d_u;     // [g*3 + d]
+    std::vector<double *> d_u_base;        // allocations behind d_u (front padding, see nf_rows.cuh)
     long long nfaces[3] = {0, 0, 0};
     double *d_sinv = nullptr; bool diag_valid = false;
     double *d_jac = nullptr; bool jac_valid = false;
@@ -346,7 +347,7 @@ static bool rows_geometry(const nf_ctx *c, RowGeom &g)
 {
     memset(&g, 0, sizeof(g));
     const int nfx = c->nx + 1, nfy = c->ny + 1;
-    if (nfx > 32 * kLC || nfy > 32 * kLC) return false;
+    if (nfx > 32 * kLC || c->ny > 32 * 64) return false;
     g.Cx = (nfx <= 8 * kLC) ? 8 : (nfx <= 16 * kLC ? 16 : 32);
     g.LcX = (nfx + g.Cx - 1) / g.Cx;
     g.PWx = 32 / g.Cx;
@@ -358,21 +359,22 @@ static bool rows_geometry(const nf_ctx *c, RowGeom &g)
     while (pj % 16 != 8) ++pj;
     g.pitchJ = pj;
     g.xsmemW = (2 * (g.NFx + 2) + g.PWx * c->M1 * g.pitchP + g.PWx * g.pitchJ + 1) & ~1;
-    g.Cy = (nfy <= 8 * kLC) ? 8 : (nfy <= 16 * kLC ? 16 : 32);
-    g.warpsY = (g.Cy == 8) ? 4 : 8;               // 16 columns per item (8 for the longest lines)
-    g.LcY = (nfy + g.Cy - 1) / g.Cy;
-    g.colsY = 32 * g.warpsY / g.Cy;
+    if (c->nx & 1) return false;                  // the y columns are processed two at a time (16-byte vectors)
+    g.warpsY = kYT / 32;
+    g.Cy = (c->ny <= 8 * 16) ? 8 : (c->ny <= 16 * 16 ? 16 : 32);      // chunks of <= 16 cells where possible
+    g.LcY = (c->ny + g.Cy - 1) / g.Cy;            // cells per chunk (the last chunk of a line also owns the top face)
+    g.colsY = 2 * (kYT / g.Cy);
     return true;
 }
 
-template <int K, int M1, int NCL>
+template <int K, int M1, int NCL, bool FULL>
 static int rows_prepare_x(nf_ctx *c)
 {
     const size_t smem = (size_t)kXW * c->rg.xsmemW * sizeof(double);
     if (smem + 2048 > c->smem_optin) { c->xrow_grid = 0; return NF_OK; }
-    CU(c, cudaFuncSetAttribute(k_xrow<K, M1, NCL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(c, cudaFuncSetAttribute(k_xrow<K, M1, NCL, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_xrow<K, M1, NCL>, 32 * kXW, smem));
+    CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_xrow<K, M1, NCL, FULL>, 32 * kXW, smem));
     const long long nrows = (long long)c->ny * c->nz;
     c->xrow_grid = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(kRedBlocks, (long long)per_sm * c->sm_count), (nrows + kXW - 1) / kXW));
     return NF_OK;
@@ -382,10 +384,14 @@ template <int K, int M1>
 static int rows_prepare_t(nf_ctx *c)
 {
     const int ncl = (c->nx + 31) / 32;
-    int r = (ncl <= 8) ? rows_prepare_x<K, M1, 8>(c) : (ncl <= 16 ? rows_prepare_x<K, M1, 16>(c) : rows_prepare_x<K, M1, 33>(c));
+    const bool full = (c->rg.LcX == kLC);          // every chunk of an x line runs all kLC steps (no guards)
+    int r = (ncl <= 8) ? (full ? rows_prepare_x<K, M1, 8, true>(c) : rows_prepare_x<K, M1, 8, false>(c))
+                       : (ncl <= 16 ? (full ? rows_prepare_x<K, M1, 16, true>(c) : rows_prepare_x<K, M1, 16, false>(c))
+                                    : rows_prepare_x<K, M1, 33, false>(c));
     if (r) return r;
     int per_sm = 0;
-    const size_t ysmem = (size_t)(c->rg.LcY + 5) * 32 * c->rg.warpsY * sizeof(double);
+    const size_t ysmem = (size_t)(c->rg.LcY + 1 + 5) * kYT * sizeof(double2);
+    if (ysmem + 2048 > c->smem_optin) { c->xrow_grid = 0; return NF_OK; }
     CU(c, cudaFuncSetAttribute(k_ycol<K, M1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ysmem));
     CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ycol<K, M1>, 32 * c->rg.warpsY, ysmem));
     const long long nitems = (long long)c->nz * ((c->nx + c->rg.colsY - 1) / c->rg.colsY) * c->nt;
@@ -408,12 +414,15 @@ static int rows_launch_t(nf_ctx *c, const FusedArgs &a, int which)
         const int ncl = (c->nx + 31) / 32;
         const size_t smem = (size_t)kXW * c->rg.xsmemW * sizeof(double);
         double *part = c->d_part + (size_t)0 * kRedBlocks;
-        if (ncl <= 8) LAUNCH(c, (k_xrow<K, M1, 8>), c->xrow_grid, 32 * kXW, smem, a, c->rg, part, c->d_ticket + 0, &c->d_cg->pAp[0]);
-        else if (ncl <= 16) LAUNCH(c, (k_xrow<K, M1, 16>), c->xrow_grid, 32 * kXW, smem, a, c->rg, part, c->d_ticket + 0, &c->d_cg->pAp[0]);
-        else LAUNCH(c, (k_xrow<K, M1, 33>), c->xrow_grid, 32 * kXW, smem, a, c->rg, part, c->d_ticket + 0, &c->d_cg->pAp[0]);
+        const bool full = (c->rg.LcX == kLC);
+#define NF_XROW(NCLV, FULLV) LAUNCH(c, (k_xrow<K, M1, NCLV, FULLV>), c->xrow_grid, 32 * kXW, smem, a, c->rg, part, c->d_ticket + 0, &c->d_cg->pAp[0])
+        if (ncl <= 8) { if (full) NF_XROW(8, true); else NF_XROW(8, false); }
+        else if (ncl <= 16) { if (full) NF_XROW(16, true); else NF_XROW(16, false); }
+        else NF_XROW(33, false);
+#undef NF_XROW
     }
     if (which & 2)
-        LAUNCH(c, (k_ycol<K, M1>), c->ycol_grid, 32 * c->rg.warpsY, (size_t)(c->rg.LcY + 5) * 32 * c->rg.warpsY * sizeof(double), a, c->rg,
+        LAUNCH(c, (k_ycol<K, M1>), c->ycol_grid, kYT, (size_t)(c->rg.LcY + 1 + 5) * kYT * sizeof(double2), a, c->rg,
                c->d_part + (size_t)1 * kRedBlocks, c->d_ticket + 1, &c->d_cg->pAp[1]);
     CU(c, cudaGetLastError());
     return NF_OK;
@@ -667,13 +676,14 @@ static int create_impl(nf_ctx **out, int rt_order, int p_order, int ng, const do
     CKU(cudaMemset(c->d_cg, 0, sizeof(CgState)));
     CKU(cudaMallocHost((void **)&c->h_scal, 16 * sizeof(double)));
     CKU(cudaMallocHost((void **)&c->h_cg, sizeof(CgState)));
-    c->d_minv.assign(G * 3, nullptr); c->d_u.assign(G * 3, nullptr);
+    c->d_minv.assign(G * 3, nullptr); c->d_u.assign(G * 3, nullptr); c->d_u_base.assign(G * 3, nullptr);
     for (size_t g = 0; g < G; ++g)
         for (int d = 0; d < c->dim; ++d) {
             CK(dalloc(c, &c->d_minv[g * 3 + d], (size_t)c->nfaces[d] + rowpad));
-            CK(dalloc(c, &c->d_u[g * 3 + d], (size_t)c->nfaces[d] + rowpad));
+            CK(dalloc(c, &c->d_u_base[g * 3 + d], (size_t)c->nfaces[d] + 2 * rowpad));
+            c->d_u[g * 3 + d] = c->d_u_base[g * 3 + d] + rowpad;          // zero rows in front and behind
             CKU(cudaMemset(c->d_minv[g * 3 + d] + c->nfaces[d], 0, rowpad * sizeof(double)));
-            CKU(cudaMemset(c->d_u[g * 3 + d] + c->nfaces[d], 0, rowpad * sizeof(double)));
+            CKU(cudaMemset(c->d_u_base[g * 3 + d], 0, ((size_t)c->nfaces[d] + 2 * rowpad) * sizeof(double)));
         }
     // geometry factors f_d(e) = Fx[d][ix]*Fy[d][iy]*Fz[d][iz]   (Piola factors, src/FEM.cpp:794-813)
     {
@@ -781,7 +791,7 @@ int nf_destroy(nf_ctx *c)
     if (c->d_items) cudaFree(c->d_items);
     if (c->comm) ncclCommDestroy(c->comm);
     for (double *p : c->d_minv) if (p) cudaFree(p);
-    for (double *p : c->d_u) if (p) cudaFree(p);
+    for (double *p : c->d_u_base) if (p) cudaFree(p);
     if (c->d_cg) cudaFree(c->d_cg);
     if (c->d_ticket) cudaFree(c->d_ticket);
     if (c->h_scal) cudaFreeHost(c->h_scal);

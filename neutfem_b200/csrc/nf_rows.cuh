@@ -34,9 +34,10 @@ struct RowGeom {
 
 // ---- the four passes over a register-resident chunk -------------------------------------------------------------------
 // um(j) = u_{f0+j-1} (0 at the first face of the line), uf(j) = u_{f0+j} (0 at the last face), mi(j) = 1/m_{f0+j}.
-// LB = loads issued ahead of each stretch of the dependent recurrence.
+// LB = loads issued ahead of each stretch of the dependent recurrence. FULL: every chunk runs all kLC steps -- the
+// caller guarantees T = 0, u = 0 (1/m finite) past the end of the line, which leaves every result unchanged.
 // A: local forward substitution from z_in = 0 and the chunk's multiplier:  z_out = A z_in + z
-template <int LB, class FU>
+template <int LB, bool FULL, class FU>
 __device__ __forceinline__ void chunk_fwd_map(const double (&T)[kLC], const int jn, FU um, double &A, double &z)
 {
     A = 1.0; z = 0.0;
@@ -45,15 +46,15 @@ __device__ __forceinline__ void chunk_fwd_map(const double (&T)[kLC], const int 
         NF_SCHED_FENCE();
         double uu[LB];
 #pragma unroll
-        for (int i = 0; i < LB; ++i) { uu[i] = 0.0; if (jb + i < kLC && jb + i < jn) uu[i] = um(jb + i); }
+        for (int i = 0; i < LB; ++i) { uu[i] = 0.0; if (jb + i < kLC && (FULL || jb + i < jn)) uu[i] = um(jb + i); }
 #pragma unroll
         for (int i = 0; i < LB; ++i)
-            if (jb + i < kLC && jb + i < jn) { z = T[jb + i] - uu[i] * z; A *= -uu[i]; }
+            if (jb + i < kLC && (FULL || jb + i < jn)) { z = T[jb + i] - uu[i] * z; A *= -uu[i]; }
     }
 }
 
 // B: forward substitution with the true incoming value; T <- d_f = z_f / m_f; returns sum_f z_f^2 / m_f of the chunk
-template <int LB, class FU, class FM>
+template <int LB, bool FULL, class FU, class FM>
 __device__ __forceinline__ double chunk_fwd_final(double (&T)[kLC], const int jn, FU um, FM mi, double z)
 {
     double q = 0.0;
@@ -62,10 +63,10 @@ __device__ __forceinline__ double chunk_fwd_final(double (&T)[kLC], const int jn
         NF_SCHED_FENCE();
         double uu[LB], mm[LB];
 #pragma unroll
-        for (int i = 0; i < LB; ++i) { uu[i] = mm[i] = 0.0; if (jb + i < kLC && jb + i < jn) { uu[i] = um(jb + i); mm[i] = mi(jb + i); } }
+        for (int i = 0; i < LB; ++i) { uu[i] = mm[i] = 0.0; if (jb + i < kLC && (FULL || jb + i < jn)) { uu[i] = um(jb + i); mm[i] = mi(jb + i); } }
 #pragma unroll
         for (int i = 0; i < LB; ++i)
-            if (jb + i < kLC && jb + i < jn) {
+            if (jb + i < kLC && (FULL || jb + i < jn)) {
                 z = T[jb + i] - uu[i] * z;
                 const double d = mm[i] * z;
                 q += z * d;
@@ -76,7 +77,7 @@ __device__ __forceinline__ double chunk_fwd_final(double (&T)[kLC], const int jn
 }
 
 // C: local backward substitution J_f = d_f - u_f J_{f+1} from J_in = 0 and the chunk's multiplier:  J_out = Bp J_in + J
-template <int LB, class FU>
+template <int LB, bool FULL, class FU>
 __device__ __forceinline__ void chunk_bwd_map(const double (&T)[kLC], const int jn, FU uf, double &Bp, double &J)
 {
     Bp = 1.0; J = 0.0;
@@ -85,15 +86,15 @@ __device__ __forceinline__ void chunk_bwd_map(const double (&T)[kLC], const int 
         NF_SCHED_FENCE();
         double uu[LB];
 #pragma unroll
-        for (int i = LB - 1; i >= 0; --i) { uu[i] = 0.0; if (jb + i < kLC && jb + i < jn) uu[i] = uf(jb + i); }
+        for (int i = LB - 1; i >= 0; --i) { uu[i] = 0.0; if (jb + i < kLC && (FULL || jb + i < jn)) uu[i] = uf(jb + i); }
 #pragma unroll
         for (int i = LB - 1; i >= 0; --i)
-            if (jb + i < kLC && jb + i < jn) { J = T[jb + i] - uu[i] * J; Bp *= -uu[i]; }
+            if (jb + i < kLC && (FULL || jb + i < jn)) { J = T[jb + i] - uu[i] * J; Bp *= -uu[i]; }
     }
 }
 
 // D: backward substitution with the true incoming value; T <- J
-template <int LB, class FU>
+template <int LB, bool FULL, class FU>
 __device__ __forceinline__ void chunk_bwd_final(double (&T)[kLC], const int jn, FU uf, double J)
 {
 #pragma unroll
@@ -101,10 +102,10 @@ __device__ __forceinline__ void chunk_bwd_final(double (&T)[kLC], const int jn, 
         NF_SCHED_FENCE();
         double uu[LB];
 #pragma unroll
-        for (int i = LB - 1; i >= 0; --i) { uu[i] = 0.0; if (jb + i < kLC && jb + i < jn) uu[i] = uf(jb + i); }
+        for (int i = LB - 1; i >= 0; --i) { uu[i] = 0.0; if (jb + i < kLC && (FULL || jb + i < jn)) uu[i] = uf(jb + i); }
 #pragma unroll
         for (int i = LB - 1; i >= 0; --i)
-            if (jb + i < kLC && jb + i < jn) { J = T[jb + i] - uu[i] * J; T[jb + i] = J; }
+            if (jb + i < kLC && (FULL || jb + i < jn)) { J = T[jb + i] - uu[i] * J; T[jb + i] = J; }
     }
 }
 
@@ -114,7 +115,7 @@ __device__ __forceinline__ void chunk_bwd_final(double (&T)[kLC], const int jn, 
 // NCL = compile-time bound on the cells a lane owns (ceil(nx / 32)): per-cell coefficients live in registers.
 constexpr int kCB = 8;          // cells per lane in one coalesced batch (256 cells)
 
-template <int K, int M1, int NCL>
+template <int K, int M1, int NCL, bool FULL>
 __device__ __forceinline__ void xrow_warp(const FusedArgs &a, const RowGeom &g, const int iz, const int iy, const double beta,
                                           double *sm, double &acc)
 {
@@ -226,9 +227,9 @@ __device__ __forceinline__ void xrow_warp(const FusedArgs &a, const RowGeom &g, 
 #pragma unroll
             for (int j = 0; j < kLC; ++j) {
                 T[j] = 0.0;
-                if (j < jn) {
+                if (FULL || j < jn) {
                     double lo, hi;
-                    cell_lo_hi<K, M1>(P0[j], P1[j], P2[j], lo, hi);     // cell n is a zero pad: T_n = lo_{n-1}
+                    cell_lo_hi<K, M1>(P0[j], P1[j], P2[j], lo, hi);     // cells >= n are zero pads: T_n = lo_{n-1}, T_f = 0 beyond
                     T[j] = lop - hi;
                     lop = lo;
                 }
@@ -239,32 +240,38 @@ __device__ __forceinline__ void xrow_warp(const FusedArgs &a, const RowGeom &g, 
         auto uf = [&](const int j) { return ub[j + 1]; };
         auto mi = [&](const int j) { return mb[j]; };
         double A, z;
-        chunk_fwd_map<11>(T, jn, um, A, z);
+        chunk_fwd_map<11, FULL>(T, jn, um, A, z);
         for (int d = 1; d < C; d <<= 1) {
             const double Ap = __shfl_up_sync(full, A, d, C), zp = __shfl_up_sync(full, z, d, C);
             if (k >= d) { z = A * zp + z; A = A * Ap; }
         }
         double zin = __shfl_up_sync(full, z, 1, C);
         if (k == 0) zin = 0.0;
-        const double q = chunk_fwd_final<11>(T, jn, um, mi, zin);
+        const double q = chunk_fwd_final<11, FULL>(T, jn, um, mi, zin);
         double Bp, J;
-        chunk_bwd_map<11>(T, jn, uf, Bp, J);
+        chunk_bwd_map<11, FULL>(T, jn, uf, Bp, J);
         for (int d = 1; d < C; d <<= 1) {
             const double Bq = __shfl_down_sync(full, Bp, d, C), Jq = __shfl_down_sync(full, J, d, C);
             if (k + d < C) { J = Bp * Jq + J; Bp = Bp * Bq; }
         }
         double Jin = __shfl_down_sync(full, J, 1, C);
         if (k == C - 1) Jin = 0.0;
-        chunk_bwd_final<11>(T, jn, uf, Jin);
+        chunk_bwd_final<11, FULL>(T, jn, uf, Jin);
         if (tv) {
             acc += a.w[t0 + s] * q;
             double *Jr = Jb + s * PJ + f0;
 #pragma unroll
             for (int j = 0; j < kLC; ++j)
-                if (j < jn) Jr[j] = T[j];
+                if (FULL || j < jn) Jr[j] = T[j];
         }
         __syncwarp();
         // ---- yp = diag * p + w B_x J (coalesced): modes outside, the lane's cells inside
+        double G0[NCL], G1[NCL], G2[NCL];
+#pragma unroll
+        for (int c = 0; c < NCL; ++c) {
+            const int ixl = min(lane + 32 * c, n - 1);
+            G0[c] = Dv[c] * __ldg(a.iFx[0] + ixl); G1[c] = Dv[c] * __ldg(a.iFx[1] + ixl); G2[c] = Dv[c] * __ldg(a.iFx[2] + ixl);
+        }
         for (int s2 = 0; s2 < np; ++s2) {
             const double w = a.w[t0 + s2];
             const double *Js = Jb + s2 * PJ + lane;
@@ -282,8 +289,7 @@ __device__ __forceinline__ void xrow_warp(const FusedArgs &a, const RowGeom &g, 
                         const double sol = (p == 0) ? w * (JR - JL) : (p == 1 ? ((K >= 1) ? w * (5.0 / 6.0) * (JL + JR) : 0.0)
                                                                               : ((K >= 2) ? w * (7.0 / 10.0) * (JR - JL) : 0.0));
                         const double xv = Pm[32 * c];
-                        const double q0 = Dv[c] * __ldg(a.iFx[0] + ix), q1 = Dv[c] * __ldg(a.iFx[1] + ix), q2 = Dv[c] * __ldg(a.iFx[2] + ix);
-                        const double dg = Sv[c] * cw + q0 * c0 + q1 * c1 + q2 * c2;
+                        const double dg = Sv[c] * cw + G0[c] * c0 + G1[c] * c1 + G2[c] * c2;
                         const double yv = dg * xv;
                         acc += yv * xv;
                         yo[32 * c] = yv + sol;
@@ -298,7 +304,7 @@ __device__ __forceinline__ void xrow_warp(const FusedArgs &a, const RowGeom &g, 
 constexpr int kXW = 1;      // warps per CTA of the stand-alone x-row kernel (every warp is autonomous)
 
 // p = M^-1 r + beta p ; yp = diag p + (x part of S p) ; red_out = p^T (diag + x part) p
-template <int K, int M1, int NCL>
+template <int K, int M1, int NCL, bool FULL>
 __global__ void __launch_bounds__(32 * kXW) k_xrow(const FusedArgs a, const RowGeom g, double *red_part, unsigned *ticket,
                                                    double *red_out)
 {
@@ -315,40 +321,53 @@ __global__ void __launch_bounds__(32 * kXW) k_xrow(const FusedArgs a, const RowG
     const long long nrows = (long long)a.ny * a.nz;
     double acc = 0.0;
     for (long long row = (long long)blockIdx.x * WPB + wib; row < nrows; row += (long long)gridDim.x * WPB)
-        xrow_warp<K, M1, NCL>(a, g, (int)(row / a.ny), (int)(row % a.ny), beta, wsm, acc);
+        xrow_warp<K, M1, NCL, FULL>(a, g, (int)(row / a.ny), (int)(row % a.ny), beta, wsm, acc);
     double v[1] = {acc};
     grid_reduce<1>(v, red_part, ticket, red_out);
 }
 
 // ---- y columns ---------------------------------------------------------------------------------------------------------
-// One CTA (NT = 32 * warpsY threads), colsY adjacent y lines of plane iz (x positions xb*colsY ...), transverse pair t.
-// Thread = (column, chunk of LcY faces). The chunk's right-hand side / solution lives in a thread-private column of
-// shared memory (sT[j * NT + tid], conflict free) so that the loops over the chunk stay rolled (few registers, many
-// resident warps); loads are issued kYB rows ahead of the dependent recurrences. Chunks are stitched through sS
-// (5 arrays of NT doubles: forward maps, backward maps, first J of every chunk).
-// Every global load is unconditional: the arrays carry kRowPad rows of padding at their end (nf_api.cu), so chunks that
-// reach past the end of the column read legal (meaningless) words that are masked when they are consumed.
-constexpr int kRowPad = 48;     // >= 32 chunks + kYB rows
+// One CTA of NT threads owns colsY adjacent y lines of plane iz (x positions xb*colsY ...) for transverse pair t.
+// Thread = (PAIR of adjacent columns, chunk of LcY cells of the y line): every load / store is a 16-byte vector shared by
+// two independent line systems (half the address arithmetic, twice the instruction-level parallelism). A chunk owns the
+// faces of its cells' lower sides; the last chunk of the line also owns the top face. The chunk's right-hand side /
+// solution lives in a thread-private column of shared memory (sT[j * NT + tid], conflict free, immediate offsets), loads are
+// issued kYB rows ahead of the dependent recurrences, partial chunks fall into a scalar remainder loop (no masks on the
+// fast path). Chunks are stitched through sS (5 arrays of NT double2: forward maps, backward maps, first J).
+// Needs nx even. The u arrays carry one row of front padding so that u_{f-1} of the first face of a column is a legal
+// load that returns 0 (it is the u of the last face of the line below, which is 0 by construction).
+constexpr int kRowPad = 48;     // rows of padding behind the arrays (unconditional batch loads run past a column's end)
 constexpr int kYB = 8;          // rows of loads issued ahead of each stretch of work
+constexpr int kYT = 128;        // threads per CTA
+
+__device__ __forceinline__ double2 ld2cg(const double *p) { return __ldcg(reinterpret_cast<const double2 *>(p)); }
+__device__ __forceinline__ double2 ld2g(const double *p) { return __ldg(reinterpret_cast<const double2 *>(p)); }
 
 template <int K, int M1>
-__device__ __forceinline__ void ycol_block(const FusedArgs &a, const RowGeom &g, const int iz, const int xb, const int t,
-                                           double *sT, double *sS, double &acc)
+__device__ __forceinline__ void lohi2(const double2 x0, const double2 x1, const double2 x2, double2 &lo, double2 &hi)
 {
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, NT = blockDim.x;
-    const int COLS = g.colsY, CY = g.Cy, Lc = g.LcY;
-    const int col = lane % COLS, kc = wid * (32 / COLS) + lane / COLS;
+    cell_lo_hi<K, M1>(x0.x, x1.x, x2.x, lo.x, hi.x);
+    cell_lo_hi<K, M1>(x0.y, x1.y, x2.y, lo.y, hi.y);
+}
+
+template <int K, int M1, int NT>
+__device__ __forceinline__ void ycol_block(const FusedArgs &a, const RowGeom &g, const int iz, const int xb, const int t,
+                                           double2 *sT, double2 *sS, double &acc)
+{
+    const int tid = threadIdx.x;
+    const int CPI = g.colsY >> 1, CY = g.Cy, Lc = g.LcY;           // column pairs per item; NT == CPI * CY
+    const int cp = tid % CPI, kc = tid / CPI;
     const int n = a.ny, nx = a.nx;
-    const int ix = xb * COLS + col;
+    const int ix = xb * g.colsY + 2 * cp;
     const bool cv = ix < nx;
-    const int ixc = cv ? ix : nx - 1;            // columns past the mesh redo the last one; nothing of theirs is stored
-    const int f0 = kc * Lc;
-    const int jn = max(0, min(Lc, n + 1 - f0));  // faces f0 .. f0+jn-1
-    const int ncell = max(0, min(jn, n - f0));   // cells f0 .. f0+ncell-1
-    double *sA = sS, *sZ = sS + NT, *sB = sS + 2 * NT, *sJ = sS + 3 * NT, *sJ0 = sS + 4 * NT;
-    double *Tt = sT + tid;
+    const int ixc = cv ? ix : nx - 2;            // column pairs past the mesh redo the last one; nothing of theirs is stored
+    const int f0 = min(kc * Lc, n + 1);
+    const int ncell = max(0, min(Lc, n - f0));   // cells f0 .. f0+ncell-1
+    const int jn = (ncell > 0 && f0 + ncell == n) ? ncell + 1 : ncell;          // faces f0 .. f0+jn-1 (top face: last chunk)
+    double2 *sA = sS, *sZ = sS + NT, *sB = sS + 2 * NT, *sJ = sS + 3 * NT, *sJ0 = sS + 4 * NT;
+    double2 *Tt = sT + tid;
     const double w = a.w[t];
-    const size_t snx = (size_t)nx;
+    const size_t S = (size_t)nx;                 // row stride (doubles)
     const size_t cell0 = (size_t)iz * n * nx + ixc + (size_t)f0 * nx;
     const double *gp0 = a.p + (size_t)a.mode[1][t][0] * a.ne + cell0;
     const double *gp1 = a.p + (size_t)a.mode[1][t][M1 >= 2 ? 1 : 0] * a.ne + cell0;
@@ -356,165 +375,202 @@ __device__ __forceinline__ void ycol_block(const FusedArgs &a, const RowGeom &g,
     double *gy0 = a.yp + (size_t)a.mode[1][t][0] * a.ne + cell0;
     double *gy1 = a.yp + (size_t)a.mode[1][t][M1 >= 2 ? 1 : 0] * a.ne + cell0;
     double *gy2 = a.yp + (size_t)a.mode[1][t][M1 >= 3 ? 2 : 0] * a.ne + cell0;
-    const double *gu = a.u[1] + (size_t)iz * (n + 1) * nx + ixc + (size_t)f0 * nx;
+    const double *gu = a.u[1] + (size_t)iz * (n + 1) * nx + ixc + (size_t)f0 * nx;       // u_f at gu + j*S, u_{f-1} at gu + (j-1)*S
     const double *gm = a.minv[1] + (size_t)iz * (n + 1) * nx + ixc + (size_t)f0 * nx;
+    const double2 zero2 = make_double2(0.0, 0.0);
     // ---- right-hand side T_f = lo(f-1) - hi(f); p was written during this launch or the previous one: L2 loads
     {
-        double lop = 0.0, dum;
-        {
-            const double *q0 = (f0 > 0) ? gp0 - snx : gp0, *q1 = (f0 > 0) ? gp1 - snx : gp1, *q2 = (f0 > 0) ? gp2 - snx : gp2;
-            const double x0 = __ldcg(q0), x1 = (K >= 1 && M1 >= 2) ? __ldcg(q1) : 0.0, x2 = (K >= 2 && M1 >= 3) ? __ldcg(q2) : 0.0;
-            cell_lo_hi<K, M1>(x0, x1, x2, lop, dum);
-            if (!(f0 > 0 && f0 - 1 < n)) lop = 0.0;
+        double2 lop = zero2, dum;
+        if (f0 > 0 && f0 <= n) lohi2<K, M1>(ld2cg(gp0 - S), (K >= 1 && M1 >= 2) ? ld2cg(gp1 - S) : zero2, (K >= 2 && M1 >= 3) ? ld2cg(gp2 - S) : zero2, lop, dum);
+        int j = 0;
+        for (; j + kYB <= ncell; j += kYB) {
+            double2 x0[kYB], x1[kYB], x2[kYB];
+            const double *q0 = gp0 + j * S, *q1 = gp1 + j * S, *q2 = gp2 + j * S;
+#pragma unroll
+            for (int i = 0; i < kYB; ++i) {
+                x0[i] = ld2cg(q0 + i * S);
+                x1[i] = (K >= 1 && M1 >= 2) ? ld2cg(q1 + i * S) : zero2;
+                x2[i] = (K >= 2 && M1 >= 3) ? ld2cg(q2 + i * S) : zero2;
+            }
+            double2 *Tb = Tt + j * NT;
+#pragma unroll
+            for (int i = 0; i < kYB; ++i) {
+                double2 lo, hi;
+                lohi2<K, M1>(x0[i], x1[i], x2[i], lo, hi);
+                Tb[i * NT] = make_double2(lop.x - hi.x, lop.y - hi.y);
+                lop = lo;
+            }
         }
-        for (int jb = 0; jb < jn; jb += kYB) {
-            double x0[kYB], x1[kYB], x2[kYB];
-            const double *q0 = gp0 + jb * snx, *q1 = gp1 + jb * snx, *q2 = gp2 + jb * snx;
-#pragma unroll
-            for (int i = 0; i < kYB; ++i) {
-                x0[i] = __ldcg(q0 + i * snx);
-                x1[i] = (K >= 1 && M1 >= 2) ? __ldcg(q1 + i * snx) : 0.0;
-                x2[i] = (K >= 2 && M1 >= 3) ? __ldcg(q2 + i * snx) : 0.0;
-            }
-#pragma unroll
-            for (int i = 0; i < kYB; ++i) {
-                const int j = jb + i;
-                if (j < jn) {
-                    double lo, hi;
-                    const bool cj = j < ncell;          // j == ncell < jn is the face past the last cell: hi = 0
-                    cell_lo_hi<K, M1>(cj ? x0[i] : 0.0, cj ? x1[i] : 0.0, cj ? x2[i] : 0.0, lo, hi);
-                    Tt[j * NT] = lop - hi;
-                    lop = lo;
-                }
-            }
+        for (; j < jn; ++j) {
+            double2 lo = zero2, hi = zero2;
+            if (j < ncell) lohi2<K, M1>(ld2cg(gp0 + j * S), (K >= 1 && M1 >= 2) ? ld2cg(gp1 + j * S) : zero2, (K >= 2 && M1 >= 3) ? ld2cg(gp2 + j * S) : zero2, lo, hi);
+            Tt[j * NT] = make_double2(lop.x - hi.x, lop.y - hi.y);         // top face of the line: hi = 0
+            lop = lo;
         }
     }
-    const int slot = kc * COLS + col;
+    const int slot = kc * CPI + cp;
+    const int nfull = (jn / kYB) * kYB;          // rows covered by full batches
     // ---- A: local forward substitution from z_in = 0 and the chunk's multiplier
-    double A = 1.0, z = 0.0;
-    for (int jb = 0; jb < jn; jb += kYB) {
-        double uu[kYB], tt[kYB];
+    double2 A = make_double2(1.0, 1.0), z = zero2;
+    {
+        int j = 0;
+        for (; j < nfull; j += kYB) {
+            double2 uu[kYB], tt[kYB];
+            const double *qu = gu + j * S - S;
+            const double2 *Tb = Tt + j * NT;
 #pragma unroll
-        for (int i = 0; i < kYB; ++i) {
-            const int j = jb + i;
-            const int jm = (j + f0 > 0) ? j - 1 : 0;
-            const double v = __ldg(gu + (long long)jm * (long long)snx);
-            uu[i] = (j + f0 > 0) ? v : 0.0;                       // u_{f-1}, 0 at the first face of the line
-            tt[i] = Tt[min(j, Lc - 1) * NT];
+            for (int i = 0; i < kYB; ++i) { uu[i] = ld2g(qu + i * S); tt[i] = Tb[i * NT]; }
+#pragma unroll
+            for (int i = 0; i < kYB; ++i) {
+                z.x = tt[i].x - uu[i].x * z.x; z.y = tt[i].y - uu[i].y * z.y;
+                A.x *= -uu[i].x; A.y *= -uu[i].y;
+            }
         }
-#pragma unroll
-        for (int i = 0; i < kYB; ++i)
-            if (jb + i < jn) { z = tt[i] - uu[i] * z; A *= -uu[i]; }
+        for (; j < jn; ++j) {
+            const double2 uu = ld2g(gu + j * S - S), tt = Tt[j * NT];
+            z.x = tt.x - uu.x * z.x; z.y = tt.y - uu.y * z.y;
+            A.x *= -uu.x; A.y *= -uu.y;
+        }
     }
     sA[slot] = A; sZ[slot] = z;
     __syncthreads();
-    double zin = 0.0;
-    for (int kk = 0; kk < kc; ++kk) zin = sA[kk * COLS + col] * zin + sZ[kk * COLS + col];
-    // ---- B: forward substitution with the true incoming value; T <- d_f = z_f / m_f; q = sum_f z_f^2 / m_f
-    double q = 0.0;
-    z = zin;
-    for (int jb = 0; jb < jn; jb += kYB) {
-        double uu[kYB], mm[kYB], tt[kYB];
-#pragma unroll
-        for (int i = 0; i < kYB; ++i) {
-            const int j = jb + i;
-            const int jm = (j + f0 > 0) ? j - 1 : 0;
-            const double v = __ldg(gu + (long long)jm * (long long)snx);
-            uu[i] = (j + f0 > 0) ? v : 0.0;
-            mm[i] = __ldg(gm + j * snx);
-            tt[i] = Tt[min(j, Lc - 1) * NT];
-        }
-#pragma unroll
-        for (int i = 0; i < kYB; ++i)
-            if (jb + i < jn) {
-                z = tt[i] - uu[i] * z;
-                const double d = mm[i] * z;
-                q += z * d;
-                Tt[(jb + i) * NT] = d;
-            }
+    double2 zin = zero2;
+    for (int kk = 0; kk < kc; ++kk) {
+        const double2 Ak = sA[kk * CPI + cp], zk = sZ[kk * CPI + cp];
+        zin.x = Ak.x * zin.x + zk.x; zin.y = Ak.y * zin.y + zk.y;
     }
-    if (cv) acc += w * q;
-    // ---- C: local backward substitution J_f = d_f - u_f J_{f+1} from J_in = 0 and the chunk's multiplier
-    double Bp = 1.0, J = 0.0;
-    for (int jb = ((jn - 1) / kYB) * kYB; jb >= 0 && jn > 0; jb -= kYB) {
-        double uu[kYB], tt[kYB];
+    // ---- B: forward substitution with the true incoming value; T <- d_f = z_f / m_f; q = sum_f z_f^2 / m_f
+    double2 q = zero2;
+    z = zin;
+    {
+        int j = 0;
+        for (; j < nfull; j += kYB) {
+            double2 uu[kYB], mm[kYB], tt[kYB];
+            const double *qu = gu + j * S - S, *qm = gm + j * S;
+            double2 *Tb = Tt + j * NT;
 #pragma unroll
-        for (int i = kYB - 1; i >= 0; --i) {
-            const int j = jb + i;
-            uu[i] = __ldg(gu + j * snx);                          // u of the last face of a line is 0
-            tt[i] = Tt[min(j, Lc - 1) * NT];
+            for (int i = 0; i < kYB; ++i) { uu[i] = ld2g(qu + i * S); mm[i] = ld2g(qm + i * S); tt[i] = Tb[i * NT]; }
+#pragma unroll
+            for (int i = 0; i < kYB; ++i) {
+                z.x = tt[i].x - uu[i].x * z.x; z.y = tt[i].y - uu[i].y * z.y;
+                const double2 d = make_double2(mm[i].x * z.x, mm[i].y * z.y);
+                q.x += z.x * d.x; q.y += z.y * d.y;
+                Tb[i * NT] = d;
+            }
         }
+        for (; j < jn; ++j) {
+            const double2 uu = ld2g(gu + j * S - S), mm = ld2g(gm + j * S), tt = Tt[j * NT];
+            z.x = tt.x - uu.x * z.x; z.y = tt.y - uu.y * z.y;
+            const double2 d = make_double2(mm.x * z.x, mm.y * z.y);
+            q.x += z.x * d.x; q.y += z.y * d.y;
+            Tt[j * NT] = d;
+        }
+    }
+    if (cv) acc += w * (q.x + q.y);
+    // ---- C: local backward substitution J_f = d_f - u_f J_{f+1} from J_in = 0 and the chunk's multiplier
+    double2 Bp = make_double2(1.0, 1.0), J = zero2;
+    {
+        int j = jn - 1;
+        for (; j >= nfull; --j) {
+            const double2 uu = ld2g(gu + j * S), tt = Tt[j * NT];           // u of the last face of a line is 0
+            J.x = tt.x - uu.x * J.x; J.y = tt.y - uu.y * J.y;
+            Bp.x *= -uu.x; Bp.y *= -uu.y;
+        }
+        for (j = nfull - kYB; j >= 0; j -= kYB) {
+            double2 uu[kYB], tt[kYB];
+            const double *qu = gu + j * S;
+            const double2 *Tb = Tt + j * NT;
 #pragma unroll
-        for (int i = kYB - 1; i >= 0; --i)
-            if (jb + i < jn) { J = tt[i] - uu[i] * J; Bp *= -uu[i]; }
+            for (int i = kYB - 1; i >= 0; --i) { uu[i] = ld2g(qu + i * S); tt[i] = Tb[i * NT]; }
+#pragma unroll
+            for (int i = kYB - 1; i >= 0; --i) {
+                J.x = tt[i].x - uu[i].x * J.x; J.y = tt[i].y - uu[i].y * J.y;
+                Bp.x *= -uu[i].x; Bp.y *= -uu[i].y;
+            }
+        }
     }
     sB[slot] = Bp; sJ[slot] = J;
     __syncthreads();
-    double Jin = 0.0;
-    for (int kk = CY - 1; kk > kc; --kk) Jin = sB[kk * COLS + col] * Jin + sJ[kk * COLS + col];
+    double2 Jin = zero2;
+    for (int kk = CY - 1; kk > kc; --kk) {
+        const double2 Bk = sB[kk * CPI + cp], Jk = sJ[kk * CPI + cp];
+        Jin.x = Bk.x * Jin.x + Jk.x; Jin.y = Bk.y * Jin.y + Jk.y;
+    }
     // ---- D: backward substitution with the true incoming value; T <- J
     J = Jin;
-    for (int jb = ((jn - 1) / kYB) * kYB; jb >= 0 && jn > 0; jb -= kYB) {
-        double uu[kYB], tt[kYB];
-#pragma unroll
-        for (int i = kYB - 1; i >= 0; --i) {
-            const int j = jb + i;
-            uu[i] = __ldg(gu + j * snx);
-            tt[i] = Tt[min(j, Lc - 1) * NT];
+    {
+        int j = jn - 1;
+        for (; j >= nfull; --j) {
+            const double2 uu = ld2g(gu + j * S), tt = Tt[j * NT];
+            J.x = tt.x - uu.x * J.x; J.y = tt.y - uu.y * J.y;
+            Tt[j * NT] = J;
         }
+        for (j = nfull - kYB; j >= 0; j -= kYB) {
+            double2 uu[kYB], tt[kYB];
+            const double *qu = gu + j * S;
+            double2 *Tb = Tt + j * NT;
 #pragma unroll
-        for (int i = kYB - 1; i >= 0; --i)
-            if (jb + i < jn) { J = tt[i] - uu[i] * J; Tt[(jb + i) * NT] = J; }
-    }
-    sJ0[slot] = (jn > 0) ? J : 0.0;               // J of the chunk's first face
-    __syncthreads();
-    const double Jnext = (kc + 1 < CY) ? sJ0[(kc + 1) * COLS + col] : 0.0;
-    // ---- yp += w B_y J for the cells f0 .. f0+ncell-1 of this column
-    for (int jb = 0; jb < ncell; jb += kYB) {
-        double y0[kYB], y1[kYB], y2[kYB], jj[kYB + 1];
-        double *q0 = gy0 + jb * snx, *q1 = gy1 + jb * snx, *q2 = gy2 + jb * snx;
+            for (int i = kYB - 1; i >= 0; --i) { uu[i] = ld2g(qu + i * S); tt[i] = Tb[i * NT]; }
 #pragma unroll
-        for (int i = 0; i < kYB; ++i) {
-            y0[i] = __ldcg(q0 + i * snx);
-            y1[i] = (M1 >= 2) ? __ldcg(q1 + i * snx) : 0.0;
-            y2[i] = (M1 >= 3) ? __ldcg(q2 + i * snx) : 0.0;
-        }
-#pragma unroll
-        for (int i = 0; i <= kYB; ++i) {
-            const int j = jb + i;
-            jj[i] = Tt[min(j, Lc - 1) * NT];
-            if (j >= jn) jj[i] = Jnext;                          // first face of the next chunk (0 past the line)
-        }
-#pragma unroll
-        for (int i = 0; i < kYB; ++i) {
-            if (jb + i < ncell && cv) {
-                const double JL = jj[i], JR = jj[i + 1];
-                q0[i * snx] = y0[i] + w * (JR - JL);
-                if (M1 >= 2) q1[i * snx] = y1[i] + ((K >= 1) ? w * (5.0 / 6.0) * (JL + JR) : 0.0);
-                if (M1 >= 3) q2[i * snx] = y2[i] + ((K >= 2) ? w * (7.0 / 10.0) * (JR - JL) : 0.0);
+            for (int i = kYB - 1; i >= 0; --i) {
+                J.x = tt[i].x - uu[i].x * J.x; J.y = tt[i].y - uu[i].y * J.y;
+                Tb[i * NT] = J;
             }
+        }
+    }
+    sJ0[slot] = (jn > 0) ? J : zero2;             // J of the chunk's first face (0 for chunks past the line)
+    __syncthreads();
+    const double2 Jnext = (kc + 1 < CY) ? sJ0[(kc + 1) * CPI + cp] : zero2;
+    // ---- yp += w B_y J for the cells f0 .. f0+ncell-1 of this column pair
+    if (cv) {
+        auto put = [&](double *y0p, double *y1p, double *y2p, const double2 y0, const double2 y1, const double2 y2, const double2 JL,
+                       const double2 JR) {
+            *reinterpret_cast<double2 *>(y0p) = make_double2(y0.x + w * (JR.x - JL.x), y0.y + w * (JR.y - JL.y));
+            if (M1 >= 2)
+                *reinterpret_cast<double2 *>(y1p) = (K >= 1) ? make_double2(y1.x + w * (5.0 / 6.0) * (JL.x + JR.x), y1.y + w * (5.0 / 6.0) * (JL.y + JR.y)) : y1;
+            if (M1 >= 3)
+                *reinterpret_cast<double2 *>(y2p) = (K >= 2) ? make_double2(y2.x + w * (7.0 / 10.0) * (JR.x - JL.x), y2.y + w * (7.0 / 10.0) * (JR.y - JL.y)) : y2;
+        };
+        int j = 0;
+        for (; j + kYB <= ncell; j += kYB) {
+            double2 y0[kYB], y1[kYB], y2[kYB], jj[kYB + 1];
+            double *q0 = gy0 + j * S, *q1 = gy1 + j * S, *q2 = gy2 + j * S;
+            const double2 *Tb = Tt + j * NT;
+#pragma unroll
+            for (int i = 0; i < kYB; ++i) {
+                y0[i] = ld2cg(q0 + i * S);
+                y1[i] = (M1 >= 2) ? ld2cg(q1 + i * S) : zero2;
+                y2[i] = (M1 >= 3) ? ld2cg(q2 + i * S) : zero2;
+                jj[i] = Tb[i * NT];
+            }
+            jj[kYB] = (j + kYB < jn) ? Tb[kYB * NT] : Jnext;
+#pragma unroll
+            for (int i = 0; i < kYB; ++i) put(q0 + i * S, q1 + i * S, q2 + i * S, y0[i], y1[i], y2[i], jj[i], jj[i + 1]);
+        }
+        for (; j < ncell; ++j) {
+            const double2 JL = Tt[j * NT], JR = (j + 1 < jn) ? Tt[(j + 1) * NT] : Jnext;
+            put(gy0 + j * S, gy1 + j * S, gy2 + j * S, ld2cg(gy0 + j * S), (M1 >= 2) ? ld2cg(gy1 + j * S) : zero2,
+                (M1 >= 3) ? ld2cg(gy2 + j * S) : zero2, JL, JR);
         }
     }
     __syncthreads();        // sS is reused by the next item
 }
 
-constexpr int kYTmax = 256;
-
-// yp += (y part of S p) ; red_out = p^T (y part) p.   Dynamic shared memory: (LcY + 5) * blockDim doubles.
+// yp += (y part of S p) ; red_out = p^T (y part) p.   Dynamic shared memory: (LcY + 1 + 5) * kYT double2.
 template <int K, int M1>
-__global__ void __launch_bounds__(kYTmax) k_ycol(const FusedArgs a, const RowGeom g, double *red_part, unsigned *ticket,
-                                                 double *red_out)
+__global__ void __launch_bounds__(kYT) k_ycol(const FusedArgs a, const RowGeom g, double *red_part, unsigned *ticket,
+                                              double *red_out)
 {
     if (a.st->done) return;
     extern __shared__ __align__(16) double sm[];
-    double *sT = sm, *sS = sm + (size_t)g.LcY * blockDim.x;
+    double2 *sT = reinterpret_cast<double2 *>(sm), *sS = sT + (size_t)(g.LcY + 1) * kYT;
     const int nxb = (a.nx + g.colsY - 1) / g.colsY;
     const long long nitems = (long long)a.nz * nxb * a.nt;
     double acc = 0.0;
     for (long long item = blockIdx.x; item < nitems; item += gridDim.x) {
         const int t = (int)(item % a.nt);
         const long long r = item / a.nt;
-        ycol_block<K, M1>(a, g, (int)(r / nxb), (int)(r % nxb), t, sT, sS, acc);
+        ycol_block<K, M1, kYT>(a, g, (int)(r / nxb), (int)(r % nxb), t, sT, sS, acc);
     }
     double v[1] = {acc};
     grid_reduce<1>(v, red_part, ticket, red_out);

@@ -86,7 +86,8 @@ def test_hybrid_equals_separate_kernels(n, rt, pp, mode):
     assert relerr(phi1, phi0) < 1e-8
 
 
-ROW_CASES = CASES + [((270, 5, 3), 1, 1), ((6, 300, 3), 1, 1), ((40, 37, 5), 2, 2), ((530, 4, 2), 1, 0)]
+ROW_CASES = CASES + [((270, 5, 3), 1, 1), ((6, 300, 3), 1, 1), ((40, 37, 5), 2, 2), ((530, 4, 2), 1, 0), ((256, 20, 2), 1, 1),
+                     ((512, 6, 2), 1, 1), ((12, 256, 2), 1, 1), ((10, 129, 3), 0, 0), ((264, 16, 2), 2, 2)]
 
 
 @pytest.mark.parametrize("n,rt,pp", ROW_CASES)
@@ -98,7 +99,10 @@ def test_rows_equals_separate_kernels(n, rt, pp, mode):
     rhs = np.random.default_rng(8).uniform(0.0, 1.0, n[0] * n[1] * n[2] * nloc)
     phi0, it0, res0, kt0 = _solve(p, rt, pp, mode, rhs, 0)
     phi1, it1, res1, kt1 = _solve(p, rt, pp, mode, rhs, 3)
-    assert kt1["path"] == 3.0 and kt1["xrow"] > 0.0 and kt1["ycol"] > 0.0
+    if n[0] % 2 == 0:           # the y columns are processed two at a time: odd nx falls back to the separate kernels
+        assert kt1["path"] == 3.0 and kt1["xrow"] > 0.0 and kt1["ycol"] > 0.0
+    else:
+        assert kt1["path"] == 0.0
     assert abs(it1 - it0) <= 2
     assert res1 < 1e-10
     assert relerr(phi1, phi0) < 1e-8
