@@ -367,33 +367,34 @@ static bool rows_geometry(const nf_ctx *c, RowGeom &g)
     return true;
 }
 
-template <int K, int M1, int NCL, bool FULL>
-static int rows_prepare_x(nf_ctx *c)
-{
-    const size_t smem = (size_t)kXW * c->rg.xsmemW * sizeof(double);
-    if (smem + 2048 > c->smem_optin) { c->xrow_grid = 0; return NF_OK; }
-    CU(c, cudaFuncSetAttribute(k_xrow<K, M1, NCL, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_xrow<K, M1, NCL, FULL>, 32 * kXW, smem));
-    const long long nrows = (long long)c->ny * c->nz;
-    c->xrow_grid = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(kRedBlocks, (long long)per_sm * c->sm_count), (nrows + kXW - 1) / kXW));
-    return NF_OK;
-}
+// variants of the x-row code: cells per lane (8 / 16 / 33), all chunks full (no guards) or not
+#define NF_ROWS_VARIANTS(ncl, full, CALL)                                                     \
+    do {                                                                                      \
+        if ((ncl) <= 8) { if (full) CALL(8, true); else CALL(8, false); }                     \
+        else if ((ncl) <= 16) { if (full) CALL(16, true); else CALL(16, false); }             \
+        else CALL(33, false);                                                                 \
+    } while (0)
 
 template <int K, int M1>
 static int rows_prepare_t(nf_ctx *c)
 {
-    const int ncl = (c->nx + 31) / 32;
-    const bool full = (c->rg.LcX == kLC);          // every chunk of an x line runs all kLC steps (no guards)
-    int r = (ncl <= 8) ? (full ? rows_prepare_x<K, M1, 8, true>(c) : rows_prepare_x<K, M1, 8, false>(c))
-                       : (ncl <= 16 ? (full ? rows_prepare_x<K, M1, 16, true>(c) : rows_prepare_x<K, M1, 16, false>(c))
-                                    : rows_prepare_x<K, M1, 33, false>(c));
-    if (r) return r;
-    int per_sm = 0;
+    const size_t smem = (size_t)kXW * c->rg.xsmemW * sizeof(double);
     const size_t ysmem = (size_t)(c->rg.LcY + 1 + 5) * kYT * sizeof(double2);
-    if (ysmem + 2048 > c->smem_optin) { c->xrow_grid = 0; return NF_OK; }
+    c->xrow_grid = 0;
+    if (smem + 2048 > c->smem_optin || ysmem + 2048 > c->smem_optin) return NF_OK;
+    int per_sm = 0;
+#define CALL(NCLV, FULLV)                                                                                                                  \
+    do {                                                                                                                                   \
+        CU(c, cudaFuncSetAttribute(k_xrow<K, M1, NCLV, kLC, FULLV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
+        CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_xrow<K, M1, NCLV, kLC, FULLV>, 32 * kXW, smem));                   \
+    } while (0)
+    NF_ROWS_VARIANTS((c->nx + 31) / 32, c->rg.LcX == kLC, CALL);
+#undef CALL
+    if (per_sm < 1) return NF_OK;
+    const long long nrows = (long long)c->ny * c->nz;
+    c->xrow_grid = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(kRedBlocks, (long long)per_sm * c->sm_count), (nrows + kXW - 1) / kXW));
     CU(c, cudaFuncSetAttribute(k_ycol<K, M1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ysmem));
-    CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ycol<K, M1>, 32 * c->rg.warpsY, ysmem));
+    CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ycol<K, M1>, kYT, ysmem));
     const long long nitems = (long long)c->nz * ((c->nx + c->rg.colsY - 1) / c->rg.colsY) * c->nt;
     c->ycol_grid = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(kRedBlocks, (long long)std::max(per_sm, 1) * c->sm_count), nitems));
     return NF_OK;
@@ -411,15 +412,11 @@ template <int K, int M1>
 static int rows_launch_t(nf_ctx *c, const FusedArgs &a, int which)
 {
     if (which & 1) {
-        const int ncl = (c->nx + 31) / 32;
         const size_t smem = (size_t)kXW * c->rg.xsmemW * sizeof(double);
         double *part = c->d_part + (size_t)0 * kRedBlocks;
-        const bool full = (c->rg.LcX == kLC);
-#define NF_XROW(NCLV, FULLV) LAUNCH(c, (k_xrow<K, M1, NCLV, FULLV>), c->xrow_grid, 32 * kXW, smem, a, c->rg, part, c->d_ticket + 0, &c->d_cg->pAp[0])
-        if (ncl <= 8) { if (full) NF_XROW(8, true); else NF_XROW(8, false); }
-        else if (ncl <= 16) { if (full) NF_XROW(16, true); else NF_XROW(16, false); }
-        else NF_XROW(33, false);
-#undef NF_XROW
+#define CALL(NCLV, FULLV) LAUNCH(c, (k_xrow<K, M1, NCLV, kLC, FULLV>), c->xrow_grid, 32 * kXW, smem, a, c->rg, part, c->d_ticket + 0, &c->d_cg->pAp[0])
+        NF_ROWS_VARIANTS((c->nx + 31) / 32, c->rg.LcX == kLC, CALL);
+#undef CALL
     }
     if (which & 2)
         LAUNCH(c, (k_ycol<K, M1>), c->ycol_grid, kYT, (size_t)(c->rg.LcY + 1 + 5) * kYT * sizeof(double2), a, c->rg,
@@ -435,6 +432,7 @@ static int rows_launch(nf_ctx *c, const FusedArgs &a, int which)
 #undef CALL
 }
 
+
 // Decide once per context whether the fused path applies (3-D, single GPU, lines fit in shared memory) and build its
 // work-item queue: round r holds the X items of plane r and the Y items of plane r-delay, the Y items starting `lag`
 // X items into the round so that they (almost) never find their plane incomplete.
@@ -442,7 +440,10 @@ static int fused_setup(nf_ctx *c)
 {
     if (c->fused >= 0) return NF_OK;
     c->fused = 0;
-    const int want_mode = env_int("NF_FUSED", 1);
+    // NF_FUSED selects the CG-iteration path of 3-D single-GPU contexts (development / test knob): unset = rows path (3)
+    // with the hybrid path (2) as fallback; 0 = separate kernels, 1 = plane-ordered fused kernel, 2 = hybrid, 3 = rows.
+    const bool auto_mode = (getenv("NF_FUSED") == nullptr || !*getenv("NF_FUSED"));
+    int want_mode = auto_mode ? 3 : env_int("NF_FUSED", 3);
     if (c->dim != 3 || c->slab || want_mode == 0) return NF_OK;
     if (want_mode == 3) {                 // rows: k_xrow (direction update + x) + k_ycol + k_zfwd + k_zback_update
         if (rows_geometry(c, c->rg)) {
@@ -454,7 +455,8 @@ static int fused_setup(nf_ctx *c)
                 return NF_OK;
             }
         }
-        return NF_OK;                     // lines too long for the register-resident solvers: separate kernels
+        if (!auto_mode) return NF_OK;     // odd nx / lines too long for the register-resident solvers: separate kernels
+        want_mode = 2;
     }
     if (want_mode == 2) {                 // hybrid: separate x / y sweeps + k_zfwd + k_zback_update
         const size_t nxy2 = (size_t)c->nx * c->ny;
@@ -551,14 +553,23 @@ static int fused_launch_t(nf_ctx *c, const FusedArgs &a, int which)
         case 8: LAUNCH(c, (k_plane_fwd<K, M1, 8>), c->fgrid, kFT, c->fsmem, a); break;
         }
     }
+    // the marching kernels are persistent grid-stride loops: whole waves of resident CTAs only (no ragged last wave)
+    static int occ_zf = 0, occ_zb = 0;
+    if (!occ_zf) {
+        CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_zf, k_zfwd<K, M1>, 128, 0));
+        CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_zb, k_zback_update<K, M1>, 128, 0));
+        occ_zf = std::max(occ_zf, 1); occ_zb = std::max(occ_zb, 1);
+    }
     if (which & 4) {
         const long long nitems = (long long)c->ny * c->nt * ((c->nx + 31) / 32);
-        const int grid = (int)std::max<long long>(1, std::min<long long>(kRedBlocks, (nitems + 3) / 4));
+        const int waves = std::max(1, kRedBlocks / (occ_zf * c->sm_count));
+        const int grid = (int)std::max<long long>(1, std::min<long long>((long long)waves * occ_zf * c->sm_count, (nitems + 3) / 4));
         LAUNCH(c, (k_zfwd<K, M1>), grid, 128, 0, a, c->d_part + (size_t)2 * kRedBlocks, c->d_ticket + 2, &c->d_cg->pAp[2]);
     }
     if (which & 2) {
         const long long nitems = (long long)c->ny * c->nt * ((c->nx + 31) / 32);
-        const int grid = (int)std::max<long long>(1, std::min<long long>(kRedBlocks, (nitems + 3) / 4));
+        const int waves = std::max(1, kRedBlocks / (occ_zb * c->sm_count));
+        const int grid = (int)std::max<long long>(1, std::min<long long>((long long)waves * occ_zb * c->sm_count, (nitems + 3) / 4));
         LAUNCH(c, (k_zback_update<K, M1>), grid, 128, 0, a);
     }
     CU(c, cudaGetLastError());

@@ -34,39 +34,39 @@ struct RowGeom {
 
 // ---- the four passes over a register-resident chunk -------------------------------------------------------------------
 // um(j) = u_{f0+j-1} (0 at the first face of the line), uf(j) = u_{f0+j} (0 at the last face), mi(j) = 1/m_{f0+j}.
-// LB = loads issued ahead of each stretch of the dependent recurrence. FULL: every chunk runs all kLC steps -- the
+// LB = loads issued ahead of each stretch of the dependent recurrence. FULL: every chunk runs all LCT steps -- the
 // caller guarantees T = 0, u = 0 (1/m finite) past the end of the line, which leaves every result unchanged.
 // A: local forward substitution from z_in = 0 and the chunk's multiplier:  z_out = A z_in + z
-template <int LB, bool FULL, class FU>
-__device__ __forceinline__ void chunk_fwd_map(const double (&T)[kLC], const int jn, FU um, double &A, double &z)
+template <int LCT, int LB, bool FULL, class FU>
+__device__ __forceinline__ void chunk_fwd_map(const double (&T)[LCT], const int jn, FU um, double &A, double &z)
 {
     A = 1.0; z = 0.0;
 #pragma unroll
-    for (int jb = 0; jb < kLC; jb += LB) {
+    for (int jb = 0; jb < LCT; jb += LB) {
         NF_SCHED_FENCE();
         double uu[LB];
 #pragma unroll
-        for (int i = 0; i < LB; ++i) { uu[i] = 0.0; if (jb + i < kLC && (FULL || jb + i < jn)) uu[i] = um(jb + i); }
+        for (int i = 0; i < LB; ++i) { uu[i] = 0.0; if (jb + i < LCT && (FULL || jb + i < jn)) uu[i] = um(jb + i); }
 #pragma unroll
         for (int i = 0; i < LB; ++i)
-            if (jb + i < kLC && (FULL || jb + i < jn)) { z = T[jb + i] - uu[i] * z; A *= -uu[i]; }
+            if (jb + i < LCT && (FULL || jb + i < jn)) { z = T[jb + i] - uu[i] * z; A *= -uu[i]; }
     }
 }
 
 // B: forward substitution with the true incoming value; T <- d_f = z_f / m_f; returns sum_f z_f^2 / m_f of the chunk
-template <int LB, bool FULL, class FU, class FM>
-__device__ __forceinline__ double chunk_fwd_final(double (&T)[kLC], const int jn, FU um, FM mi, double z)
+template <int LCT, int LB, bool FULL, class FU, class FM>
+__device__ __forceinline__ double chunk_fwd_final(double (&T)[LCT], const int jn, FU um, FM mi, double z)
 {
     double q = 0.0;
 #pragma unroll
-    for (int jb = 0; jb < kLC; jb += LB) {
+    for (int jb = 0; jb < LCT; jb += LB) {
         NF_SCHED_FENCE();
         double uu[LB], mm[LB];
 #pragma unroll
-        for (int i = 0; i < LB; ++i) { uu[i] = mm[i] = 0.0; if (jb + i < kLC && (FULL || jb + i < jn)) { uu[i] = um(jb + i); mm[i] = mi(jb + i); } }
+        for (int i = 0; i < LB; ++i) { uu[i] = mm[i] = 0.0; if (jb + i < LCT && (FULL || jb + i < jn)) { uu[i] = um(jb + i); mm[i] = mi(jb + i); } }
 #pragma unroll
         for (int i = 0; i < LB; ++i)
-            if (jb + i < kLC && (FULL || jb + i < jn)) {
+            if (jb + i < LCT && (FULL || jb + i < jn)) {
                 z = T[jb + i] - uu[i] * z;
                 const double d = mm[i] * z;
                 q += z * d;
@@ -77,35 +77,35 @@ __device__ __forceinline__ double chunk_fwd_final(double (&T)[kLC], const int jn
 }
 
 // C: local backward substitution J_f = d_f - u_f J_{f+1} from J_in = 0 and the chunk's multiplier:  J_out = Bp J_in + J
-template <int LB, bool FULL, class FU>
-__device__ __forceinline__ void chunk_bwd_map(const double (&T)[kLC], const int jn, FU uf, double &Bp, double &J)
+template <int LCT, int LB, bool FULL, class FU>
+__device__ __forceinline__ void chunk_bwd_map(const double (&T)[LCT], const int jn, FU uf, double &Bp, double &J)
 {
     Bp = 1.0; J = 0.0;
 #pragma unroll
-    for (int jb = ((kLC - 1) / LB) * LB; jb >= 0; jb -= LB) {
+    for (int jb = ((LCT - 1) / LB) * LB; jb >= 0; jb -= LB) {
         NF_SCHED_FENCE();
         double uu[LB];
 #pragma unroll
-        for (int i = LB - 1; i >= 0; --i) { uu[i] = 0.0; if (jb + i < kLC && (FULL || jb + i < jn)) uu[i] = uf(jb + i); }
+        for (int i = LB - 1; i >= 0; --i) { uu[i] = 0.0; if (jb + i < LCT && (FULL || jb + i < jn)) uu[i] = uf(jb + i); }
 #pragma unroll
         for (int i = LB - 1; i >= 0; --i)
-            if (jb + i < kLC && (FULL || jb + i < jn)) { J = T[jb + i] - uu[i] * J; Bp *= -uu[i]; }
+            if (jb + i < LCT && (FULL || jb + i < jn)) { J = T[jb + i] - uu[i] * J; Bp *= -uu[i]; }
     }
 }
 
 // D: backward substitution with the true incoming value; T <- J
-template <int LB, bool FULL, class FU>
-__device__ __forceinline__ void chunk_bwd_final(double (&T)[kLC], const int jn, FU uf, double J)
+template <int LCT, int LB, bool FULL, class FU>
+__device__ __forceinline__ void chunk_bwd_final(double (&T)[LCT], const int jn, FU uf, double J)
 {
 #pragma unroll
-    for (int jb = ((kLC - 1) / LB) * LB; jb >= 0; jb -= LB) {
+    for (int jb = ((LCT - 1) / LB) * LB; jb >= 0; jb -= LB) {
         NF_SCHED_FENCE();
         double uu[LB];
 #pragma unroll
-        for (int i = LB - 1; i >= 0; --i) { uu[i] = 0.0; if (jb + i < kLC && (FULL || jb + i < jn)) uu[i] = uf(jb + i); }
+        for (int i = LB - 1; i >= 0; --i) { uu[i] = 0.0; if (jb + i < LCT && (FULL || jb + i < jn)) uu[i] = uf(jb + i); }
 #pragma unroll
         for (int i = LB - 1; i >= 0; --i)
-            if (jb + i < kLC && (FULL || jb + i < jn)) { J = T[jb + i] - uu[i] * J; T[jb + i] = J; }
+            if (jb + i < LCT && (FULL || jb + i < jn)) { J = T[jb + i] - uu[i] * J; T[jb + i] = J; }
     }
 }
 
@@ -115,7 +115,7 @@ __device__ __forceinline__ void chunk_bwd_final(double (&T)[kLC], const int jn, 
 // NCL = compile-time bound on the cells a lane owns (ceil(nx / 32)): per-cell coefficients live in registers.
 constexpr int kCB = 8;          // cells per lane in one coalesced batch (256 cells)
 
-template <int K, int M1, int NCL, bool FULL>
+template <int K, int M1, int NCL, int LCT, bool FULL>
 __device__ __forceinline__ void xrow_warp(const FusedArgs &a, const RowGeom &g, const int iz, const int iy, const double beta,
                                           double *sm, double &acc)
 {
@@ -219,13 +219,13 @@ __device__ __forceinline__ void xrow_warp(const FusedArgs &a, const RowGeom &g, 
         // ---- chunk ownership: lane = (pair slot s, chunk k)
         const bool tv = s < np;
         const int sp = tv ? s : 0;
-        double T[kLC];
+        double T[LCT];
         {
             const double *P0 = P + (sp * M1) * PP + f0, *P1 = P0 + (M1 >= 2 ? PP : 0), *P2 = P0 + (M1 >= 3 ? 2 * PP : 0);
             double lop = 0.0, dum;
             if (f0 > 0) cell_lo_hi<K, M1>(P0[-1], P1[-1], P2[-1], lop, dum);
 #pragma unroll
-            for (int j = 0; j < kLC; ++j) {
+            for (int j = 0; j < LCT; ++j) {
                 T[j] = 0.0;
                 if (FULL || j < jn) {
                     double lo, hi;
@@ -240,28 +240,28 @@ __device__ __forceinline__ void xrow_warp(const FusedArgs &a, const RowGeom &g, 
         auto uf = [&](const int j) { return ub[j + 1]; };
         auto mi = [&](const int j) { return mb[j]; };
         double A, z;
-        chunk_fwd_map<11, FULL>(T, jn, um, A, z);
+        chunk_fwd_map<LCT, (LCT > 17 ? 11 : 9), FULL>(T, jn, um, A, z);
         for (int d = 1; d < C; d <<= 1) {
             const double Ap = __shfl_up_sync(full, A, d, C), zp = __shfl_up_sync(full, z, d, C);
             if (k >= d) { z = A * zp + z; A = A * Ap; }
         }
         double zin = __shfl_up_sync(full, z, 1, C);
         if (k == 0) zin = 0.0;
-        const double q = chunk_fwd_final<11, FULL>(T, jn, um, mi, zin);
+        const double q = chunk_fwd_final<LCT, (LCT > 17 ? 11 : 9), FULL>(T, jn, um, mi, zin);
         double Bp, J;
-        chunk_bwd_map<11, FULL>(T, jn, uf, Bp, J);
+        chunk_bwd_map<LCT, (LCT > 17 ? 11 : 9), FULL>(T, jn, uf, Bp, J);
         for (int d = 1; d < C; d <<= 1) {
             const double Bq = __shfl_down_sync(full, Bp, d, C), Jq = __shfl_down_sync(full, J, d, C);
             if (k + d < C) { J = Bp * Jq + J; Bp = Bp * Bq; }
         }
         double Jin = __shfl_down_sync(full, J, 1, C);
         if (k == C - 1) Jin = 0.0;
-        chunk_bwd_final<11, FULL>(T, jn, uf, Jin);
+        chunk_bwd_final<LCT, (LCT > 17 ? 11 : 9), FULL>(T, jn, uf, Jin);
         if (tv) {
             acc += a.w[t0 + s] * q;
             double *Jr = Jb + s * PJ + f0;
 #pragma unroll
-            for (int j = 0; j < kLC; ++j)
+            for (int j = 0; j < LCT; ++j)
                 if (FULL || j < jn) Jr[j] = T[j];
         }
         __syncwarp();
@@ -301,12 +301,14 @@ __device__ __forceinline__ void xrow_warp(const FusedArgs &a, const RowGeom &g, 
     }
 }
 
-constexpr int kXW = 1;      // warps per CTA of the stand-alone x-row kernel (every warp is autonomous)
+constexpr int kXW = 1;      // warps per CTA of the x-row kernel (every warp is autonomous)
 
-// p = M^-1 r + beta p ; yp = diag p + (x part of S p) ; red_out = p^T (diag + x part) p
-template <int K, int M1, int NCL, bool FULL>
-__global__ void __launch_bounds__(32 * kXW) k_xrow(const FusedArgs a, const RowGeom g, double *red_part, unsigned *ticket,
-                                                   double *red_out)
+// p = M^-1 r + beta p ; yp = diag p + (x part of S p) ; red_out = p^T (diag + x part) p.
+// (Letting the z-direction forward substitution ride along here -- rows in plane order, per-row flags for the carry -- was
+// measured and rejected: the nz-long chain of flag hand-overs costs more than the separate marching kernel k_zfwd.)
+template <int K, int M1, int NCL, int LCT, bool FULL>
+__global__ void __launch_bounds__(32 * kXW, 7) k_xrow(const FusedArgs a, const RowGeom g, double *red_part, unsigned *ticket,
+                                                      double *red_out)
 {
     if (a.st->done) return;
     extern __shared__ __align__(16) double sm[];
@@ -321,7 +323,7 @@ __global__ void __launch_bounds__(32 * kXW) k_xrow(const FusedArgs a, const RowG
     const long long nrows = (long long)a.ny * a.nz;
     double acc = 0.0;
     for (long long row = (long long)blockIdx.x * WPB + wib; row < nrows; row += (long long)gridDim.x * WPB)
-        xrow_warp<K, M1, NCL, FULL>(a, g, (int)(row / a.ny), (int)(row % a.ny), beta, wsm, acc);
+        xrow_warp<K, M1, NCL, LCT, FULL>(a, g, (int)(row / a.ny), (int)(row % a.ny), beta, wsm, acc);
     double v[1] = {acc};
     grid_reduce<1>(v, red_part, ticket, red_out);
 }
