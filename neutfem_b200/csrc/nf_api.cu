@@ -360,10 +360,10 @@ static bool rows_geometry(const nf_ctx *c, RowGeom &g)
     g.pitchJ = pj;
     g.xsmemW = (2 * (g.NFx + 2) + g.PWx * c->M1 * g.pitchP + g.PWx * g.pitchJ + 1) & ~1;
     if (c->nx & 1) return false;                  // the y columns are processed two at a time (16-byte vectors)
-    g.warpsY = kYT / 32;
     g.Cy = (c->ny <= 8 * 16) ? 8 : (c->ny <= 16 * 16 ? 16 : 32);      // chunks of <= 16 cells where possible
+    g.warpsY = kYT / 32;                          // (256-thread CTAs for the longest lines were measured slower)
     g.LcY = (c->ny + g.Cy - 1) / g.Cy;            // cells per chunk (the last chunk of a line also owns the top face)
-    g.colsY = 2 * (kYT / g.Cy);
+    g.colsY = 2 * (32 * g.warpsY / g.Cy);
     return true;
 }
 
@@ -379,7 +379,8 @@ template <int K, int M1>
 static int rows_prepare_t(nf_ctx *c)
 {
     const size_t smem = (size_t)kXW * c->rg.xsmemW * sizeof(double);
-    const size_t ysmem = (size_t)(c->rg.LcY + 1 + 5) * kYT * sizeof(double2);
+    const int ynt = 32 * c->rg.warpsY;
+    const size_t ysmem = (size_t)(c->rg.LcY + 1 + 5) * ynt * sizeof(double2);
     c->xrow_grid = 0;
     if (smem + 2048 > c->smem_optin || ysmem + 2048 > c->smem_optin) return NF_OK;
     int per_sm = 0;
@@ -393,8 +394,13 @@ static int rows_prepare_t(nf_ctx *c)
     if (per_sm < 1) return NF_OK;
     const long long nrows = (long long)c->ny * c->nz;
     c->xrow_grid = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(kRedBlocks, (long long)per_sm * c->sm_count), (nrows + kXW - 1) / kXW));
-    CU(c, cudaFuncSetAttribute(k_ycol<K, M1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ysmem));
-    CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ycol<K, M1>, kYT, ysmem));
+    if (ynt == 128) {
+        CU(c, cudaFuncSetAttribute(k_ycol<K, M1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ysmem));
+        CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ycol<K, M1, 128>, 128, ysmem));
+    } else {
+        CU(c, cudaFuncSetAttribute(k_ycol<K, M1, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ysmem));
+        CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ycol<K, M1, 256>, 256, ysmem));
+    }
     const long long nitems = (long long)c->nz * ((c->nx + c->rg.colsY - 1) / c->rg.colsY) * c->nt;
     c->ycol_grid = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(kRedBlocks, (long long)std::max(per_sm, 1) * c->sm_count), nitems));
     return NF_OK;
@@ -418,9 +424,12 @@ static int rows_launch_t(nf_ctx *c, const FusedArgs &a, int which)
         NF_ROWS_VARIANTS((c->nx + 31) / 32, c->rg.LcX == kLC, CALL);
 #undef CALL
     }
-    if (which & 2)
-        LAUNCH(c, (k_ycol<K, M1>), c->ycol_grid, kYT, (size_t)(c->rg.LcY + 1 + 5) * kYT * sizeof(double2), a, c->rg,
-               c->d_part + (size_t)1 * kRedBlocks, c->d_ticket + 1, &c->d_cg->pAp[1]);
+    if (which & 2) {
+        const int ynt = 32 * c->rg.warpsY;
+        const size_t ysmem = (size_t)(c->rg.LcY + 1 + 5) * ynt * sizeof(double2);
+        if (ynt == 128) LAUNCH(c, (k_ycol<K, M1, 128>), c->ycol_grid, 128, ysmem, a, c->rg, c->d_part + (size_t)1 * kRedBlocks, c->d_ticket + 1, &c->d_cg->pAp[1]);
+        else LAUNCH(c, (k_ycol<K, M1, 256>), c->ycol_grid, 256, ysmem, a, c->rg, c->d_part + (size_t)1 * kRedBlocks, c->d_ticket + 1, &c->d_cg->pAp[1]);
+    }
     CU(c, cudaGetLastError());
     return NF_OK;
 }

@@ -127,17 +127,7 @@ __device__ __forceinline__ void xrow_warp(const FusedArgs &a, const RowGeom &g, 
     const size_t e0 = (size_t)line * n;
     const bool pcg = a.pcg != 0, hasb = (beta != 0.0);
     const int ncb = (n + 32 * kCB - 1) / (32 * kCB);         // coalesced batches per mode
-    // ---- everything the row needs besides the vectors is requested first: per-cell coefficients (registers), factors
-    double Dv[NCL], Sv[NCL];
-#pragma unroll
-    for (int c = 0; c < NCL; ++c) {
-        const int ix = lane + 32 * c;
-        const int ixl = min(ix, n - 1);
-        Dv[c] = __ldg(a.D + e0 + ixl); Sv[c] = __ldg(a.SigR + e0 + ixl);
-    }
-    double Vv[NCL];
-#pragma unroll
-    for (int c = 0; c < NCL; ++c) Vv[c] = __ldg(a.vol + e0 + min(lane + 32 * c, n - 1));
+    // ---- the factors are requested first (asynchronous copies)
     {   // LDL^T factors of the line: UB[f] = u_{f-1}, MINV[f] = 1/m_f (asynchronous copies, waited for before the solve)
         const double *gm = a.minv[0] + line * (n + 1), *gu = a.u[0] + line * (n + 1);
         for (int f = lane; f <= NF; f += 32) {
@@ -209,9 +199,14 @@ __device__ __forceinline__ void xrow_warp(const FusedArgs &a, const RowGeom &g, 
                 }
             }
         }
-        if (t0 == 0) {     // first use of everything requested at the top of the row
+        // per-cell coefficients of the lane's cells: requested now, first used after the solve
+        double Dv[NCL], Sv[NCL], Vv[NCL];
 #pragma unroll
-            for (int c = 0; c < NCL; ++c) Sv[c] *= Vv[c];
+        for (int c = 0; c < NCL; ++c) {
+            const int ixl = min(lane + 32 * c, n - 1);
+            Dv[c] = __ldg(a.D + e0 + ixl); Sv[c] = __ldg(a.SigR + e0 + ixl); Vv[c] = __ldg(a.vol + e0 + ixl);
+        }
+        if (t0 == 0) {     // first use of the factors requested at the top of the row
             ify0 = 1.0 / (fy0 * fz0); ify1 = 1.0 / (fy1 * fz1); ify2 = 1.0 / (fy2 * fz2);
             asm volatile("cp.async.wait_group 0;\n" ::: "memory");
         }
@@ -265,34 +260,40 @@ __device__ __forceinline__ void xrow_warp(const FusedArgs &a, const RowGeom &g, 
                 if (FULL || j < jn) Jr[j] = T[j];
         }
         __syncwarp();
-        // ---- yp = diag * p + w B_x J (coalesced): modes outside, the lane's cells inside
-        double G0[NCL], G1[NCL], G2[NCL];
+        // ---- yp = diag * p + w B_x J (coalesced): batches of 8 cells per lane, modes outside, cells inside
 #pragma unroll
-        for (int c = 0; c < NCL; ++c) {
-            const int ixl = min(lane + 32 * c, n - 1);
-            G0[c] = Dv[c] * __ldg(a.iFx[0] + ixl); G1[c] = Dv[c] * __ldg(a.iFx[1] + ixl); G2[c] = Dv[c] * __ldg(a.iFx[2] + ixl);
-        }
-        for (int s2 = 0; s2 < np; ++s2) {
-            const double w = a.w[t0 + s2];
-            const double *Js = Jb + s2 * PJ + lane;
+        for (int cb = 0; cb < NCL; cb += kCB) {
+            if (lane + 32 * cb < n) {
+                double G0[kCB], G1[kCB], G2[kCB], SV[kCB];
 #pragma unroll
-            for (int p = 0; p < M1; ++p) {
-                const int md = a.mode[0][t0 + s2][p];
-                const double cw = a.wC[md], c0 = a.cb[0][md] * ify0, c1 = a.cb[1][md] * ify1, c2 = a.cb[2][md] * ify2;
-                const double *Pm = P + (s2 * M1 + p) * PP + lane;
-                double *yo = a.yp + (size_t)md * a.ne + e0 + lane;
+                for (int c = 0; c < kCB; ++c) {
+                    const int cc = (cb + c < NCL) ? cb + c : NCL - 1;
+                    const int ixl = min(lane + 32 * cc, n - 1);
+                    G0[c] = Dv[cc] * __ldg(a.iFx[0] + ixl); G1[c] = Dv[cc] * __ldg(a.iFx[1] + ixl); G2[c] = Dv[cc] * __ldg(a.iFx[2] + ixl);
+                    SV[c] = Sv[cc] * Vv[cc];
+                }
+                for (int s2 = 0; s2 < np; ++s2) {
+                    const double w = a.w[t0 + s2];
+                    const double *Js = Jb + s2 * PJ + lane + 32 * cb;
 #pragma unroll
-                for (int c = 0; c < NCL; ++c) {
-                    const int ix = lane + 32 * c;
-                    if (ix < n) {
-                        const double JL = Js[32 * c], JR = Js[32 * c + 1];
-                        const double sol = (p == 0) ? w * (JR - JL) : (p == 1 ? ((K >= 1) ? w * (5.0 / 6.0) * (JL + JR) : 0.0)
-                                                                              : ((K >= 2) ? w * (7.0 / 10.0) * (JR - JL) : 0.0));
-                        const double xv = Pm[32 * c];
-                        const double dg = Sv[c] * cw + G0[c] * c0 + G1[c] * c1 + G2[c] * c2;
-                        const double yv = dg * xv;
-                        acc += yv * xv;
-                        yo[32 * c] = yv + sol;
+                    for (int p = 0; p < M1; ++p) {
+                        const int md = a.mode[0][t0 + s2][p];
+                        const double cw = a.wC[md], c0 = a.cb[0][md] * ify0, c1 = a.cb[1][md] * ify1, c2 = a.cb[2][md] * ify2;
+                        const double *Pm = P + (s2 * M1 + p) * PP + lane + 32 * cb;
+                        double *yo = a.yp + (size_t)md * a.ne + e0 + lane + 32 * cb;
+#pragma unroll
+                        for (int c = 0; c < kCB; ++c) {
+                            if (cb + c < NCL && lane + 32 * (cb + c) < n) {
+                                const double JL = Js[32 * c], JR = Js[32 * c + 1];
+                                const double sol = (p == 0) ? w * (JR - JL) : (p == 1 ? ((K >= 1) ? w * (5.0 / 6.0) * (JL + JR) : 0.0)
+                                                                                      : ((K >= 2) ? w * (7.0 / 10.0) * (JR - JL) : 0.0));
+                                const double xv = Pm[32 * c];
+                                const double dg = SV[c] * cw + G0[c] * c0 + G1[c] * c1 + G2[c] * c2;
+                                const double yv = dg * xv;
+                                acc += yv * xv;
+                                yo[32 * c] = yv + sol;
+                            }
+                        }
                     }
                 }
             }
@@ -340,7 +341,7 @@ __global__ void __launch_bounds__(32 * kXW, 7) k_xrow(const FusedArgs a, const R
 // load that returns 0 (it is the u of the last face of the line below, which is 0 by construction).
 constexpr int kRowPad = 48;     // rows of padding behind the arrays (unconditional batch loads run past a column's end)
 constexpr int kYB = 8;          // rows of loads issued ahead of each stretch of work
-constexpr int kYT = 128;        // threads per CTA
+constexpr int kYT = 128;        // threads per CTA (256 for lines of more than 256 cells: 16 columns per item)
 
 __device__ __forceinline__ double2 ld2cg(const double *p) { return __ldcg(reinterpret_cast<const double2 *>(p)); }
 __device__ __forceinline__ double2 ld2g(const double *p) { return __ldg(reinterpret_cast<const double2 *>(p)); }
@@ -558,21 +559,21 @@ __device__ __forceinline__ void ycol_block(const FusedArgs &a, const RowGeom &g,
     __syncthreads();        // sS is reused by the next item
 }
 
-// yp += (y part of S p) ; red_out = p^T (y part) p.   Dynamic shared memory: (LcY + 1 + 5) * kYT double2.
-template <int K, int M1>
-__global__ void __launch_bounds__(kYT) k_ycol(const FusedArgs a, const RowGeom g, double *red_part, unsigned *ticket,
-                                              double *red_out)
+// yp += (y part of S p) ; red_out = p^T (y part) p.   Dynamic shared memory: (LcY + 1 + 5) * NT double2.
+template <int K, int M1, int NT>
+__global__ void __launch_bounds__(NT) k_ycol(const FusedArgs a, const RowGeom g, double *red_part, unsigned *ticket,
+                                             double *red_out)
 {
     if (a.st->done) return;
     extern __shared__ __align__(16) double sm[];
-    double2 *sT = reinterpret_cast<double2 *>(sm), *sS = sT + (size_t)(g.LcY + 1) * kYT;
+    double2 *sT = reinterpret_cast<double2 *>(sm), *sS = sT + (size_t)(g.LcY + 1) * NT;
     const int nxb = (a.nx + g.colsY - 1) / g.colsY;
     const long long nitems = (long long)a.nz * nxb * a.nt;
     double acc = 0.0;
     for (long long item = blockIdx.x; item < nitems; item += gridDim.x) {
         const int t = (int)(item % a.nt);
         const long long r = item / a.nt;
-        ycol_block<K, M1, kYT>(a, g, (int)(r / nxb), (int)(r % nxb), t, sT, sS, acc);
+        ycol_block<K, M1, NT>(a, g, (int)(r / nxb), (int)(r % nxb), t, sT, sS, acc);
     }
     double v[1] = {acc};
     grid_reduce<1>(v, red_part, ticket, red_out);
