@@ -146,6 +146,28 @@ def run_reference(args):
     return 0
 
 
+PATH_KERNELS = {
+    0: "k_sweep_x + k_sweep_march(y) + k_sweep_march(z) + k_(p)cg_update + k_(p)cg_pupdate",
+    1: "k_plane_fwd + k_zback_update",
+    2: "k_(p)cg_pupdate + k_sweep_x + k_sweep_march(y) + k_zfwd + k_zback_update",
+    3: "k_xrow (direction update + x lines) + k_ycol (y lines) + k_zfwd + k_zback_update (z back substitution + x/r update)",
+    5: "k_xrow + k_ycol + k_march_slab_fwd + ncclAllGather + k_march_slab_bwd + k_(p)cg_update (+ 2 ncclAllReduce)",
+}
+
+
+def measured_traffic(mesh, n_phi, path):
+    """DRAM bytes of one CG iteration from the committed ncu capture (profiles/traffic.json), scaled per DOF; None when the
+    capture was taken on another path."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None
+    with open(p) as fh:
+        d = json.load(fh)
+    if int(d.get("path", -1)) != int(path):
+        return None
+    return float(d["dram_bytes_per_dof_per_cg_iteration"]) * n_phi
+
+
 def workload_config(args, mesh):
     return {"workload": f"synthetic IAEA-3D refined to {mesh[0]}x{mesh[1]}x{mesh[2]} cells, RT{args.rt}-P{args.p}, 2 groups, "
                         f"6x Dirichlet (BASELINE.json configs[4])",
@@ -281,8 +303,8 @@ def run_ours(args):
                 "seconds": dt, "what": "nf_upload_xs(pinned host)+nf_build+nf_solve_keff(K outer)+nf_get_flux(host)"},
         "gpu_launches": int(launches),
         "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"], "samples": clocks["samples"]},
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
-                     "peak_source": how, "per": "GPU", "kernel": "one Schur-CG iteration = k_sweep_x + k_sweep_march(y) + k_sweep_march(z) + k_(p)cg_update + k_(p)cg_pupdate",
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": measured_traffic(mesh, ctx.n_Phi, kt.get("path", 0)),
+                     "peak_source": how, "per": "GPU", "kernel": "one Schur-CG iteration = " + PATH_KERNELS.get(int(kt.get("path", 0)), "?"),
                      "algorithmic_bytes_per_dof": 88.0 + 16.0 / nl, "dofs_per_launch": ctx.n_Phi,
                      "ms_per_launch": kt["cg_iteration"],
                      "kernels_ms": {k: v for k, v in kt.items()}},

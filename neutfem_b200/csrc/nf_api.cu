@@ -453,7 +453,14 @@ static int fused_setup(nf_ctx *c)
     // with the hybrid path (2) as fallback; 0 = separate kernels, 1 = plane-ordered fused kernel, 2 = hybrid, 3 = rows.
     const bool auto_mode = (getenv("NF_FUSED") == nullptr || !*getenv("NF_FUSED"));
     int want_mode = auto_mode ? 3 : env_int("NF_FUSED", 3);
-    if (c->dim != 3 || c->slab || want_mode == 0) return NF_OK;
+    if (c->dim != 3 || want_mode == 0) return NF_OK;
+    if (c->slab) {                        // z-slab ranks: the x rows / y columns are slab-local, the z sweep stays substructured
+        if ((auto_mode || want_mode == 3) && rows_geometry(c, c->rg)) {
+            { int r = rows_prepare(c); if (r) return r; }
+            if (c->xrow_grid > 0) c->fused = 5;
+        }
+        return NF_OK;
+    }
     if (want_mode == 3) {                 // rows: k_xrow (direction update + x) + k_ycol + k_zfwd + k_zback_update
         if (rows_geometry(c, c->rg)) {
             { int r = rows_prepare(c); if (r) return r; }
@@ -1047,9 +1054,9 @@ static int solve_group(nf_ctx *c, int g, const double *b, double *x, int *iters_
         LAUNCH(c, k_cg_finalize, 1, 1, 0, c->d_cg, 0, tol, pcg ? 1 : 0);
     }
     { int r = fused_setup(c); if (r) return r; }
-    const bool fused = (c->fused == 1), hybrid = (c->fused == 2), rows = (c->fused == 3);
+    const bool fused = (c->fused == 1), hybrid = (c->fused == 2), rows = (c->fused == 3), slabrows = (c->fused == 5);
     FusedArgs fa;
-    if (fused || hybrid || rows) fill_fused_args(c, fa, g, x, jac);
+    if (fused || hybrid || rows || slabrows) fill_fused_args(c, fa, g, x, jac);
     // poll the device-side done flag every few iterations; iterations after convergence are no-ops on the device
     const double est_us = (double)n * 160.0 / 6.0e6 + 15.0;
     int poll = (int)std::max(1.0, std::min(16.0, 200.0 / est_us));
@@ -1066,6 +1073,16 @@ static int solve_group(nf_ctx *c, int g, const double *b, double *x, int *iters_
             if (rows) {           // direction update + x rows | y columns | z forward | z back + update
                 { int r = rows_launch(c, fa, 3); if (r) return r; }
                 { int r = fused_launch(c, fa, 4 | 2); if (r) return r; }
+                continue;
+            }
+            if (slabrows) {       // z-slab rank: x rows (direction update fused) | y columns | substructured z sweep | update
+                { int r = rows_launch(c, fa, 3); if (r) return r; }
+                { int r = apply_schur(c, g, c->d_p, c->d_Ap, true, 4); if (r) return r; }
+                { int r = allreduce_sum(c, c->d_cg->pAp, 4); if (r) return r; }
+                if (!pcg) LAUNCH(c, k_cg_update, blocks, 256, 0, c->d_p, c->d_Ap, x, c->d_r, n, c->d_cg, c->d_part + 4 * kRedBlocks, c->d_ticket + 4, 0);
+                else LAUNCH(c, k_pcg_update, blocks, 256, 0, c->d_p, c->d_Ap, jac, x, c->d_r, n, c->d_cg, c->d_part + 4 * kRedBlocks, c->d_ticket + 4, 0);
+                { int r = allreduce_sum(c, c->d_cg->tmp, 2); if (r) return r; }
+                LAUNCH(c, k_cg_finalize, 1, 1, 0, c->d_cg, 1, tol, pcg ? 1 : 0);
                 continue;
             }
             if (hybrid) {         // direction update, x and y sweeps as separate kernels, then z forward | z back + update
@@ -1481,6 +1498,34 @@ int nf_time_kernels(nf_ctx *c, int g, int reps, int fast, double *ms_out)
         }
     }
     ms_out[12] = (double)c->fused;
+    if (c->fused == 5) {                          // z-slab ranks: k_xrow | k_ycol | slab z sweep (+ all-gather) | update
+        FusedArgs fa;
+        fill_fused_args(c, fa, g, c->d_tot, jac);
+        auto slabit = [&](int what) -> int {       // 1: x rows, 2: y columns, 4: z sweep, 8: update
+            if (what & 3) { int r = rows_launch(c, fa, what & 3); if (r) return r; }
+            if (what & 4) { int r = apply_schur(c, g, c->d_p, c->d_Ap, true, 4); if (r) return r; }
+            if (what & 8) {
+                { int r = allreduce_sum(c, c->d_cg->pAp, 4); if (r) return r; }
+                if (!fast) LAUNCH(c, k_cg_update, blocks, 256, 0, c->d_p, c->d_Ap, c->d_tot, c->d_r, n, c->d_cg, c->d_part + 4 * kRedBlocks, c->d_ticket + 4, 0);
+                else LAUNCH(c, k_pcg_update, blocks, 256, 0, c->d_p, c->d_Ap, jac, c->d_tot, c->d_r, n, c->d_cg, c->d_part + 4 * kRedBlocks, c->d_ticket + 4, 0);
+                { int r = allreduce_sum(c, c->d_cg->tmp, 2); if (r) return r; }
+                LAUNCH(c, k_cg_finalize, 1, 1, 0, c->d_cg, 1, 0.0, fast ? 1 : 0);
+            }
+            return NF_OK;
+        };
+        { int r = slabit(15); if (r) return r; }
+        const int which[3] = {1, 2, 15};
+        const int slot[3] = {9, 10, 5};
+        for (int w = 0; w < 3; ++w) {
+            CU(c, cudaEventRecord(c->ev2, c->stream));
+            for (int i = 0; i < reps; ++i) { int r = slabit(which[w]); if (r) return r; }
+            CU(c, cudaEventRecord(c->ev3, c->stream));
+            CU(c, cudaEventSynchronize(c->ev3));
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, c->ev2, c->ev3);
+            ms_out[slot[w]] = ms / reps;
+        }
+    }
     if (c->fused == 3) {                          // rows path: k_xrow | k_ycol | k_zfwd | k_zback_update
         FusedArgs fa;
         fill_fused_args(c, fa, g, c->d_tot, jac);
