@@ -40,7 +40,7 @@ struct nf_ctx {
     std::vector<double *> d_u_base;        // allocations behind d_u (front padding, see nf_rows.cuh)
     long long nfaces[3] = {0, 0, 0};
     double *d_sinv = nullptr; bool diag_valid = false;
-    double *d_jac = nullptr; bool jac_valid = false;
+    jac_t *d_jac = nullptr; bool jac_valid = false;
     double *d_phi = nullptr, *d_phi_adj = nullptr, *d_old = nullptr, *d_h0 = nullptr, *d_h1 = nullptr;
     double *d_tot = nullptr, *d_rhs = nullptr, *d_r = nullptr, *d_p = nullptr, *d_Ap = nullptr, *d_tmp = nullptr;
     double *d_zscratch = nullptr; size_t zscratch_bytes = 0;
@@ -69,6 +69,7 @@ struct nf_ctx {
     std::vector<double *> d_s0;            // [g] column 0 of the local z-line inverses
     double *d_E = nullptr, *d_Eall = nullptr;      // [g][3][nxy], [g][nranks][3][nxy]
     double *d_vG = nullptr, *d_vGall = nullptr;    // [2][nt][nxy], [nranks][2][nt][nxy]
+    double *d_lam = nullptr;                       // [2][nt][nxy] interface multipliers of this rank (fused slab update)
     // ---- fused two-kernel CG iteration (nf_fused.cuh), 3-D single-GPU contexts
     int fused = -1;                        // -1: not yet decided, 0: unavailable / disabled, 1: ready
     int fLW = 4, fLcX = 1, fTS = 0, fPS = 0, fLcY = 1, fnX = 0, fnY = 0, fnitems = 0, fgrid = 0;
@@ -346,9 +347,12 @@ static int fused_prepare(nf_ctx *c, size_t smem, int *per_sm)
 static bool rows_geometry(const nf_ctx *c, RowGeom &g)
 {
     memset(&g, 0, sizeof(g));
-    const int nfx = c->nx + 1, nfy = c->ny + 1;
+    const int nfx = c->nx + 1;
     if (nfx > 32 * kLC || c->ny > 32 * 64) return false;
     g.Cx = (nfx <= 8 * kLC) ? 8 : (nfx <= 16 * kLC ? 16 : 32);
+    // long lines (265 .. 512 cells): one pair at a time over all 32 lanes, 17 faces per lane -- a 21 KB tile per warp instead
+    // of 34 KB, so 10 warps fit on an SM instead of 6
+    if (g.Cx == 16 && c->nx <= 512 && nfx <= 32 * 17 && env_int("NF_XROW_LC17", 1)) g.Cx = 32;
     g.LcX = (nfx + g.Cx - 1) / g.Cx;
     g.PWx = 32 / g.Cx;
     g.NFx = g.Cx * g.LcX;
@@ -367,12 +371,15 @@ static bool rows_geometry(const nf_ctx *c, RowGeom &g)
     return true;
 }
 
-// variants of the x-row code: cells per lane (8 / 16 / 33), all chunks full (no guards) or not
-#define NF_ROWS_VARIANTS(ncl, full, CALL)                                                     \
-    do {                                                                                      \
-        if ((ncl) <= 8) { if (full) CALL(8, true); else CALL(8, false); }                     \
-        else if ((ncl) <= 16) { if (full) CALL(16, true); else CALL(16, false); }             \
-        else CALL(33, false);                                                                 \
+// variants of the x-row code: cells per lane (8 / 16 / 33), faces per lane chunk (33, or 17 for the long-line layout), all
+// chunks full (no guards) or not
+#define NF_ROWS_VARIANTS(c, CALL)                                                                          \
+    do {                                                                                                   \
+        const int ncl_ = ((c)->nx + 31) / 32, lc_ = (c)->rg.LcX;                                           \
+        if ((c)->rg.Cx == 32 && lc_ <= 17 && ncl_ <= 16) { if (lc_ == 17) CALL(16, 17, true); else CALL(16, 17, false); } \
+        else if (ncl_ <= 8) { if (lc_ == kLC) CALL(8, kLC, true); else CALL(8, kLC, false); }              \
+        else if (ncl_ <= 16) { if (lc_ == kLC) CALL(16, kLC, true); else CALL(16, kLC, false); }           \
+        else CALL(33, kLC, false);                                                                         \
     } while (0)
 
 template <int K, int M1>
@@ -384,12 +391,12 @@ static int rows_prepare_t(nf_ctx *c)
     c->xrow_grid = 0;
     if (smem + 2048 > c->smem_optin || ysmem + 2048 > c->smem_optin) return NF_OK;
     int per_sm = 0;
-#define CALL(NCLV, FULLV)                                                                                                                  \
+#define CALL(NCLV, LCTV, FULLV)                                                                                                            \
     do {                                                                                                                                   \
-        CU(c, cudaFuncSetAttribute(k_xrow<K, M1, NCLV, kLC, FULLV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
-        CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_xrow<K, M1, NCLV, kLC, FULLV>, 32 * kXW, smem));                   \
+        CU(c, cudaFuncSetAttribute(k_xrow<K, M1, NCLV, LCTV, FULLV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
+        CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_xrow<K, M1, NCLV, LCTV, FULLV>, 32 * kXW, smem));                  \
     } while (0)
-    NF_ROWS_VARIANTS((c->nx + 31) / 32, c->rg.LcX == kLC, CALL);
+    NF_ROWS_VARIANTS(c, CALL);
 #undef CALL
     if (per_sm < 1) return NF_OK;
     const long long nrows = (long long)c->ny * c->nz;
@@ -420,8 +427,8 @@ static int rows_launch_t(nf_ctx *c, const FusedArgs &a, int which)
     if (which & 1) {
         const size_t smem = (size_t)kXW * c->rg.xsmemW * sizeof(double);
         double *part = c->d_part + (size_t)0 * kRedBlocks;
-#define CALL(NCLV, FULLV) LAUNCH(c, (k_xrow<K, M1, NCLV, kLC, FULLV>), c->xrow_grid, 32 * kXW, smem, a, c->rg, part, c->d_ticket + 0, &c->d_cg->pAp[0])
-        NF_ROWS_VARIANTS((c->nx + 31) / 32, c->rg.LcX == kLC, CALL);
+#define CALL(NCLV, LCTV, FULLV) LAUNCH(c, (k_xrow<K, M1, NCLV, LCTV, FULLV>), c->xrow_grid, 32 * kXW, smem, a, c->rg, part, c->d_ticket + 0, &c->d_cg->pAp[0])
+        NF_ROWS_VARIANTS(c, CALL);
 #undef CALL
     }
     if (which & 2) {
@@ -532,7 +539,7 @@ static int fused_setup(nf_ctx *c)
     return NF_OK;
 }
 
-static void fill_fused_args(nf_ctx *c, FusedArgs &a, int g, double *x, const double *jac)
+static void fill_fused_args(nf_ctx *c, FusedArgs &a, int g, double *x, const jac_t *jac)
 {
     memset(&a, 0, sizeof(a));
     a.r = c->d_r; a.rw = c->d_r; a.jac = jac; a.p = c->d_p; a.yp = c->d_Ap; a.x = x;
@@ -595,6 +602,62 @@ static int fused_launch_t(nf_ctx *c, const FusedArgs &a, int which)
 static int fused_launch(nf_ctx *c, const FusedArgs &a, int which)
 {
 #define CALL(KK, MM) fused_launch_t<KK, MM>(c, a, which)
+    NF_ORDER_SWITCH(c, CALL);
+#undef CALL
+}
+
+// z-slab ranks, second half of a CG iteration: local z forward substitution | all-gather of the interface values |
+// interface solve (+ its share of p^T S p) | all-reduce of p^T S p | z back substitution fused with the x / r update |
+// all-reduce of the new residual norms | scalar recurrences. x rows and y columns (rows_launch) must have run before.
+template <int K, int M1>
+static int slab_zupdate_t(nf_ctx *c, int g, double *x, const jac_t *jac, double tol)
+{
+    SweepArgs a;
+    fill_sweep_args(c, a, g, 2, c->d_p, c->d_Ap, true);
+    MarchGeom mg;
+    mg.n = c->nz; mg.north = c->ny; mg.stride = (long long)c->nx * c->ny;
+    mg.ostride_cell = c->nx; mg.ostride_face = c->nx;
+    const int WPB = 4;
+    const long long nitems = (long long)mg.north * c->nt * ((c->nx + 31) / 32);
+    static int occ_f = 0, occ_b = 0;
+    if (!occ_f) {
+        CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, k_march_slab_fwd<K, M1>, WPB * 32, 0));
+        CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, k_slab_back_update<K, M1>, WPB * 32, 0));
+        occ_f = std::max(occ_f, 1); occ_b = std::max(occ_b, 1);
+    }
+    auto wave_grid = [&](int occ) {
+        const int waves = std::max(1, kRedBlocks / (occ * c->sm_count));
+        return (int)std::max<long long>(1, std::min<long long>((long long)waves * occ * c->sm_count, (nitems + WPB - 1) / WPB));
+    };
+    const size_t need = (size_t)nitems * (mg.n + 1) * 32 * sizeof(double);
+    if (need > c->zscratch_bytes) {
+        CU(c, cudaStreamSynchronize(c->stream));
+        if (c->d_zscratch) cudaFree(c->d_zscratch);
+        c->d_zscratch = nullptr; c->zscratch_bytes = 0;
+        CU(c, cudaMalloc((void **)&c->d_zscratch, need));
+        c->zscratch_bytes = need;
+    }
+    if (!c->d_lam) { int r = dalloc(c, &c->d_lam, (size_t)2 * c->nt * c->nxy); if (r) return r; }
+    a.zscratch = c->d_zscratch;
+    LAUNCH(c, (k_march_slab_fwd<K, M1>), wave_grid(occ_f), WPB * 32, 0, a, mg);
+    NC(c, ncclAllGather(c->d_vG, c->d_vGall, (size_t)2 * c->nt * c->nxy, ncclDouble, c->comm, c->stream));
+    SlabUpd u;
+    u.p = c->d_p; u.yp = c->d_Ap; u.x = x; u.r = c->d_r; u.jac = jac; u.lam = c->d_lam; u.st = c->d_cg;
+    u.red_part = c->d_part + (size_t)4 * kRedBlocks; u.ticket = c->d_ticket + 4; u.pcg = jac ? 1 : 0;
+    a.red_out = &c->d_cg->pAp[3];
+    a.red_part = c->d_part + (size_t)3 * kRedBlocks; a.ticket = c->d_ticket + 3;
+    LAUNCH(c, (k_slab_iface<K, M1>), (int)std::max<long long>(1, std::min<long long>(kRedBlocks, (c->nxy * c->nt + 127) / 128)), 128, 0, a, u);
+    { int r = allreduce_sum(c, c->d_cg->pAp, 4); if (r) return r; }
+    LAUNCH(c, (k_slab_back_update<K, M1>), wave_grid(occ_b), WPB * 32, 0, a, mg, u);
+    { int r = allreduce_sum(c, c->d_cg->tmp, 2); if (r) return r; }
+    LAUNCH(c, k_cg_finalize, 1, 1, 0, c->d_cg, 1, tol, jac ? 1 : 0);
+    CU(c, cudaGetLastError());
+    return NF_OK;
+}
+
+static int slab_zupdate(nf_ctx *c, int g, double *x, const jac_t *jac, double tol)
+{
+#define CALL(KK, MM) slab_zupdate_t<KK, MM>(c, g, x, jac, tol)
     NF_ORDER_SWITCH(c, CALL);
 #undef CALL
 }
@@ -807,13 +870,14 @@ int nf_destroy(nf_ctx *c)
     cudaSetDevice(c->dev);
     if (c->stream) cudaStreamSynchronize(c->stream);
     double *ptrs[] = {c->d_hx, c->d_hy, c->d_hz, c->d_vol, c->d_D, c->d_SigR, c->d_NSF, c->d_Chi, c->d_SigS, c->d_SRC,
-                      c->d_sinv, c->d_jac, c->d_phi, c->d_phi_adj, c->d_old, c->d_h0, c->d_h1, c->d_tot, c->d_rhs, c->d_r,
+                      c->d_sinv, c->d_phi, c->d_phi_adj, c->d_old, c->d_h0, c->d_h1, c->d_tot, c->d_rhs, c->d_r,
                       c->d_p, c->d_Ap, c->d_tmp, c->d_zscratch, c->d_J, c->d_part, c->d_scal};
     for (double *p : ptrs) if (p) cudaFree(p);
+    if (c->d_jac) cudaFree(c->d_jac);
     for (int d = 0; d < 3; ++d) for (int ax = 0; ax < 3; ++ax) if (c->d_F[d][ax]) cudaFree(c->d_F[d][ax]);
     for (int d = 0; d < 3; ++d) if (c->d_iFx[d]) cudaFree(c->d_iFx[d]);
     for (double *p : c->d_s0) if (p) cudaFree(p);
-    for (double *p : {c->d_E, c->d_Eall, c->d_vG, c->d_vGall, c->d_zs, c->d_W, c->d_fpart}) if (p) cudaFree(p);
+    for (double *p : {c->d_E, c->d_Eall, c->d_vG, c->d_vGall, c->d_lam, c->d_zs, c->d_W, c->d_fpart}) if (p) cudaFree(p);
     if (c->d_fq) cudaFree(c->d_fq);
     if (c->d_items) cudaFree(c->d_items);
     if (c->comm) ncclCommDestroy(c->comm);
@@ -1039,7 +1103,7 @@ static int solve_group(nf_ctx *c, int g, const double *b, double *x, int *iters_
     if (fast || direct) { int r = build_jacobi(c); if (r) return r; }
     const bool pcg = fast || direct;
     const int fin = c->slab ? 0 : 1;        // scalar recurrences inside the reducing kernel unless ranks must be summed first
-    const double *jac = pcg ? c->d_jac + (size_t)g * c->nphi : nullptr;
+    const jac_t *jac = pcg ? c->d_jac + (size_t)g * c->nphi : nullptr;
     CU(c, cudaEventRecord(c->ev2, c->stream));
     if (!pcg) {
         LAUNCH(c, k_cg_init, blocks, 256, 0, b, x, c->d_r, c->d_p, n, tol, c->d_cg, c->d_part + 4 * kRedBlocks, c->d_ticket + 4, fin);
@@ -1075,14 +1139,9 @@ static int solve_group(nf_ctx *c, int g, const double *b, double *x, int *iters_
                 { int r = fused_launch(c, fa, 4 | 2); if (r) return r; }
                 continue;
             }
-            if (slabrows) {       // z-slab rank: x rows (direction update fused) | y columns | substructured z sweep | update
+            if (slabrows) {       // z-slab rank: x rows (direction update fused) | y columns | substructured z sweep fused with the update
                 { int r = rows_launch(c, fa, 3); if (r) return r; }
-                { int r = apply_schur(c, g, c->d_p, c->d_Ap, true, 4); if (r) return r; }
-                { int r = allreduce_sum(c, c->d_cg->pAp, 4); if (r) return r; }
-                if (!pcg) LAUNCH(c, k_cg_update, blocks, 256, 0, c->d_p, c->d_Ap, x, c->d_r, n, c->d_cg, c->d_part + 4 * kRedBlocks, c->d_ticket + 4, 0);
-                else LAUNCH(c, k_pcg_update, blocks, 256, 0, c->d_p, c->d_Ap, jac, x, c->d_r, n, c->d_cg, c->d_part + 4 * kRedBlocks, c->d_ticket + 4, 0);
-                { int r = allreduce_sum(c, c->d_cg->tmp, 2); if (r) return r; }
-                LAUNCH(c, k_cg_finalize, 1, 1, 0, c->d_cg, 1, tol, pcg ? 1 : 0);
+                { int r = slab_zupdate(c, g, x, jac, tol); if (r) return r; }
                 continue;
             }
             if (hybrid) {         // direction update, x and y sweeps as separate kernels, then z forward | z back + update
@@ -1438,7 +1497,7 @@ int nf_time_kernels(nf_ctx *c, int g, int reps, int fast, double *ms_out)
     const long long n = c->nphi;
     const int blocks = ew_blocks(n);
     if (fast) { int r = build_jacobi(c); if (r) return r; }
-    const double *jac = fast ? c->d_jac + (size_t)g * c->nphi : nullptr;
+    const jac_t *jac = fast ? c->d_jac + (size_t)g * c->nphi : nullptr;
     LAUNCH(c, k_fill, blocks, 256, 0, c->d_rhs, n, 1.0);
     const int fin = c->slab ? 0 : 1;
     LAUNCH(c, k_cg_init, blocks, 256, 0, c->d_rhs, c->d_tot, c->d_r, c->d_p, n, 0.0, c->d_cg, c->d_part + 4 * kRedBlocks, c->d_ticket + 4, fin);
@@ -1501,22 +1560,15 @@ int nf_time_kernels(nf_ctx *c, int g, int reps, int fast, double *ms_out)
     if (c->fused == 5) {                          // z-slab ranks: k_xrow | k_ycol | slab z sweep (+ all-gather) | update
         FusedArgs fa;
         fill_fused_args(c, fa, g, c->d_tot, jac);
-        auto slabit = [&](int what) -> int {       // 1: x rows, 2: y columns, 4: z sweep, 8: update
+        auto slabit = [&](int what) -> int {       // 1: x rows, 2: y columns, 12: z sweep fused with the update
             if (what & 3) { int r = rows_launch(c, fa, what & 3); if (r) return r; }
-            if (what & 4) { int r = apply_schur(c, g, c->d_p, c->d_Ap, true, 4); if (r) return r; }
-            if (what & 8) {
-                { int r = allreduce_sum(c, c->d_cg->pAp, 4); if (r) return r; }
-                if (!fast) LAUNCH(c, k_cg_update, blocks, 256, 0, c->d_p, c->d_Ap, c->d_tot, c->d_r, n, c->d_cg, c->d_part + 4 * kRedBlocks, c->d_ticket + 4, 0);
-                else LAUNCH(c, k_pcg_update, blocks, 256, 0, c->d_p, c->d_Ap, jac, c->d_tot, c->d_r, n, c->d_cg, c->d_part + 4 * kRedBlocks, c->d_ticket + 4, 0);
-                { int r = allreduce_sum(c, c->d_cg->tmp, 2); if (r) return r; }
-                LAUNCH(c, k_cg_finalize, 1, 1, 0, c->d_cg, 1, 0.0, fast ? 1 : 0);
-            }
+            if (what & 12) { int r = slab_zupdate(c, g, c->d_tot, jac, 0.0); if (r) return r; }
             return NF_OK;
         };
         { int r = slabit(15); if (r) return r; }
-        const int which[3] = {1, 2, 15};
-        const int slot[3] = {9, 10, 5};
-        for (int w = 0; w < 3; ++w) {
+        const int which[4] = {1, 2, 12, 15};
+        const int slot[4] = {9, 10, 7, 5};
+        for (int w = 0; w < 4; ++w) {
             CU(c, cudaEventRecord(c->ev2, c->stream));
             for (int i = 0; i < reps; ++i) { int r = slabit(which[w]); if (r) return r; }
             CU(c, cudaEventRecord(c->ev3, c->stream));

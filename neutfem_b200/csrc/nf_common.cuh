@@ -13,6 +13,11 @@
 
 namespace nf {
 
+// The Jacobi preconditioner M^-1 is stored in single precision: any fixed SPD M leaves the PCG limit unchanged, and the
+// array is read twice per CG iteration (8 -> 4 bytes per DOF each time). It is widened to fp64 on load; every kernel uses
+// the same rounded values, so z = M^-1 r and r.z stay consistent.
+typedef float jac_t;
+
 constexpr int kMaxModes = 27;   // (m+1)^3, m <= 2
 constexpr int kMaxT = 9;        // transverse mode pairs per direction, (m+1)^2
 constexpr int kRedBlocks = 1184; // upper bound on the grid size of any reducing kernel (8 * 148)

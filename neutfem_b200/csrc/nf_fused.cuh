@@ -35,7 +35,7 @@ constexpr int kFMaxLW = 8;      // y lines per Y item (template parameter LW) is
 
 struct FusedArgs {
     const double *r;        // residual (SoA)                    [pass 1: read, pass 2: read+write through rw]
-    const double *jac;      // Jacobi M^-1 (SoA) or nullptr (parity mode: M = I)
+    const jac_t *jac;       // Jacobi M^-1 (SoA, single precision) or nullptr (parity mode: M = I)
     double *p;              // search direction, updated in place by pass 1
     double *yp;             // partial S p (everything but the z part)
     double *x, *rw;         // pass 2: solution and residual (rw == r)
@@ -252,7 +252,7 @@ __device__ __forceinline__ void fused_x_item(const FusedArgs &a, const int iz, c
                     if (m0 + j < nloc) {
                         const size_t o = (size_t)(m0 + j) * a.ne + e0 + f;
                         rv[j] = __ldg(a.r + o);
-                        if (pcg) jv[j] = __ldg(a.jac + o);
+                        if (pcg) jv[j] = (double)__ldg(a.jac + o);
                         if (hasb) po[j] = a.p[o];
                     }
                 }
@@ -697,7 +697,7 @@ __global__ void __launch_bounds__(128, 4) k_zback_update(const FusedArgs a)
                             const size_t o = mo[p] + (size_t)f * sxy;
                             ly[j][p] = __ldg(a.yp + o); lp[j][p] = __ldg(a.p + o);
                             lx[j][p] = a.x[o]; lr[j][p] = a.rw[o];
-                            lj[j][p] = pcg ? __ldg(a.jac + o) : 1.0;
+                            lj[j][p] = pcg ? (double)__ldg(a.jac + o) : 1.0;
                         }
                     }
                 }
@@ -733,6 +733,174 @@ __global__ void __launch_bounds__(128, 4) k_zback_update(const FusedArgs a)
         if (pcg) { st->tmp[0] = out[0]; st->tmp[1] = out[1]; }
         else { st->tmp[0] = out[1]; }
         if (a.fin) cg_update_fin(st, a.pcg);
+    }
+}
+
+// ---- z-slab ranks: interface solve and back substitution fused with the CG update ---------------------------------------
+// After k_march_slab_fwd and the all-gather of the interface values (nf_sweeps.cuh), k_slab_iface solves the reduced
+// interface system of every (x, y, pair) line redundantly, keeps this rank's two multipliers and adds the interface share
+// of p^T S p (so that alpha is known before the update). k_slab_back_update then marches the local back substitution
+// J_f = v_f + s0_f lam_0 + sn_f lam_n down the slab, completes Ap = yp + w B_z J in registers and applies the CG update in
+// the same pass (the slab counterpart of k_zback_update; Ap is never written).
+struct SlabUpd {
+    const double *p;        // search direction
+    const double *yp;       // partial S p (diag + x + y parts)
+    double *x, *r;
+    const jac_t *jac;       // Jacobi M^-1 or nullptr
+    double *lam;            // [2][nt][nxy] interface multipliers of this rank
+    CgState *st;
+    double *red_part; unsigned *ticket;
+    int pcg;
+};
+
+template <int K, int M1>
+__global__ void __launch_bounds__(128) k_slab_iface(const SweepArgs a, const SlabUpd u)
+{
+    if (u.st->done) return;
+    const int P = a.nranks, me = a.rank;
+    const long long nl = a.nxy * a.nt;
+    double acc = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nl; i += (long long)gridDim.x * blockDim.x) {
+        const int t = (int)(i / a.nxy);
+        const long long lxy = i - (long long)t * a.nxy;
+        double dg[kMaxRanks], of[kMaxRanks], gg[kMaxRanks];
+        for (int k = 0; k < P; ++k) { dg[k] = 0.0; of[k] = 0.0; gg[k] = 0.0; }
+        double myG00 = 1.0, myG0n = 0.0, myGnn = 1.0, myv0 = 0.0, myvn = 0.0;
+        for (int rr = 0; rr < P; ++rr) {
+            const double G00 = __ldg(a.Eall + ((size_t)rr * 3 + 0) * a.nxy + lxy);
+            const double G0n = __ldg(a.Eall + ((size_t)rr * 3 + 1) * a.nxy + lxy);
+            const double Gnn = __ldg(a.Eall + ((size_t)rr * 3 + 2) * a.nxy + lxy);
+            const double v0 = __ldg(a.vGall + (((size_t)rr * 2 + 0) * a.nt + t) * a.nxy + lxy);
+            const double vn = __ldg(a.vGall + (((size_t)rr * 2 + 1) * a.nt + t) * a.nxy + lxy);
+            if (rr == me) { myG00 = G00; myG0n = G0n; myGnn = Gnn; myv0 = v0; myvn = vn; }
+            const int lo = rr - 1, hi = rr;
+            if (rr == 0) { dg[hi] += 1.0 / Gnn; gg[hi] += vn / Gnn; }
+            else if (rr == P - 1) { dg[lo] += 1.0 / G00; gg[lo] += v0 / G00; }
+            else {
+                const double idet = 1.0 / (G00 * Gnn - G0n * G0n);
+                const double S00 = Gnn * idet, S0n = -G0n * idet, Snn = G00 * idet;
+                dg[lo] += S00; dg[hi] += Snn; of[lo] += S0n;
+                gg[lo] += S00 * v0 + S0n * vn; gg[hi] += S0n * v0 + Snn * vn;
+            }
+        }
+        const int m = P - 1;
+        for (int k = 1; k < m; ++k) {               // Thomas on (dg, of, gg)
+            const double l = of[k - 1] / dg[k - 1];
+            dg[k] -= l * of[k - 1];
+            gg[k] -= l * gg[k - 1];
+        }
+        gg[m - 1] /= dg[m - 1];
+        for (int k = m - 2; k >= 0; --k) gg[k] = (gg[k] - of[k] * gg[k + 1]) / dg[k];
+        double lam0 = 0.0, lamn = 0.0;
+        if (me == 0) lamn = (gg[0] - myvn) / myGnn;
+        else if (me == P - 1) lam0 = (gg[P - 2] - myv0) / myG00;
+        else {
+            const double idet = 1.0 / (myG00 * myGnn - myG0n * myG0n);
+            const double d0 = gg[me - 1] - myv0, dn = gg[me] - myvn;
+            lam0 = (myGnn * d0 - myG0n * dn) * idet;
+            lamn = (-myG0n * d0 + myG00 * dn) * idet;
+        }
+        acc += a.w[t] * (myv0 * lam0 + myvn * lamn);
+        u.lam[i] = lam0;
+        u.lam[nl + i] = lamn;
+    }
+    double v[1] = {acc};
+    grid_reduce<1>(v, a.red_part, a.ticket, a.red_out);
+}
+
+template <int K, int M1>
+__global__ void __launch_bounds__(128, 4) k_slab_back_update(const SweepArgs a, const MarchGeom g, const SlabUpd u)
+{
+    CgState *st = u.st;
+    if (st->done) return;
+    const double pAp = (st->pAp[0] + st->pAp[1]) + (st->pAp[2] + st->pAp[3]);
+    if (fabs(pAp) < (u.pcg ? 1e-300 : 1e-30)) {        // breakdown guard, solvers.cpp:605
+        __syncthreads();
+        if (blockIdx.x == 0 && threadIdx.x == 0) { st->breakdown = 1; st->done = 1; }
+        return;
+    }
+    constexpr int UNR = NF_ZB_UNR;
+    const double alpha = st->rr / pAp;
+    const bool pcg = u.pcg != 0;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, WPB = blockDim.x >> 5;
+    const int n = g.n;
+    const int nxb = (a.nx + 31) >> 5;
+    const long long nitems = (long long)g.north * a.nt * nxb;
+    const long long nl = a.nxy * a.nt;
+    double acc[2] = {0.0, 0.0};
+    for (long long item = (long long)blockIdx.x * WPB + wib; item < nitems; item += (long long)gridDim.x * WPB) {
+        const int xb = (int)(item % nxb);
+        const long long r = item / nxb;
+        const int t = (int)(r % a.nt);
+        const int orth = (int)(r / a.nt);
+        const int ix = xb * 32 + lane;
+        if (ix >= a.nx) continue;
+        const double *__restrict__ zb = a.zscratch + (size_t)item * (size_t)(n + 1) * 32 + lane;
+        const double w = a.w[t];
+        const long long lxy = (long long)orth * a.nx + ix;
+        const double lam0 = __ldg(u.lam + (size_t)t * a.nxy + lxy), lamn = __ldg(u.lam + nl + (size_t)t * a.nxy + lxy);
+        const long long c0 = (long long)orth * g.ostride_cell + ix;
+        const long long s0o = (long long)orth * g.ostride_face + ix;
+        const long long stz = g.stride;
+        const double *__restrict__ um = a.u + s0o;
+        const double *__restrict__ mi = a.minv + s0o;
+        const double *__restrict__ sp = a.s0 + s0o;
+        size_t mo[3];
+#pragma unroll
+        for (int p = 0; p < 3; ++p) mo[p] = (size_t)a.mode[t][p < M1 ? p : 0] * a.ne + c0;
+        double vnx = 0.0, snx = 0.0, Jn = 0.0;
+        for (int fb = n; fb >= 0; fb -= UNR) {
+            double lz[UNR], lu[UNR], lm[UNR], ls[UNR], ly[UNR][3], lp[UNR][3], lx[UNR][3], lr[UNR][3], lj[UNR][3];
+#pragma unroll
+            for (int j = 0; j < UNR; ++j) {
+                const int f = fb - j;
+                lz[j] = lu[j] = lm[j] = ls[j] = 0.0;
+                if (f >= 0) {
+                    const long long o = (long long)f * stz;
+                    lz[j] = zb[(size_t)f * 32]; lu[j] = __ldg(um + o); lm[j] = __ldg(mi + o); ls[j] = __ldg(sp + o);
+                    if (f < n) {
+#pragma unroll
+                        for (int p = 0; p < M1; ++p) {
+                            const size_t oo = mo[p] + (size_t)o;
+                            ly[j][p] = __ldg(u.yp + oo); lp[j][p] = __ldg(u.p + oo);
+                            lx[j][p] = u.x[oo]; lr[j][p] = u.r[oo];
+                            lj[j][p] = pcg ? (double)__ldg(u.jac + oo) : 1.0;
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < UNR; ++j) {
+                const int f = fb - j;
+                if (f >= 0) {
+                    const double v = lm[j] * lz[j] - lu[j] * vnx;
+                    const double sn = (f == n) ? lm[j] : -lu[j] * snx;
+                    const double J = v + ls[j] * lam0 + sn * lamn;
+                    if (f < n) {
+                        double sol[3];
+                        sol[0] = w * (Jn - J);
+                        sol[1] = (K >= 1) ? w * (5.0 / 6.0) * (J + Jn) : 0.0;
+                        sol[2] = (K >= 2) ? w * (7.0 / 10.0) * (Jn - J) : 0.0;
+#pragma unroll
+                        for (int p = 0; p < M1; ++p) {
+                            const size_t oo = mo[p] + (size_t)((long long)f * stz);
+                            const double Apv = ly[j][p] + sol[p];
+                            u.x[oo] = lx[j][p] + alpha * lp[j][p];
+                            const double rv = lr[j][p] - alpha * Apv;
+                            u.r[oo] = rv;
+                            acc[0] += rv * rv * lj[j][p];
+                            acc[1] += rv * rv;
+                        }
+                    }
+                    vnx = v; snx = sn; Jn = J;
+                }
+            }
+        }
+    }
+    __shared__ double out[2];
+    if (grid_reduce<2>(acc, u.red_part, u.ticket, out) && threadIdx.x == 0) {
+        if (pcg) { st->tmp[0] = out[0]; st->tmp[1] = out[1]; }
+        else { st->tmp[0] = out[1]; }
     }
 }
 

@@ -165,7 +165,7 @@ __device__ __forceinline__ void xrow_warp(const FusedArgs &a, const RowGeom &g, 
 #pragma unroll
                     for (int h = 0; h < 2; ++h)
 #pragma unroll
-                        for (int i = 0; i < kCB; ++i) jv[h][i] = __ldg(a.jac + off[h] + min(ibu[h] + 32 * i, n - 1));
+                        for (int i = 0; i < kCB; ++i) jv[h][i] = (double)__ldg(a.jac + off[h] + min(ibu[h] + 32 * i, n - 1));
                 } else {
 #pragma unroll
                     for (int h = 0; h < 2; ++h)
@@ -308,7 +308,7 @@ constexpr int kXW = 1;      // warps per CTA of the x-row kernel (every warp is 
 // (Letting the z-direction forward substitution ride along here -- rows in plane order, per-row flags for the carry -- was
 // measured and rejected: the nz-long chain of flag hand-overs costs more than the separate marching kernel k_zfwd.)
 template <int K, int M1, int NCL, int LCT, bool FULL>
-__global__ void __launch_bounds__(32 * kXW, 7) k_xrow(const FusedArgs a, const RowGeom g, double *red_part, unsigned *ticket,
+__global__ void __launch_bounds__(32 * kXW, (LCT == 17 ? 10 : 7)) k_xrow(const FusedArgs a, const RowGeom g, double *red_part, unsigned *ticket,
                                                       double *red_out)
 {
     if (a.st->done) return;

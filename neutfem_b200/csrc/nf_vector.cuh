@@ -151,13 +151,13 @@ __global__ void __launch_bounds__(256) k_cg_pupdate(const double *__restrict__ r
 // ---- Jacobi-preconditioned CG with warm start (fast mode) ------------------------------------------------------
 // r = b - Sx (Sx given), z = Minv r, p = z, rr = r.z
 __global__ void __launch_bounds__(256) k_pcg_init(const double *__restrict__ b, const double *__restrict__ Sx,
-                                                  const double *__restrict__ minv, double *__restrict__ r,
+                                                  const jac_t *__restrict__ minv, double *__restrict__ r,
                                                   double *__restrict__ p, long long n, double tol, CgState *st,
                                                   double *part, unsigned *ticket, int fin)
 {
     double acc[3] = {0.0, 0.0, 0.0};
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const double bv = b[i], rv = bv - Sx[i], zv = minv[i] * rv;
+        const double bv = b[i], rv = bv - Sx[i], zv = (double)minv[i] * rv;
         r[i] = rv; p[i] = zv;
         acc[0] += rv * zv; acc[1] += bv * bv; acc[2] += rv * rv;
     }
@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(256) k_pcg_init(const double *__restrict__ b, 
 }
 
 __global__ void __launch_bounds__(256) k_pcg_update(const double *__restrict__ p, const double *__restrict__ Ap,
-                                                    const double *__restrict__ minv, double *__restrict__ x,
+                                                    const jac_t *__restrict__ minv, double *__restrict__ x,
                                                     double *__restrict__ r, long long n, CgState *st, double *part,
                                                     unsigned *ticket, int fin)
 {
@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(256) k_pcg_update(const double *__restrict__ p
         x[i] += alpha * p[i];
         const double rv = r[i] - alpha * Ap[i];
         r[i] = rv;
-        acc[0] += rv * rv * minv[i];
+        acc[0] += rv * rv * (double)minv[i];
         acc[1] += rv * rv;
     }
     __shared__ double out[2];
@@ -197,13 +197,13 @@ __global__ void __launch_bounds__(256) k_pcg_update(const double *__restrict__ p
     }
 }
 
-__global__ void __launch_bounds__(256) k_pcg_pupdate(const double *__restrict__ r, const double *__restrict__ minv,
+__global__ void __launch_bounds__(256) k_pcg_pupdate(const double *__restrict__ r, const jac_t *__restrict__ minv,
                                                      double *__restrict__ p, long long n, const CgState *st)
 {
     if (st->done) return;
     const double beta = st->beta;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-        p[i] = minv[i] * r[i] + beta * p[i];
+        p[i] = (double)minv[i] * r[i] + beta * p[i];
 }
 
 // ---- outer iteration ----------------------------------------------------------------------------------------------
@@ -373,7 +373,7 @@ struct JacobiArgs {
     const double *D, *SigR, *vol;
     const double *Fx[3], *Fy[3], *Fz[3];
     const double *hx, *hy, *hz;
-    double *minv;          // [nloc*ne]
+    jac_t *minv;           // [nloc*ne]
     long long ne;
     int nx, ny, nz, dim, K, nloc, M1;
     int dirichlet[6];
@@ -419,7 +419,7 @@ __global__ void k_build_jacobi(const JacobiArgs a)
     for (int mode = 0; mode < a.nloc; ++mode) {
         double dg = Sv * a.wC[mode];
         for (int d = 0; d < a.dim; ++d) dg += q[d] * a.cb[d][mode] + a.wface[d][mode] * face_sum[d];
-        a.minv[(size_t)mode * a.ne + e] = (dg > 0.0) ? 1.0 / dg : 1.0;
+        a.minv[(size_t)mode * a.ne + e] = (jac_t)((dg > 0.0) ? 1.0 / dg : 1.0);
     }
 }
 
