@@ -350,9 +350,6 @@ static bool rows_geometry(const nf_ctx *c, RowGeom &g)
     const int nfx = c->nx + 1;
     if (nfx > 32 * kLC || c->ny > 32 * 64) return false;
     g.Cx = (nfx <= 8 * kLC) ? 8 : (nfx <= 16 * kLC ? 16 : 32);
-    // long lines (265 .. 512 cells): one pair at a time over all 32 lanes, 17 faces per lane -- a 21 KB tile per warp instead
-    // of 34 KB, so 10 warps fit on an SM instead of 6
-    if (g.Cx == 16 && c->nx <= 512 && nfx <= 32 * 17 && env_int("NF_XROW_LC17", 1)) g.Cx = 32;
     g.LcX = (nfx + g.Cx - 1) / g.Cx;
     g.PWx = 32 / g.Cx;
     g.NFx = g.Cx * g.LcX;
@@ -371,13 +368,12 @@ static bool rows_geometry(const nf_ctx *c, RowGeom &g)
     return true;
 }
 
-// variants of the x-row code: cells per lane (8 / 16 / 33), faces per lane chunk (33, or 17 for the long-line layout), all
-// chunks full (no guards) or not
+// variants of the x-row code: cells per lane (8 / 16 / 33), all chunks full (no guards) or not. (A 32-lane x 17-face layout
+// for 265..512-cell lines -- 21 KB instead of 34 KB of shared memory per warp -- was measured: no gain.)
 #define NF_ROWS_VARIANTS(c, CALL)                                                                          \
     do {                                                                                                   \
         const int ncl_ = ((c)->nx + 31) / 32, lc_ = (c)->rg.LcX;                                           \
-        if ((c)->rg.Cx == 32 && lc_ <= 17 && ncl_ <= 16) { if (lc_ == 17) CALL(16, 17, true); else CALL(16, 17, false); } \
-        else if (ncl_ <= 8) { if (lc_ == kLC) CALL(8, kLC, true); else CALL(8, kLC, false); }              \
+        if (ncl_ <= 8) { if (lc_ == kLC) CALL(8, kLC, true); else CALL(8, kLC, false); }                   \
         else if (ncl_ <= 16) { if (lc_ == kLC) CALL(16, kLC, true); else CALL(16, kLC, false); }           \
         else CALL(33, kLC, false);                                                                         \
     } while (0)

@@ -308,7 +308,7 @@ constexpr int kXW = 1;      // warps per CTA of the x-row kernel (every warp is 
 // (Letting the z-direction forward substitution ride along here -- rows in plane order, per-row flags for the carry -- was
 // measured and rejected: the nz-long chain of flag hand-overs costs more than the separate marching kernel k_zfwd.)
 template <int K, int M1, int NCL, int LCT, bool FULL>
-__global__ void __launch_bounds__(32 * kXW, (LCT == 17 ? 10 : 7)) k_xrow(const FusedArgs a, const RowGeom g, double *red_part, unsigned *ticket,
+__global__ void __launch_bounds__(32 * kXW, 7) k_xrow(const FusedArgs a, const RowGeom g, double *red_part, unsigned *ticket,
                                                       double *red_out)
 {
     if (a.st->done) return;
@@ -381,6 +381,7 @@ __device__ __forceinline__ void ycol_block(const FusedArgs &a, const RowGeom &g,
     const double *gu = a.u[1] + (size_t)iz * (n + 1) * nx + ixc + (size_t)f0 * nx;       // u_f at gu + j*S, u_{f-1} at gu + (j-1)*S
     const double *gm = a.minv[1] + (size_t)iz * (n + 1) * nx + ixc + (size_t)f0 * nx;
     const double2 zero2 = make_double2(0.0, 0.0);
+    // (prefetching the factor / yp rows towards L2 here was measured: 12 % slower)
     // ---- right-hand side T_f = lo(f-1) - hi(f); p was written during this launch or the previous one: L2 loads
     {
         double2 lop = zero2, dum;
