@@ -151,7 +151,7 @@ PATH_KERNELS = {
     1: "k_plane_fwd + k_zback_update",
     2: "k_(p)cg_pupdate + k_sweep_x + k_sweep_march(y) + k_zfwd + k_zback_update",
     3: "k_xrow (direction update + x lines) + k_ycol (y lines) + k_zfwd + k_zback_update (z back substitution + x/r update)",
-    5: "k_xrow + k_ycol + k_march_slab_fwd + ncclAllGather + k_march_slab_bwd + k_(p)cg_update (+ 2 ncclAllReduce)",
+    5: "k_xrow + k_ycol + k_march_slab_fwd + ncclAllGather + k_slab_iface + ncclAllReduce + k_slab_back_update (z back substitution + x/r update) + ncclAllReduce",
 }
 
 
@@ -193,6 +193,32 @@ def cpu_baseline(args):
     return {"value": st.cg_dof_iterations / dt / 1e9, "unit": UNIT, "cores": 1, "kind": "port",
             "sample": f"oracle port of the reference algorithm on synthetic IAEA-3D {mesh[0]}x{mesh[1]}x{mesh[2]} RT{args.rt}-P{args.p}, "
                       f"2 outer iterations, {sum(st.cg_iterations)} CG iterations, {dt:.1f} s, SparseLU of A per group solve included"}
+
+
+def converged_solve(args, device):
+    """BASELINE.json's other half of the metric, absolute time to a converged k-eff: the same problem family refined to a
+    mesh whose full power iteration finishes in well under a minute (default 128x128x100, RT1-P1, 2 groups), script
+    tolerances (1e-5 on k, 1e-4 on the flux), Chebyshev acceleration, through the C ABI from host buffers."""
+    from neutfem_b200 import benchmarks as bm, cabi
+    mesh = tuple(args.converged_mesh)
+    p = bm.problem_iaea3d_synthetic(*mesh)
+    t0 = time.perf_counter()
+    c = cabi.Context(args.rt, args.p, p.ng, p.x_breaks, p.y_breaks, p.z_breaks, device=device)
+    for a, t, v in p.bcs:
+        c.set_bc(a, t, v)
+    c.set_solver(solver_type=cabi.BICGSTAB, tol_keff=1e-5, tol_flux=1e-4, max_outer=1000, max_inner=2000,
+                 mode=cabi.MODE_FAST if args.mode == "fast" else cabi.MODE_PARITY)
+    c.upload_xs(D=p.D, SigR=p.SigR, NSF=p.NSF, Chi=p.Chi, SigS=p.SigS)
+    c.build()
+    k, st = c.solve_keff(False)
+    c.get_flux()
+    dt = time.perf_counter() - t0
+    out = {"mesh": list(mesh), "n_phi_per_group": int(c.n_Phi), "seconds": dt, "keff": k, "converged": bool(st["converged"]),
+           "outer_iterations": st["outer_iterations"], "cg_iterations": st["cg_iterations"], "ms_device": st["ms_total"],
+           "schur_cg_gdof_per_s": st["cg_dof_iterations"] / max(st["ms_schur_cg"], 1e-9) / 1e6,
+           "what": "nf_create + nf_upload_xs + nf_build + nf_solve_keff (to tol_keff 1e-5, tol_flux 1e-4) + nf_get_flux, wall clock"}
+    c.close()
+    return out
 
 
 def run_ours(args):
@@ -314,6 +340,8 @@ def run_ours(args):
     if rank == 0 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args)
     ctx.close()
+    if world == 1 and not args.no_converged:
+        line["time_to_keff"] = converged_solve(args, local_rank)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -337,6 +365,8 @@ def main():
     ap.add_argument("--mode", default="fast", choices=["fast", "parity"])
     ap.add_argument("--tol-flux", type=float, default=1e-4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-converged", action="store_true", help="skip the time-to-converged-k-eff run on the reduced mesh")
+    ap.add_argument("--converged-mesh", type=int, nargs=3, default=[128, 128, 100])
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
