@@ -359,7 +359,7 @@ static bool rows_geometry(const nf_ctx *c, RowGeom &g)
     int pj = g.NFx + 2;
     while (pj % 16 != 8) ++pj;
     g.pitchJ = pj;
-    g.xsmemW = (2 * (g.NFx + 2) + std::max(g.PWx * c->M1 * g.pitchP, g.PWx * g.pitchJ) + 1) & ~1;      // J reuses the P tile
+    g.xsmemW = (2 * (g.NFx + 2) + g.PWx * c->M1 * g.pitchP + g.PWx * g.pitchJ + 1) & ~1;
     if (c->nx & 1) return false;                  // the y columns are processed two at a time (16-byte vectors)
     g.Cy = (c->ny <= 8 * 16) ? 8 : (c->ny <= 16 * 16 ? 16 : 32);      // chunks of <= 16 cells where possible
     g.warpsY = kYT / 32;                          // (256-thread CTAs for the longest lines were measured slower)

@@ -122,7 +122,8 @@ __device__ __forceinline__ void xrow_warp(const FusedArgs &a, const RowGeom &g, 
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int n = a.nx, C = g.Cx, Lc = g.LcX, PW = g.PWx, NF = g.NFx, PP = g.pitchP, PJ = g.pitchJ;
-    double *UB = sm, *MINV = UB + NF + 2, *P = MINV + NF + 2, *Jb = P;     // J reuses the P tile once the chunks hold T in registers
+    double *UB = sm, *MINV = UB + NF + 2, *P = MINV + NF + 2, *Jb = P + PW * M1 * PP;
+    // (letting J reuse the P tile -- 9 KB less per warp, p re-read from L2 for the output -- was measured: 12-25 % slower)
     const long long line = (long long)iz * a.ny + iy;
     const size_t e0 = (size_t)line * n;
     const bool pcg = a.pcg != 0, hasb = (beta != 0.0);
@@ -145,10 +146,6 @@ __device__ __forceinline__ void xrow_warp(const FusedArgs &a, const RowGeom &g, 
     const int jn = max(0, min(Lc, n + 1 - f0));
     for (int t0 = 0; t0 < a.nt; t0 += PW) {
         const int np = min(PW, a.nt - t0);
-        if (t0 > 0 || true) {   // the previous J rows overwrote the zero pads (cells >= nx) of the P rows: restore them
-            const int npad = PP - n;
-            for (int i = lane; i < PW * M1 * npad; i += 32) P[(i / npad) * PP + n + (i % npad)] = 0.0;
-        }
         // ---- direction update p = M^-1 r + beta p for the modes of these pairs, staged in P (coalesced).
         // Units of (mode, 256-cell batch) are processed two at a time: 48 independent loads per lane in flight.
         {
@@ -234,7 +231,6 @@ __device__ __forceinline__ void xrow_warp(const FusedArgs &a, const RowGeom &g, 
                 }
             }
         }
-        __syncwarp();               // every lane holds its T: the P tile may now be overwritten by J
         const double *ub = UB + f0, *mb = MINV + f0;
         auto um = [&](const int j) { return ub[j]; };
         auto uf = [&](const int j) { return ub[j + 1]; };
@@ -284,7 +280,7 @@ __device__ __forceinline__ void xrow_warp(const FusedArgs &a, const RowGeom &g, 
                     for (int p = 0; p < M1; ++p) {
                         const int md = a.mode[0][t0 + s2][p];
                         const double cw = a.wC[md], c0 = a.cb[0][md] * ify0, c1 = a.cb[1][md] * ify1, c2 = a.cb[2][md] * ify2;
-                        const double *Pm = a.p + (size_t)md * a.ne + e0 + lane + 32 * cb;     // this lane's own stores of a moment ago
+                        const double *Pm = P + (s2 * M1 + p) * PP + lane + 32 * cb;
                         double *yo = a.yp + (size_t)md * a.ne + e0 + lane + 32 * cb;
 #pragma unroll
                         for (int c = 0; c < kCB; ++c) {
@@ -313,7 +309,7 @@ constexpr int kXW = 1;      // warps per CTA of the x-row kernel (every warp is 
 // (Letting the z-direction forward substitution ride along here -- rows in plane order, per-row flags for the carry -- was
 // measured and rejected: the nz-long chain of flag hand-overs costs more than the separate marching kernel k_zfwd.)
 template <int K, int M1, int NCL, int LCT, bool FULL>
-__global__ void __launch_bounds__(32 * kXW, 8) k_xrow(const FusedArgs a, const RowGeom g, double *red_part, unsigned *ticket,
+__global__ void __launch_bounds__(32 * kXW, 7) k_xrow(const FusedArgs a, const RowGeom g, double *red_part, unsigned *ticket,
                                                       double *red_out)
 {
     if (a.st->done) return;
