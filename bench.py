@@ -197,7 +197,7 @@ def cpu_baseline(args):
 
 def converged_solve(args, device):
     """BASELINE.json's other half of the metric, absolute time to a converged k-eff: the same problem family refined to a
-    mesh whose full power iteration finishes in well under a minute (default 128x128x100, RT1-P1, 2 groups), script
+    mesh whose full power iteration finishes in well under a minute (default 256x256x200 = 105 M flux DOFs per group, RT1-P1), script
     tolerances (1e-5 on k, 1e-4 on the flux), Chebyshev acceleration, through the C ABI from host buffers."""
     from neutfem_b200 import benchmarks as bm, cabi
     mesh = tuple(args.converged_mesh)
@@ -366,7 +366,7 @@ def main():
     ap.add_argument("--tol-flux", type=float, default=1e-4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-converged", action="store_true", help="skip the time-to-converged-k-eff run on the reduced mesh")
-    ap.add_argument("--converged-mesh", type=int, nargs=3, default=[128, 128, 100])
+    ap.add_argument("--converged-mesh", type=int, nargs=3, default=[256, 256, 200])
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
