@@ -114,6 +114,10 @@ __device__ __forceinline__ void chunk_bwd_final(double (&T)[LCT], const int jn, 
 // J[PW][pitchJ]; the cells >= nx of the P rows must be zero on entry (they are never written).
 // NCL = compile-time bound on the cells a lane owns (ceil(nx / 32)): per-cell coefficients live in registers.
 constexpr int kCB = 8;          // cells per lane in one coalesced batch (256 cells)
+#ifndef NF_XROW_UB
+#define NF_XROW_UB 2
+#endif
+constexpr int kUB = NF_XROW_UB; // (mode, batch) units loaded together in the direction update: 24 * kUB independent loads per lane
 
 template <int K, int M1, int NCL, int LCT, bool FULL>
 __device__ __forceinline__ void xrow_warp(const FusedArgs &a, const RowGeom &g, const int iz, const int iy, const double beta,
@@ -147,15 +151,15 @@ __device__ __forceinline__ void xrow_warp(const FusedArgs &a, const RowGeom &g, 
     for (int t0 = 0; t0 < a.nt; t0 += PW) {
         const int np = min(PW, a.nt - t0);
         // ---- direction update p = M^-1 r + beta p for the modes of these pairs, staged in P (coalesced).
-        // Units of (mode, 256-cell batch) are processed two at a time: 48 independent loads per lane in flight.
+        // Units of (mode, 256-cell batch) are processed kUB at a time: 24 * kUB independent loads per lane in flight.
         {
             const int nunits = np * M1 * ncb;
-            for (int u0 = 0; u0 < nunits; u0 += 2) {
-                double rv[2][kCB], jv[2][kCB], po[2][kCB];
-                size_t off[2]; int mmu[2], ibu[2];
+            for (int u0 = 0; u0 < nunits; u0 += kUB) {
+                double rv[kUB][kCB], jv[kUB][kCB], po[kUB][kCB];
+                size_t off[kUB]; int mmu[kUB], ibu[kUB];
                 // loads are unconditional (indices clamped into the row): nothing may wait on a load before all are issued
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
+                for (int h = 0; h < kUB; ++h) {
                     const int u = min(u0 + h, nunits - 1);
                     mmu[h] = u / ncb; ibu[h] = (u - mmu[h] * ncb) * (32 * kCB) + lane;
                     off[h] = (size_t)a.mode[0][t0 + mmu[h] / M1][mmu[h] % M1] * a.ne + e0;
@@ -164,28 +168,28 @@ __device__ __forceinline__ void xrow_warp(const FusedArgs &a, const RowGeom &g, 
                 }
                 if (pcg) {
 #pragma unroll
-                    for (int h = 0; h < 2; ++h)
+                    for (int h = 0; h < kUB; ++h)
 #pragma unroll
                         for (int i = 0; i < kCB; ++i) jv[h][i] = (double)__ldg(a.jac + off[h] + min(ibu[h] + 32 * i, n - 1));
                 } else {
 #pragma unroll
-                    for (int h = 0; h < 2; ++h)
+                    for (int h = 0; h < kUB; ++h)
 #pragma unroll
                         for (int i = 0; i < kCB; ++i) jv[h][i] = 1.0;
                 }
                 if (hasb) {
 #pragma unroll
-                    for (int h = 0; h < 2; ++h)
+                    for (int h = 0; h < kUB; ++h)
 #pragma unroll
                         for (int i = 0; i < kCB; ++i) po[h][i] = a.p[off[h] + min(ibu[h] + 32 * i, n - 1)];
                 } else {
 #pragma unroll
-                    for (int h = 0; h < 2; ++h)
+                    for (int h = 0; h < kUB; ++h)
 #pragma unroll
                         for (int i = 0; i < kCB; ++i) po[h][i] = 0.0;
                 }
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
+                for (int h = 0; h < kUB; ++h) {
                     const bool hv = (u0 + h < nunits);
                     double *Pm = P + mmu[h] * PP;
 #pragma unroll
@@ -201,11 +205,13 @@ __device__ __forceinline__ void xrow_warp(const FusedArgs &a, const RowGeom &g, 
             }
         }
         // per-cell coefficients of the lane's cells: requested now, first used after the solve
-        double Dv[NCL], Sv[NCL], Vv[NCL];
+        // (3-D only: 1/Fx of the y and z directions are both hx, and the cell volume is hx * hy * hz = hx * ify0)
+        double Dv[NCL], Sv[NCL], Hx[NCL], F0[NCL];
 #pragma unroll
         for (int c = 0; c < NCL; ++c) {
             const int ixl = min(lane + 32 * c, n - 1);
-            Dv[c] = __ldg(a.D + e0 + ixl); Sv[c] = __ldg(a.SigR + e0 + ixl); Vv[c] = __ldg(a.vol + e0 + ixl);
+            Dv[c] = __ldg(a.D + e0 + ixl); Sv[c] = __ldg(a.SigR + e0 + ixl);
+            Hx[c] = __ldg(a.iFx[1] + ixl); F0[c] = __ldg(a.iFx[0] + ixl);
         }
         if (t0 == 0) {     // first use of the factors requested at the top of the row
             ify0 = 1.0 / (fy0 * fz0); ify1 = 1.0 / (fy1 * fz1); ify2 = 1.0 / (fy2 * fz2);
@@ -269,9 +275,8 @@ __device__ __forceinline__ void xrow_warp(const FusedArgs &a, const RowGeom &g, 
 #pragma unroll
                 for (int c = 0; c < kCB; ++c) {
                     const int cc = (cb + c < NCL) ? cb + c : NCL - 1;
-                    const int ixl = min(lane + 32 * cc, n - 1);
-                    G0[c] = Dv[cc] * __ldg(a.iFx[0] + ixl); G1[c] = Dv[cc] * __ldg(a.iFx[1] + ixl); G2[c] = Dv[cc] * __ldg(a.iFx[2] + ixl);
-                    SV[c] = Sv[cc] * Vv[cc];
+                    G0[c] = Dv[cc] * F0[cc]; G1[c] = Dv[cc] * Hx[cc]; G2[c] = G1[c];
+                    SV[c] = Sv[cc] * (Hx[cc] * ify0);
                 }
                 for (int s2 = 0; s2 < np; ++s2) {
                     const double w = a.w[t0 + s2];
