@@ -109,6 +109,17 @@ def pinned(arr):
     return v, t
 
 
+def single_thread():
+    """The reference path is single-threaded (no OpenMP pragmas, column-major Eigen products); keep numpy /
+    scipy's BLAS pools from fanning the oracle port out over the host cores so that `cores: 1` is what really ran."""
+    try:
+        from threadpoolctl import threadpool_limits
+        return threadpool_limits(limits=1)
+    except Exception:
+        import contextlib
+        return contextlib.nullcontext()
+
+
 def run_reference(args):
     """CPU arm: the oracle port of the reference algorithm (SparseLU of A per group solve + unpreconditioned CG,
     src/NeutFEM.cpp:2084-2105, src/solvers.cpp:149-240, 577-636) on a bounded sample of the workload."""
@@ -124,11 +135,12 @@ def run_reference(args):
     o.set_tol(1e-5, 1e-4, 1e-4, 200, 1000)
     p.apply(o)
     o.BuildMatrices()
-    if args.warmup > 0:
-        o.SolveKeff(max_outer_override=args.warmup)
-    t0 = time.perf_counter()
-    k = o.SolveKeff(max_outer_override=args.steps)
-    dt = time.perf_counter() - t0
+    with single_thread():
+        if args.warmup > 0:
+            o.SolveKeff(max_outer_override=args.warmup)
+        t0 = time.perf_counter()
+        k = o.SolveKeff(max_outer_override=args.steps)
+        dt = time.perf_counter() - t0
     st = o.stats
     val = st.cg_dof_iterations / dt / 1e9
     sample = (f"oracle port, synthetic IAEA-3D {mesh[0]}x{mesh[1]}x{mesh[2]} RT{args.rt}-P{args.p} (n_phi={o.fes.n_Phi}/group), "
@@ -186,9 +198,10 @@ def cpu_baseline(args):
     o.set_tol(1e-5, 1e-4, 1e-4, 200, 1000)
     p.apply(o)
     o.BuildMatrices()
-    t0 = time.perf_counter()
-    o.SolveKeff(max_outer_override=2)
-    dt = time.perf_counter() - t0
+    with single_thread():
+        t0 = time.perf_counter()
+        o.SolveKeff(max_outer_override=2)
+        dt = time.perf_counter() - t0
     st = o.stats
     return {"value": st.cg_dof_iterations / dt / 1e9, "unit": UNIT, "cores": 1, "kind": "port",
             "sample": f"oracle port of the reference algorithm on synthetic IAEA-3D {mesh[0]}x{mesh[1]}x{mesh[2]} RT{args.rt}-P{args.p}, "
