@@ -50,6 +50,51 @@ static std::vector<double> to_vec(const darray &a)
     return std::vector<double>(p, p + b.size);
 }
 
+// ---- refined-mesh projection (reference surface: project_flux / project_power, src/wrapper.cpp:1003-1043; declared in
+// include/NeutFEM.hpp:303-312 but never defined there, so only the docstring semantics exist: "exact mean values of the
+// polynomial flux on a finer sub-mesh, using the Legendre coefficients"). The flux of a cell is
+// sum_abc c_abc P_a(xi) P_b(eta) P_c(zeta) on [-1,1]^d with the local index a + (m+1) b + (m+1)^2 c (src/FEM.cpp:638-654);
+// the mean of P_a over a sub-interval [s0, s1] is 1, (s0+s1)/2, (s0^2 + s0 s1 + s1^2 - 1)/2 for a = 0, 1, 2.
+// dofs: [ne * nloc] of one group, element-major. Returns the sub-cell means on the mesh refined by (rx, ry, rz),
+// index ((iz*rz + kz) * (ny*ry) + iy*ry + ky) * (nx*rx) + ix*rx + kx. Host arithmetic on accessor data, not on the hot path.
+static inline double legendre_mean(int a, double s0, double s1)
+{
+    if (a == 0) return 1.0;
+    if (a == 1) return 0.5 * (s0 + s1);
+    return 0.5 * (s0 * s0 + s0 * s1 + s1 * s1 - 1.0);
+}
+
+static std::vector<double> project_legendre(const double *dofs, int nx, int ny, int nz, int dim, int m, int rx, int ry, int rz)
+{
+    const int m1 = m + 1;
+    const int r[3] = {std::max(rx, 1), dim >= 2 ? std::max(ry, 1) : 1, dim >= 3 ? std::max(rz, 1) : 1};
+    const int nloc = (dim == 1) ? m1 : (dim == 2 ? m1 * m1 : m1 * m1 * m1);
+    std::vector<std::vector<double>> w(3);            // w[d][k * m1 + a] = mean of P_a over sub-interval k of direction d
+    for (int d = 0; d < 3; ++d) {
+        w[d].assign((size_t)r[d] * m1, 0.0);
+        for (int k = 0; k < r[d]; ++k)
+            for (int a = 0; a < m1; ++a) w[d][k * m1 + a] = legendre_mean(a, -1.0 + 2.0 * k / r[d], -1.0 + 2.0 * (k + 1) / r[d]);
+    }
+    const long long NX = (long long)nx * r[0], NY = (long long)ny * r[1], NZ = (long long)nz * r[2];
+    std::vector<double> out((size_t)(NX * NY * NZ));
+    for (int iz = 0; iz < nz; ++iz)
+        for (int iy = 0; iy < ny; ++iy)
+            for (int ix = 0; ix < nx; ++ix) {
+                const double *c = dofs + (((size_t)iz * ny + iy) * nx + ix) * nloc;
+                for (int kz = 0; kz < r[2]; ++kz)
+                    for (int ky = 0; ky < r[1]; ++ky)
+                        for (int kx = 0; kx < r[0]; ++kx) {
+                            double v = 0.0;
+                            for (int l = 0; l < nloc; ++l) {
+                                const int a = l % m1, b = (dim >= 2) ? (l / m1) % m1 : 0, cc = (dim >= 3) ? l / (m1 * m1) : 0;
+                                v += c[l] * w[0][kx * m1 + a] * w[1][ky * m1 + b] * w[2][kz * m1 + cc];
+                            }
+                            out[(size_t)(((long long)iz * r[2] + kz) * NY + (long long)iy * r[1] + ky) * NX + (long long)ix * r[0] + kx] = v;
+                        }
+            }
+    return out;
+}
+
 class NeutFEM {
 public:
     NeutFEM(int rt_order, int p_order, int ng, const std::vector<double> &xb, const std::vector<double> &yb,
@@ -251,6 +296,54 @@ public:
         return {kc, proj};
     }
 
+    // ---- refined-mesh projections (docstring semantics of src/wrapper.cpp:1003-1043; PARITY UNPINNED: no reference body)
+    static std::vector<int> refine3(const std::vector<int> &refine)
+    {
+        std::vector<int> r = {1, 1, 1};
+        for (size_t i = 0; i < refine.size() && i < 3; ++i) r[i] = std::max(refine[i], 1);
+        return r;
+    }
+    py::array_t<double> shaped(const std::vector<double> &v, bool groups, const std::vector<int> &r) const
+    {
+        std::vector<py::ssize_t> shape;
+        if (groups) shape.push_back(ng_);
+        if (dim_ >= 3) shape.push_back((py::ssize_t)nz_ * r[2]);
+        if (dim_ >= 2) shape.push_back((py::ssize_t)ny_ * r[1]);
+        shape.push_back((py::ssize_t)nx_ * r[0]);
+        py::array_t<double> a(shape);
+        std::copy(v.begin(), v.end(), a.mutable_data());
+        return a;
+    }
+    py::array_t<double> ProjectFlux(const std::vector<int> &refine, bool adjoint)
+    {
+        const std::vector<int> r = refine3(refine);
+        const std::vector<double> &src = adjoint ? PhiAdj_ : Phi_;
+        std::vector<double> all;
+        for (int g = 0; g < ng_; ++g) {
+            std::vector<double> one = project_legendre(src.data() + (size_t)g * nphi_, nx_, ny_, nz_, dim_, p_, r[0], r[1], r[2]);
+            all.insert(all.end(), one.begin(), one.end());
+        }
+        return shaped(all, true, r);
+    }
+    py::array_t<double> ProjectPower(const std::vector<int> &refine, bool adjoint)
+    {
+        const std::vector<int> r = refine3(refine);
+        const std::vector<double> &src = adjoint ? PhiAdj_ : Phi_;
+        const int rr[3] = {r[0], dim_ >= 2 ? r[1] : 1, dim_ >= 3 ? r[2] : 1};
+        const long long NX = (long long)nx_ * rr[0], NY = (long long)ny_ * rr[1], NZ = (long long)nz_ * rr[2];
+        std::vector<double> pw((size_t)(NX * NY * NZ), 0.0);
+        for (int g = 0; g < ng_; ++g) {
+            std::vector<double> one = project_legendre(src.data() + (size_t)g * nphi_, nx_, ny_, nz_, dim_, p_, r[0], r[1], r[2]);
+            for (long long Z = 0; Z < NZ; ++Z)
+                for (long long Y = 0; Y < NY; ++Y)
+                    for (long long X = 0; X < NX; ++X) {
+                        const long long e = ((Z / rr[2]) * ny_ + Y / rr[1]) * nx_ + X / rr[0];      // parent cell: XS are cell-wise
+                        pw[(size_t)((Z * NY + Y) * NX + X)] += KSF_[(size_t)g * ne_ + e] * one[(size_t)((Z * NY + Y) * NX + X)];
+                    }
+        }
+        return shaped(pw, false, r);
+    }
+
     // ---- accessors (src/NeutFEM.cpp:2626-2730)
     py::array_t<double> view(std::vector<double> &v, bool sigs, py::object owner)
     {
@@ -419,6 +512,19 @@ PYBIND11_MODULE(_neutfem_eigen, m)
         .value("BICGSTAB", LinearSolverType::BICGSTAB).value("BICGSTAB_DIAG", LinearSolverType::BICGSTAB_DIAG)
         .value("BICGSTAB_ILU", LinearSolverType::BICGSTAB_ILU).value("LCG", LinearSolverType::LCG);
 
+    m.def("project_legendre", [](const darray &dofs, int nx, int ny, int nz, int dim, int m_order, const std::vector<int> &refine) {
+              const int m1 = m_order + 1;
+              const long long nloc = (dim == 1) ? m1 : (dim == 2 ? m1 * m1 : (long long)m1 * m1 * m1);
+              if (dofs.size() != (py::ssize_t)((long long)nx * ny * nz * nloc)) throw std::runtime_error("project_legendre: dofs has the wrong size");
+              std::vector<int> r = {1, 1, 1};
+              for (size_t i = 0; i < refine.size() && i < 3; ++i) r[i] = std::max(refine[i], 1);
+              std::vector<double> v = project_legendre(dofs.data(), nx, ny, nz, dim, m_order, r[0], r[1], r[2]);
+              py::array_t<double> a((py::ssize_t)v.size());
+              std::copy(v.begin(), v.end(), a.mutable_data());
+              return a;
+          }, py::arg("dofs"), py::arg("nx"), py::arg("ny"), py::arg("nz"), py::arg("dim"), py::arg("p_order"), py::arg("refine"),
+          "Host helper behind project_flux: sub-cell means of a tensor-Legendre expansion (element-major DOFs of one group)");
+
     auto unimplemented = [](const char *name) {
         return [name](NeutFEM &, const std::vector<int> &, bool) -> py::object {
             throw std::runtime_error(std::string(name) + ": declared but never defined in the reference (include/NeutFEM.hpp:303-312); not provided");
@@ -491,7 +597,9 @@ PYBIND11_MODULE(_neutfem_eigen, m)
         .def("GetLastKeff", [](const NeutFEM &s) { return s.last_k_; })
         .def("GetLastKeffAdjoint", [](const NeutFEM &s) { return s.last_k_adj_; })
         .def("GetSolverName", &NeutFEM::GetSolverName)
-        .def("project_flux", unimplemented("project_flux"), py::arg("refine"), py::arg("adjoint") = false)
-        .def("project_power", unimplemented("project_power"), py::arg("refine"), py::arg("adjoint") = false)
+        .def("project_flux", &NeutFEM::ProjectFlux, py::arg("refine"), py::arg("adjoint") = false,
+             "Exact sub-cell means of the polynomial flux on the mesh refined by [rx, ry, rz]; shape (ng[, nz*rz][, ny*ry], nx*rx)")
+        .def("project_power", &NeutFEM::ProjectPower, py::arg("refine"), py::arg("adjoint") = false,
+             "sum_g KSF_g * projected flux_g on the refined mesh; shape ([nz*rz][, ny*ry], nx*rx)")
         .def("zoom_resolved", unimplemented("zoom_resolved"), py::arg("refine"), py::arg("adjoint") = false);
 }

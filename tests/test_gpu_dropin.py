@@ -83,4 +83,24 @@ def test_errors_are_runtime_errors():
     with pytest.raises(RuntimeError):
         s.SolveKeff()                # before BuildMatrices (solvers.cpp:204-207)
     with pytest.raises(RuntimeError):
-        s.project_flux([2, 2, 1])
+        s.zoom_resolved([2, 2, 1])   # declared, never defined in the reference; not provided here either
+
+
+def test_project_flux_and_power_on_refined_mesh():
+    """project_flux / project_power (declared but undefined in the reference: docstring semantics, parity unpinned):
+    shapes follow the get_flux convention, the refined values average back to the cell means, power = sum_g KSF_g * flux_g."""
+    p = bm.problem_2d("biblis2d", 1)
+    s = _script_style_solver(p, 1, 1)
+    s.get_KSF()[...] = np.asarray(s.get_NSF()) * 0.4
+    s.set_tol(1e-7, 1e-7, 1e-7, 300, 3000)
+    s.SolveKeff()
+    nx, ny = s.get_flux().shape[-1], s.get_flux().shape[-2]
+    f = s.project_flux([2, 3, 1])
+    assert f.shape == (p.ng, ny * 3, nx * 2)
+    back = f.reshape(p.ng, ny, 3, nx, 2).mean(axis=(2, 4))
+    assert relerr(back, s.get_flux()) < 1e-13
+    pw = s.project_power([2, 3, 1])
+    assert pw.shape == (ny * 3, nx * 2)
+    ksf = np.repeat(np.repeat(np.asarray(s.get_KSF()), 3, axis=1), 2, axis=2)
+    assert relerr(pw, (ksf * f).sum(axis=0)) < 1e-13
+    assert s.project_flux([1, 1, 1], adjoint=True).shape == (p.ng, ny, nx)
