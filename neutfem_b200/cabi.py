@@ -53,10 +53,11 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        raise RuntimeError(f"{LIB_PATH} not found: build the CUDA library first (__graft_entry__.build()); "
+    path = os.environ.get("NEUTFEM_B200_LIB") or LIB_PATH          # development knob: a differently tuned build of the library
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} not found: build the CUDA library first (__graft_entry__.build()); "
                            "there is no CPU fallback")
-    L = ctypes.CDLL(LIB_PATH)
+    L = ctypes.CDLL(path)
     dp = ctypes.POINTER(ctypes.c_double)
     vp = ctypes.c_void_p
     L.nf_create.argtypes = [ctypes.POINTER(vp), ctypes.c_int, ctypes.c_int, ctypes.c_int, dp, ctypes.c_int, dp,

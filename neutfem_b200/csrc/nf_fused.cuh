@@ -581,10 +581,13 @@ __global__ void __launch_bounds__(kFT, NF_FUSED_MINB) k_plane_fwd(const FusedArg
 // ---- z forward substitution alone (hybrid path: separate x / y sweep kernels + this + k_zback_update) --------------------
 // One thread per (ix, iy, transverse pair), marching up in z; writes zs and accumulates w * sum_f z_f^2 / m_f.
 #ifndef NF_ZF_UNR
-#define NF_ZF_UNR 4
+#define NF_ZF_UNR 2
+#endif
+#ifndef NF_ZF_MINB
+#define NF_ZF_MINB 8
 #endif
 template <int K, int M1>
-__global__ void __launch_bounds__(128, 6) k_zfwd(const FusedArgs a, double *red_part, unsigned *ticket, double *red_out)
+__global__ void __launch_bounds__(128, NF_ZF_MINB) k_zfwd(const FusedArgs a, double *red_part, unsigned *ticket, double *red_out)
 {
     if (a.st->done) return;
     constexpr int UNR = NF_ZF_UNR;
@@ -645,7 +648,7 @@ __global__ void __launch_bounds__(128, 6) k_zfwd(const FusedArgs a, double *red_
 // One thread per (ix, iy, transverse pair of the z direction), marching from the top plane down. For every cell:
 // Ap = yp + w B_z J ; x += alpha p ; r -= alpha Ap ; accumulates r.M^-1 r and r.r (solvers.cpp:601-631).
 #ifndef NF_ZB_UNR
-#define NF_ZB_UNR 2
+#define NF_ZB_UNR 3
 #endif
 template <int K, int M1>
 __global__ void __launch_bounds__(128, 4) k_zback_update(const FusedArgs a)

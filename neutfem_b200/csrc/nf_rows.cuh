@@ -346,7 +346,10 @@ __global__ void __launch_bounds__(32 * kXW, 7) k_xrow(const FusedArgs a, const R
 // Needs nx even. The u arrays carry one row of front padding so that u_{f-1} of the first face of a column is a legal
 // load that returns 0 (it is the u of the last face of the line below, which is 0 by construction).
 constexpr int kRowPad = 48;     // rows of padding behind the arrays (unconditional batch loads run past a column's end)
-constexpr int kYB = 8;          // rows of loads issued ahead of each stretch of work
+#ifndef NF_YB
+#define NF_YB 8
+#endif
+constexpr int kYB = NF_YB;      // rows of loads issued ahead of each stretch of work
 constexpr int kYT = 128;        // threads per CTA (256 for lines of more than 256 cells: 16 columns per item)
 
 __device__ __forceinline__ double2 ld2cg(const double *p) { return __ldcg(reinterpret_cast<const double2 *>(p)); }
