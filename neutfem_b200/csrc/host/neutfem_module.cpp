@@ -344,6 +344,110 @@ public:
         return shaped(pw, false, r);
     }
 
+    // zoom_resolved (docstring of src/wrapper.cpp:1044-1063: "re-solves the problem on a refined mesh with the sources frozen
+    // from the coarse mesh"; no reference body, PARITY UNPINNED). The converged coarse flux gives, per group, the frozen source
+    // q_g = chi_g/k * sum_g' nuSigf_g' phi_g' + sum_{g' != g} Sigs_{g'->g} phi_g' as a polynomial per coarse cell; it is
+    // re-expanded exactly in the Legendre basis of every fine cell, weighted with the fine mass matrix, and one fixed-source
+    // Schur solve per group runs on the fine mesh (nf_schur_solve). With refine = [1,1,1] this reproduces the coarse flux.
+    // Returns the cell means (DOF 0) on the refined mesh, shaped like get_flux().
+    py::array_t<double> ZoomResolved(const std::vector<int> &refine, bool adjoint)
+    {
+        require_built("zoom_resolved");
+        if (adjoint) throw std::runtime_error("zoom_resolved: the adjoint variant is not provided");
+        if (!has_valid_) throw std::runtime_error("zoom_resolved: appeler SolveKeff() avant zoom_resolved()");
+        const std::vector<int> r = refine3(refine);
+        const int rr[3] = {r[0], dim_ >= 2 ? r[1] : 1, dim_ >= 3 ? r[2] : 1};
+        auto subdivide = [](const std::vector<double> &b, int k) {
+            if (b.size() < 2) return b;
+            std::vector<double> o;
+            o.reserve((b.size() - 1) * (size_t)k + 1);
+            for (size_t i = 0; i + 1 < b.size(); ++i)
+                for (int j = 0; j < k; ++j) o.push_back(b[i] + (b[i + 1] - b[i]) * j / k);
+            o.push_back(b.back());
+            return o;
+        };
+        const std::vector<double> xf = subdivide(xb_, rr[0]), yf = subdivide(yb_, rr[1]), zf = subdivide(zb_, rr[2]);
+        NeutFEM f(rt_, p_, ng_, xf, yf, zf, true);
+        f.mode_ = mode_;
+        f.SetLinearSolver(solver_);
+        f.SetTolerance(tol_keff_, tol_flux_, tol_L2_, max_outer_, max_inner_);
+        f.SetVerbosity(VerbosityLevel::SILENT);
+        for (auto &kv : bc_) f.SetBC(kv.first, kv.second.first, kv.second.second);
+        const long long NX = (long long)nx_ * rr[0], NY = (long long)ny_ * rr[1], NZ = (long long)nz_ * rr[2], nef = NX * NY * NZ;
+        auto parent = [&](long long X, long long Y, long long Z) { return ((Z / rr[2]) * ny_ + Y / rr[1]) * nx_ + X / rr[0]; };
+        for (int g = 0; g < ng_; ++g)
+            for (long long Z = 0; Z < NZ; ++Z)
+                for (long long Y = 0; Y < NY; ++Y)
+                    for (long long X = 0; X < NX; ++X) {
+                        const long long ef = (Z * NY + Y) * NX + X, e = parent(X, Y, Z);
+                        f.D_[g * nef + ef] = D_[(size_t)g * ne_ + e]; f.SigR_[g * nef + ef] = SigR_[(size_t)g * ne_ + e];
+                        f.NSF_[g * nef + ef] = NSF_[(size_t)g * ne_ + e]; f.Chi_[g * nef + ef] = Chi_[(size_t)g * ne_ + e];
+                        f.KSF_[g * nef + ef] = KSF_[(size_t)g * ne_ + e];
+                        for (int gf = 0; gf < ng_; ++gf)
+                            f.SigS_[((size_t)g * ng_ + gf) * nef + ef] = SigS_[((size_t)g * ng_ + gf) * ne_ + e];
+                    }
+        f.BuildMatrices();
+        // re-expansion of P_a on the parent interval in the Legendre basis of sub-interval k: P_a(mid + half t) = sum_a' T[a'][a] P_a'(t)
+        const int m1 = p_ + 1;
+        std::vector<std::vector<double>> T(3);
+        for (int d = 0; d < 3; ++d) {
+            T[d].assign((size_t)rr[d] * 9, 0.0);
+            for (int k = 0; k < rr[d]; ++k) {
+                const double half = 1.0 / rr[d], mid = -1.0 + (2.0 * k + 1.0) * half;
+                double *t = &T[d][(size_t)k * 9];          // t[a' * 3 + a]
+                t[0 * 3 + 0] = 1.0;
+                t[0 * 3 + 1] = mid; t[1 * 3 + 1] = half;
+                t[0 * 3 + 2] = 0.5 * (3.0 * mid * mid - 1.0) + 0.5 * half * half; t[1 * 3 + 2] = 3.0 * mid * half; t[2 * 3 + 2] = half * half;
+            }
+        }
+        const double two_dim = (dim_ == 1) ? 2.0 : (dim_ == 2 ? 4.0 : 8.0);
+        auto thr14 = [](double v) { return std::fabs(v) > 1e-14 ? v : 0.0; };
+        const long long nphif = nef * nloc_;
+        std::vector<double> rhs((size_t)nphif), phif((size_t)ng_ * nphif, 0.0), coef((size_t)ng_ * nloc_);
+        for (int g = 0; g < ng_; ++g) {
+            for (long long Z = 0; Z < NZ; ++Z)
+                for (long long Y = 0; Y < NY; ++Y)
+                    for (long long X = 0; X < NX; ++X) {
+                        const long long ef = (Z * NY + Y) * NX + X, e = parent(X, Y, Z);
+                        const double *tx = &T[0][(size_t)(X % rr[0]) * 9], *ty = &T[1][(size_t)(Y % rr[1]) * 9], *tz = &T[2][(size_t)(Z % rr[2]) * 9];
+                        double vol = xf[X + 1] - xf[X];
+                        if (dim_ >= 2) vol *= yf[Y + 1] - yf[Y];
+                        if (dim_ >= 3) vol *= zf[Z + 1] - zf[Z];
+                        // fine-cell Legendre coefficients of every group's coarse flux
+                        for (int gp = 0; gp < ng_; ++gp)
+                            for (int lf = 0; lf < nloc_; ++lf) {
+                                const int af = lf % m1, bf = (dim_ >= 2) ? (lf / m1) % m1 : 0, cf = (dim_ >= 3) ? lf / (m1 * m1) : 0;
+                                double v = 0.0;
+                                for (int l = 0; l < nloc_; ++l) {
+                                    const int a = l % m1, b = (dim_ >= 2) ? (l / m1) % m1 : 0, c = (dim_ >= 3) ? l / (m1 * m1) : 0;
+                                    v += Phi_[(size_t)gp * nphi_ + e * nloc_ + l] * tx[af * 3 + a] * (dim_ >= 2 ? ty[bf * 3 + b] : (b == 0 && bf == 0 ? 1.0 : 0.0))
+                                         * (dim_ >= 3 ? tz[cf * 3 + c] : (c == 0 && cf == 0 ? 1.0 : 0.0));
+                                }
+                                coef[(size_t)gp * nloc_ + lf] = v;
+                            }
+                        for (int lf = 0; lf < nloc_; ++lf) {
+                            const int af = lf % m1, bf = (dim_ >= 2) ? (lf / m1) % m1 : 0, cf = (dim_ >= 3) ? lf / (m1 * m1) : 0;
+                            double wfull = 2.0 / (2.0 * af + 1.0);
+                            if (dim_ >= 2) wfull *= 2.0 / (2.0 * bf + 1.0);
+                            if (dim_ >= 3) wfull *= 2.0 / (2.0 * cf + 1.0);
+                            const double mw = vol * ((p_ == 0) ? 1.0 : wfull / two_dim);      // weighted mass (src/NeutFEM.cpp:1204-1302)
+                            double fis = 0.0, sca = 0.0;
+                            for (int gp = 0; gp < ng_; ++gp) {
+                                fis += thr14(NSF_[(size_t)gp * ne_ + e]) * coef[(size_t)gp * nloc_ + lf];
+                                if (gp != g) sca += thr14(SigS_[((size_t)g * ng_ + gp) * ne_ + e]) * coef[(size_t)gp * nloc_ + lf];
+                            }
+                            rhs[(size_t)ef * nloc_ + lf] = mw * (Chi_[(size_t)g * ne_ + e] / last_k_ * fis + sca);
+                        }
+                    }
+            int its = 0; double res = 0.0;
+            f.check(nf_schur_solve(f.ctx_, g, rhs.data(), phif.data() + (size_t)g * nphif, &its, &res), "nf_schur_solve");
+        }
+        std::vector<double> means((size_t)ng_ * nef);
+        for (int g = 0; g < ng_; ++g)
+            for (long long ef = 0; ef < nef; ++ef) means[(size_t)g * nef + ef] = phif[(size_t)g * nphif + ef * nloc_];
+        return shaped(means, true, r);
+    }
+
     // ---- accessors (src/NeutFEM.cpp:2626-2730)
     py::array_t<double> view(std::vector<double> &v, bool sigs, py::object owner)
     {
@@ -525,12 +629,6 @@ PYBIND11_MODULE(_neutfem_eigen, m)
           }, py::arg("dofs"), py::arg("nx"), py::arg("ny"), py::arg("nz"), py::arg("dim"), py::arg("p_order"), py::arg("refine"),
           "Host helper behind project_flux: sub-cell means of a tensor-Legendre expansion (element-major DOFs of one group)");
 
-    auto unimplemented = [](const char *name) {
-        return [name](NeutFEM &, const std::vector<int> &, bool) -> py::object {
-            throw std::runtime_error(std::string(name) + ": declared but never defined in the reference (include/NeutFEM.hpp:303-312); not provided");
-        };
-    };
-
     py::class_<NeutFEM>(m, "NeutFEM")
         .def(py::init([](int order, int ng, const darray &x, const darray &y, const darray &z) {
                  return std::make_unique<NeutFEM>(order, order, ng, to_vec(x), to_vec(y), to_vec(z));
@@ -601,5 +699,7 @@ PYBIND11_MODULE(_neutfem_eigen, m)
              "Exact sub-cell means of the polynomial flux on the mesh refined by [rx, ry, rz]; shape (ng[, nz*rz][, ny*ry], nx*rx)")
         .def("project_power", &NeutFEM::ProjectPower, py::arg("refine"), py::arg("adjoint") = false,
              "sum_g KSF_g * projected flux_g on the refined mesh; shape ([nz*rz][, ny*ry], nx*rx)")
-        .def("zoom_resolved", unimplemented("zoom_resolved"), py::arg("refine"), py::arg("adjoint") = false);
+        .def("zoom_resolved", &NeutFEM::ZoomResolved, py::arg("refine"), py::arg("adjoint") = false,
+             "Fixed-source re-solve on the mesh refined by [rx, ry, rz] with the sources frozen from the converged coarse flux; "
+             "returns the cell means, shape (ng[, nz*rz][, ny*ry], nx*rx)");
 }

@@ -83,7 +83,7 @@ def test_errors_are_runtime_errors():
     with pytest.raises(RuntimeError):
         s.SolveKeff()                # before BuildMatrices (solvers.cpp:204-207)
     with pytest.raises(RuntimeError):
-        s.zoom_resolved([2, 2, 1])   # declared, never defined in the reference; not provided here either
+        s.zoom_resolved([2, 2, 1])   # needs BuildMatrices + a converged SolveKeff first
 
 
 def test_project_flux_and_power_on_refined_mesh():
@@ -104,3 +104,22 @@ def test_project_flux_and_power_on_refined_mesh():
     ksf = np.repeat(np.repeat(np.asarray(s.get_KSF()), 3, axis=1), 2, axis=2)
     assert relerr(pw, (ksf * f).sum(axis=0)) < 1e-13
     assert s.project_flux([1, 1, 1], adjoint=True).shape == (p.ng, ny, nx)
+
+
+def test_zoom_resolved_reproduces_and_refines_the_coarse_solution():
+    """zoom_resolved (docstring semantics, parity unpinned): fixed-source re-solve on the refined mesh with the sources frozen
+    from the coarse flux. With refine [1,1,1] the frozen-source problem IS the converged coarse equation, so the coarse flux
+    comes back; with [2,2,1] the refined cell means average back to the coarse ones up to the discretisation error."""
+    p = bm.problem_2d("biblis2d", 1)
+    s = _script_style_solver(p, 1, 1)
+    s.set_mode("fast")
+    s.set_tol(1e-10, 1e-10, 1e-10, 800, 5000)
+    s.SolveKeff()
+    same = s.zoom_resolved([1, 1, 1])
+    assert same.shape == s.get_flux().shape
+    assert relerr(same, s.get_flux()) < 1e-6
+    fine = s.zoom_resolved([2, 2, 1])
+    ng, ny, nx = s.get_flux().shape
+    assert fine.shape == (ng, 2 * ny, 2 * nx)
+    back = fine.reshape(ng, ny, 2, nx, 2).mean(axis=(2, 4))
+    assert relerr(back, s.get_flux()) < 5e-2
