@@ -5,9 +5,9 @@
  * The reference (jujuC31/NeutFEM) has no FFI of its own for this path: its only boundary is the pybind11 module
  * `_neutfem_eigen` (reference src/wrapper.cpp:20-1065) over the C++ class `NeutFEM` (include/NeutFEM.hpp:170-510).
  * The entry points below are what a C++ (or ctypes/cgo/JNI) host would bind in place of the members of that
- * class that sit on the hot path; each one cites the member it replaces. The in-tree host class
- * (neutfem_b200/csrc/host/neutfem_host.cpp) and the pybind11 module (neutfem/_neutfem_eigen) are built on
- * exactly these calls; INTEGRATION.md shows the reference-side stub.
+ * class that sit on the hot path; each one cites the member it replaces. The in-tree pybind11 module
+ * neutfem/_neutfem_eigen (neutfem_b200/csrc/host/neutfem_module.cpp) is built on exactly these calls;
+ * INTEGRATION.md shows the reference-side stub.
  *
  * Conventions: plain pointers and sizes only; all arrays are caller-owned HOST buffers of IEEE fp64 in the
  * reference's layouts (group-major, element index e = iz*nx*ny + iy*nx + ix, flux DOF e*n_loc + local, current
@@ -126,9 +126,9 @@ NF_API int nf_get_diagonal_cache(nf_ctx *ctx, int g, double *s_inv);
 
 /* Average device time (ms) per launch of the hot-path kernels, CUDA events on the library's stream. ms_out holds 16
  * doubles: [0..2] x/y/z sweep, [3] CG update, [4] CG direction update and [8] one CG iteration of the
- * separate-kernel path; [6] forward kernel (k_plane_fwd / k_zfwd), [7] k_zback_update, [9] k_xrow, [10] k_ycol of the
- * 3-D single-GPU paths (else 0); [5] one CG iteration of the path the solver uses; [12] id of that path
- * (0 separate kernels, 1 plane-ordered fused, 2 hybrid, 3 rows). fast != 0 times the Jacobi-PCG variants.
+ * separate-kernel path; [6] k_zfwd, [7] k_zback_update (z-slab ranks: interface solve + back substitution + update),
+ * [9] k_xrow, [10] k_ycol of the 3-D paths (else 0); [5] one CG iteration of the path the solver uses; [12] id of that
+ * path (0 separate kernels, 2 hybrid, 3 rows, 5 rows on a z-slab rank). fast != 0 times the Jacobi-PCG variants.
  * Measurement hook for bench.py's roofline; no reference counterpart. */
 NF_API int nf_time_kernels(nf_ctx *ctx, int g, int reps, int fast, double *ms_out);
 

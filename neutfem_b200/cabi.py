@@ -234,7 +234,7 @@ class Context:
         out = np.zeros(16)
         self._ck(self._L.nf_time_kernels(self._h, int(g), int(reps), int(fast), _dp(out)), "nf_time_kernels")
         return dict(sweep_x=out[0], sweep_y=out[1], sweep_z=out[2], cg_update=out[3], cg_pupdate=out[4], cg_iteration=out[5],
-                    plane_fwd=out[6], zback_update=out[7], cg_iteration_separate=out[8], xrow=out[9], ycol=out[10],
+                    zfwd=out[6], zback_update=out[7], cg_iteration_separate=out[8], xrow=out[9], ycol=out[10],
                     path=out[12])
 
     def comm_init(self, id_bytes, rank, nranks):

@@ -548,10 +548,14 @@ public:
         }
         if (xs) {
             const std::pair<const char *, std::vector<double> *> tabs[] = {{"D_g", &D_}, {"SigmaR_g", &SigR_}, {"NuSigF_g", &NSF_},
-                                                                          {"Chi_g", &Chi_}, {"KappaSigF_g", &KSF_}};
+                                                                          {"Chi_g", &Chi_}, {"KappaSigF_g", &KSF_}, {"Source_g", &SRC_}};
             for (auto &t : tabs)
                 for (int g = 0; g < ng_; ++g)
                     scalars(std::string(t.first) + std::to_string(g), [&](long long e) { return (*t.second)[(size_t)g * ne_ + e]; });
+            for (int gf = 0; gf < ng_; ++gf)            // scattering matrices, offset rule GetSigSOffset (NeutFEM.hpp:365-367)
+                for (int gt = 0; gt < ng_; ++gt)
+                    scalars("SigS_" + std::to_string(gf) + "_to_" + std::to_string(gt),
+                            [&](long long e) { return SigS_[((size_t)gt * ng_ + gf) * ne_ + e]; });
         }
     }
 

@@ -70,14 +70,13 @@ struct nf_ctx {
     double *d_E = nullptr, *d_Eall = nullptr;      // [g][3][nxy], [g][nranks][3][nxy]
     double *d_vG = nullptr, *d_vGall = nullptr;    // [2][nt][nxy], [nranks][2][nt][nxy]
     double *d_lam = nullptr;                       // [2][nt][nxy] interface multipliers of this rank (fused slab update)
-    // ---- fused two-kernel CG iteration (nf_fused.cuh), 3-D single-GPU contexts
-    int fused = -1;                        // -1: not yet decided, 0: unavailable / disabled, 1: ready
-    int fLW = 4, fLcX = 1, fTS = 0, fPS = 0, fLcY = 1, fnX = 0, fnY = 0, fnitems = 0, fgrid = 0;
-    size_t fsmem = 0;
-    double *d_zs = nullptr, *d_W = nullptr, *d_fpart = nullptr;
+    // ---- CG-iteration path of 3-D contexts (nf_rows.cuh, nf_fused.cuh)
+    int fused = -1;                        // -1: not yet decided, 0: separate kernels, 2: hybrid, 3: rows, 5: rows on a z-slab rank
+    double *d_zs = nullptr;                // z-forward intermediates
     RowGeom rg; int xrow_grid = 0, ycol_grid = 0;   // register-resident x-row / y-column kernels (nf_rows.cuh)
-    int *d_fq = nullptr;                   // [0] queue head, [2] ticket, [4..4+nz) plane counters, then ny row counters
-    int2 *d_items = nullptr;
+    int zf_grid = 0, zb_grid = 0;          // whole waves of resident CTAs of the z marching kernels
+    cudaStream_t stream2 = nullptr;        // z-slab ranks: side stream (z forward substitution + all-gather beside the y columns)
+    cudaEvent_t evx = nullptr, evz = nullptr;
 };
 
 #define NC(ctx, call)                                                                                      \
@@ -208,14 +207,13 @@ static int launch_sweeps_t(nf_ctx *c, int g, const double *x, double *y, bool us
         Lc |= 1;                                   // odd chunk stride: conflict-free shared-memory columns
         a.Lc = Lc;
         const size_t smem = ((size_t)(5 + M1) * kXT * Lc + 2) * sizeof(double);
-        static size_t maxdyn = 0;          // opt-in dynamic shared memory of this instantiation (static part excluded)
-        if (maxdyn == 0) {
-            cudaFuncAttributes fa;
-            CU(c, cudaFuncGetAttributes(&fa, k_sweep_x<K, M1>));
-            const size_t lim = c->smem_optin - fa.sharedSizeBytes - 1024;
-            CU(c, cudaFuncSetAttribute(k_sweep_x<K, M1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lim));
-            maxdyn = lim;
-        }
+        // opt-in dynamic shared memory of this instantiation (static part excluded). The attribute is per DEVICE: it is set
+        // on every launch rather than cached per process (a process may hold contexts on several devices).
+        cudaFuncAttributes fa;
+        CU(c, cudaFuncGetAttributes(&fa, k_sweep_x<K, M1>));
+        const size_t maxdyn = c->smem_optin - fa.sharedSizeBytes - 1024;
+        if (smem > 48 * 1024 && smem <= maxdyn)
+            CU(c, cudaFuncSetAttribute(k_sweep_x<K, M1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)maxdyn));
         if (smem > maxdyn) NF_FAIL(c, NF_ERR_ARG, "nx=%d too large for the shared-memory line solver", c->nx);
         const long long nlines = (long long)c->ny * c->nz;
         const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(16, (c->smem_optin) / (smem + 1024)));
@@ -259,11 +257,8 @@ static int launch_sweeps_t(nf_ctx *c, int g, const double *x, double *y, bool us
         }
         const size_t zs = (size_t)(mg.n + 1) * 32 * sizeof(double) * WPB;
         if (zs <= 96 * 1024) {
-            static bool conf = false;
-            if (!conf) {
+            if (zs > 48 * 1024)
                 CU(c, cudaFuncSetAttribute(k_sweep_march<K, M1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-                conf = true;
-            }
             LAUNCH(c, (k_sweep_march<K, M1, true>), grid, WPB * 32, zs, a, mg);
         } else {
             const size_t need = zs * (size_t)grid;
@@ -297,30 +292,11 @@ static int apply_schur(nf_ctx *c, int g, const double *x, double *y, bool use_cg
 }
 
 
-// ---- fused two-kernel CG iteration (nf_fused.cuh) ---------------------------------------------------------------------
+// ---- CG-iteration paths of 3-D contexts ----------------------------------------------------------------------------------
 static int env_int(const char *name, int def)
 {
     const char *v = getenv(name);
     return (v && *v) ? atoi(v) : def;
-}
-
-template <int K, int M1, int LW>
-static int fused_prepare_t(nf_ctx *c, size_t smem, int *per_sm)
-{
-    CU(c, cudaFuncSetAttribute(k_plane_fwd<K, M1, LW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, k_plane_fwd<K, M1, LW>, kFT, smem));
-    return NF_OK;
-}
-
-template <int K, int M1>
-static int fused_prepare_lw(nf_ctx *c, size_t smem, int *per_sm)
-{
-    switch (c->fLW) {
-    case 2: return fused_prepare_t<K, M1, 2>(c, smem, per_sm);
-    case 4: return fused_prepare_t<K, M1, 4>(c, smem, per_sm);
-    case 8: return fused_prepare_t<K, M1, 8>(c, smem, per_sm);
-    }
-    NF_FAIL(c, NF_ERR_STATE, "fused path: unsupported y tile width %d", c->fLW);
 }
 
 #define NF_ORDER_SWITCH(c, CALL)                                              \
@@ -334,33 +310,35 @@ static int fused_prepare_lw(nf_ctx *c, size_t smem, int *per_sm)
     }                                                                         \
     NF_FAIL(c, NF_ERR_STATE, "unsupported order RT%d-P%d", (c)->K, (c)->M)
 
-static int fused_prepare(nf_ctx *c, size_t smem, int *per_sm)
-{
-#define CALL(KK, MM) fused_prepare_lw<KK, MM>(c, smem, per_sm)
-    NF_ORDER_SWITCH(c, CALL);
-#undef CALL
-}
-
 // ---- register-resident x-row / y-column kernels (nf_rows.cuh) ----------------------------------------------------------
-// Chunking of the lines: every thread owns <= kLC faces; the x lines use 8 / 16 / 32 lanes per (line, pair), the y lines
-// 8 / 16 / 32 chunks spread over the warps of a CTA. Returns false when a line is too long (> 32 * kLC - 1 cells).
+// Chunking of the lines: every thread owns 17 (lines of up to 543 cells) or 33 faces; an x line and pair takes 8 / 16 / 32
+// lanes, so a warp solves 4 / 2 / 1 pairs side by side; the y lines use 8 / 16 / 32 chunks spread over the warps of a CTA.
+// Returns false when a line is too long (> 32 * kLC - 1 cells) or nx is odd (the y columns go two at a time).
 static bool rows_geometry(const nf_ctx *c, RowGeom &g)
 {
     memset(&g, 0, sizeof(g));
     const int nfx = c->nx + 1;
     if (nfx > 32 * kLC || c->ny > 32 * 64) return false;
-    g.Cx = (nfx <= 8 * kLC) ? 8 : (nfx <= 16 * kLC ? 16 : 32);
-    g.LcX = (nfx + g.Cx - 1) / g.Cx;
-    g.PWx = 32 / g.Cx;
-    g.NFx = g.Cx * g.LcX;
+    if (c->nx & 1) return false;                  // the y columns are processed two at a time (16-byte vectors)
+    if (nfx <= 8 * kLCs) { g.PWx = 4; g.LcX = kLCs; }
+    else if (nfx <= 16 * kLCs) { g.PWx = 2; g.LcX = kLCs; }
+    else if (nfx <= 32 * kLCs) { g.PWx = 1; g.LcX = kLCs; }
+    else { g.PWx = 1; g.LcX = kLC; }
+    g.NFx = (32 / g.PWx) * g.LcX;
     int pp = g.NFx + 1;
-    while ((c->M1 * pp) % 16 != 8) ++pp;          // pair slots of a half-warp land in disjoint bank halves
+    while ((c->M1 * pp) % 16 != 8) ++pp;          // pair slots of a half-warp land in disjoint bank halves (pp comes out even)
     g.pitchP = pp;
     int pj = g.NFx + 2;
     while (pj % 16 != 8) ++pj;
     g.pitchJ = pj;
-    g.xsmemW = (2 * (g.NFx + 2) + g.PWx * c->M1 * g.pitchP + g.PWx * g.pitchJ + 1) & ~1;
-    if (c->nx & 1) return false;                  // the y columns are processed two at a time (16-byte vectors)
+    const int rows = g.PWx * c->M1;
+    g.offPO = 2 * (g.NFx + 2) + rows * g.pitchP;
+    const int po = std::max(rows * c->nx, g.PWx * g.pitchJ);
+    g.offJAC = g.offPO + ((po + 1) & ~1);
+    const int jacd = (rows * c->nx * (int)sizeof(jac_t) + 7) / 8;
+    g.offBAR = g.offJAC + ((jacd + 1) & ~1);
+    g.xsmemW = g.offBAR + 2;
+    g.bulk = (c->nx % 8 == 0) && env_int("NF_XROW_BULK", 1);
     g.Cy = (c->ny <= 8 * 16) ? 8 : (c->ny <= 16 * 16 ? 16 : 32);      // chunks of <= 16 cells where possible
     g.warpsY = kYT / 32;                          // (256-thread CTAs for the longest lines were measured slower)
     g.LcY = (c->ny + g.Cy - 1) / g.Cy;            // cells per chunk (the last chunk of a line also owns the top face)
@@ -368,14 +346,13 @@ static bool rows_geometry(const nf_ctx *c, RowGeom &g)
     return true;
 }
 
-// variants of the x-row code: cells per lane (8 / 16 / 33), all chunks full (no guards) or not. (A 32-lane x 17-face layout
-// for 265..512-cell lines -- 21 KB instead of 34 KB of shared memory per warp -- was measured: no gain.)
-#define NF_ROWS_VARIANTS(c, CALL)                                                                          \
-    do {                                                                                                   \
-        const int ncl_ = ((c)->nx + 31) / 32, lc_ = (c)->rg.LcX;                                           \
-        if (ncl_ <= 8) { if (lc_ == kLC) CALL(8, kLC, true); else CALL(8, kLC, false); }                   \
-        else if (ncl_ <= 16) { if (lc_ == kLC) CALL(16, kLC, true); else CALL(16, kLC, false); }           \
-        else CALL(33, kLC, false);                                                                         \
+// variants of the x-row code: (pairs per pass, cells per lane, faces per chunk)
+#define NF_ROWS_VARIANTS(c, CALL)                                                        \
+    do {                                                                                 \
+        if ((c)->rg.PWx == 4) CALL(4, 5, kLCs);                                          \
+        else if ((c)->rg.PWx == 2) CALL(2, 9, kLCs);                                     \
+        else if ((c)->rg.LcX == kLCs) CALL(1, 17, kLCs);                                 \
+        else CALL(1, 33, kLC);                                                           \
     } while (0)
 
 template <int K, int M1>
@@ -387,14 +364,16 @@ static int rows_prepare_t(nf_ctx *c)
     c->xrow_grid = 0;
     if (smem + 2048 > c->smem_optin || ysmem + 2048 > c->smem_optin) return NF_OK;
     int per_sm = 0;
-#define CALL(NCLV, LCTV, FULLV)                                                                                                            \
+#define CALL(PWV, NCLV, LCTV)                                                                                                              \
     do {                                                                                                                                   \
-        CU(c, cudaFuncSetAttribute(k_xrow<K, M1, NCLV, LCTV, FULLV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
-        CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_xrow<K, M1, NCLV, LCTV, FULLV>, 32 * kXW, smem));                  \
+        CU(c, cudaFuncSetAttribute(k_xrow<K, M1, PWV, NCLV, LCTV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
+        CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_xrow<K, M1, PWV, NCLV, LCTV, true>, 32 * kXW, smem));              \
     } while (0)
     NF_ROWS_VARIANTS(c, CALL);
 #undef CALL
     if (per_sm < 1) return NF_OK;
+    const int xcap = env_int("NF_XROW_CTAS", 0);
+    if (xcap > 0) per_sm = std::min(per_sm, xcap);
     const long long nrows = (long long)c->ny * c->nz;
     c->xrow_grid = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(kRedBlocks, (long long)per_sm * c->sm_count), (nrows + kXW - 1) / kXW));
     if (ynt == 128) {
@@ -406,6 +385,22 @@ static int rows_prepare_t(nf_ctx *c)
     }
     const long long nitems = (long long)c->nz * ((c->nx + c->rg.colsY - 1) / c->rg.colsY) * c->nt;
     c->ycol_grid = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(kRedBlocks, (long long)std::max(per_sm, 1) * c->sm_count), nitems));
+    // the z marching kernels are persistent grid-stride loops: whole waves of resident CTAs only (no ragged last wave)
+    int occ_zf = 0, occ_zb = 0;
+    if (c->slab) {
+        CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_zf, k_zfwd<K, M1, true>, 128, 0));
+        CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_zb, k_slab_back_update<K, M1>, 128, 0));
+    } else {
+        CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_zf, k_zfwd<K, M1, false>, 128, 0));
+        CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_zb, k_zback_update<K, M1, true>, 128, 0));
+    }
+    const long long zitems = (long long)c->ny * c->nt * ((c->nx + 31) / 32);
+    auto wave_grid = [&](int occ) {
+        occ = std::max(occ, 1);
+        const int waves = std::max(1, kRedBlocks / (occ * c->sm_count));
+        return (int)std::max<long long>(1, std::min<long long>((long long)waves * occ * c->sm_count, (zitems + 3) / 4));
+    };
+    c->zf_grid = wave_grid(occ_zf); c->zb_grid = wave_grid(occ_zb);
     return NF_OK;
 }
 
@@ -416,14 +411,14 @@ static int rows_prepare(nf_ctx *c)
 #undef CALL
 }
 
-// which: bit 0 = k_xrow (direction update + x part), bit 1 = k_ycol (y part)
+// which: bit 0 = k_xrow (solution + direction update + x part), bit 1 = k_ycol (y part)
 template <int K, int M1>
 static int rows_launch_t(nf_ctx *c, const FusedArgs &a, int which)
 {
     if (which & 1) {
         const size_t smem = (size_t)kXW * c->rg.xsmemW * sizeof(double);
         double *part = c->d_part + (size_t)0 * kRedBlocks;
-#define CALL(NCLV, LCTV, FULLV) LAUNCH(c, (k_xrow<K, M1, NCLV, LCTV, FULLV>), c->xrow_grid, 32 * kXW, smem, a, c->rg, part, c->d_ticket + 0, &c->d_cg->pAp[0])
+#define CALL(PWV, NCLV, LCTV) LAUNCH(c, (k_xrow<K, M1, PWV, NCLV, LCTV, true>), c->xrow_grid, 32 * kXW, smem, a, c->rg, part, c->d_ticket + 0, &c->d_cg->pAp[0])
         NF_ROWS_VARIANTS(c, CALL);
 #undef CALL
     }
@@ -444,31 +439,36 @@ static int rows_launch(nf_ctx *c, const FusedArgs &a, int which)
 #undef CALL
 }
 
-
-// Decide once per context whether the fused path applies (3-D, single GPU, lines fit in shared memory) and build its
-// work-item queue: round r holds the X items of plane r and the Y items of plane r-delay, the Y items starting `lag`
-// X items into the round so that they (almost) never find their plane incomplete.
+// Decide once per context which CG-iteration path applies. NF_FUSED (development / test knob): unset = rows path (3) with
+// the hybrid path (2) as fallback for odd nx or very long lines; 0 = separate kernels, 2 = hybrid, 3 = rows.
 static int fused_setup(nf_ctx *c)
 {
     if (c->fused >= 0) return NF_OK;
     c->fused = 0;
-    // NF_FUSED selects the CG-iteration path of 3-D single-GPU contexts (development / test knob): unset = rows path (3)
-    // with the hybrid path (2) as fallback; 0 = separate kernels, 1 = plane-ordered fused kernel, 2 = hybrid, 3 = rows.
     const bool auto_mode = (getenv("NF_FUSED") == nullptr || !*getenv("NF_FUSED"));
     int want_mode = auto_mode ? 3 : env_int("NF_FUSED", 3);
     if (c->dim != 3 || want_mode == 0) return NF_OK;
-    if (c->slab) {                        // z-slab ranks: the x rows / y columns are slab-local, the z sweep stays substructured
+    const size_t nxy2 = (size_t)c->nx * c->ny;
+    if (c->slab) {                        // z-slab ranks: the x rows / y columns are slab-local, the z sweep is substructured
         if ((auto_mode || want_mode == 3) && rows_geometry(c, c->rg)) {
             { int r = rows_prepare(c); if (r) return r; }
-            if (c->xrow_grid > 0) c->fused = 5;
+            if (c->xrow_grid > 0) {
+                { int r = dalloc(c, &c->d_zs, (size_t)(c->nz + 1) * c->nt * nxy2); if (r) return r; }
+                if (!c->d_lam) { int r = dalloc(c, &c->d_lam, (size_t)2 * c->nt * c->nxy); if (r) return r; }
+                if (env_int("NF_SLAB_OVERLAP", 1)) {
+                    CU(c, cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+                    CU(c, cudaEventCreateWithFlags(&c->evx, cudaEventDisableTiming));
+                    CU(c, cudaEventCreateWithFlags(&c->evz, cudaEventDisableTiming));
+                }
+                c->fused = 5;
+            }
         }
         return NF_OK;
     }
-    if (want_mode == 3) {                 // rows: k_xrow (direction update + x) + k_ycol + k_zfwd + k_zback_update
+    if (want_mode == 3) {                 // rows: k_xrow (updates + x) + k_ycol + k_zfwd + k_zback_update
         if (rows_geometry(c, c->rg)) {
             { int r = rows_prepare(c); if (r) return r; }
             if (c->xrow_grid > 0) {
-                const size_t nxy2 = (size_t)c->nx * c->ny;
                 { int r = dalloc(c, &c->d_zs, (size_t)(c->nz + 1) * c->nt * nxy2); if (r) return r; }
                 c->fused = 3;
                 return NF_OK;
@@ -478,60 +478,11 @@ static int fused_setup(nf_ctx *c)
         want_mode = 2;
     }
     if (want_mode == 2) {                 // hybrid: separate x / y sweeps + k_zfwd + k_zback_update
-        const size_t nxy2 = (size_t)c->nx * c->ny;
         { int r = dalloc(c, &c->d_zs, (size_t)(c->nz + 1) * c->nt * nxy2); if (r) return r; }
+        c->zf_grid = c->zb_grid = 0;
         c->fused = 2;
         return NF_OK;
     }
-    int LW = env_int("NF_FUSED_LW", 4);
-    if (LW != 2 && LW != 4 && LW != 8) LW = 4;
-    c->fLW = LW;
-    const int GX = (c->M1 == 1) ? 1 : 4;           // transverse pairs of an x line solved side by side
-    c->fLcX = ((c->nx + 1 + kFT / GX - 1) / (kFT / GX)) | 1;
-    c->fLcY = ((c->ny + 1 + kFT / LW - 1) / (kFT / LW)) | 1;
-    c->fTS = (c->nx + 3) & ~1;
-    c->fPS = (c->nx + 1) & ~1;
-    const size_t smemX = ((size_t)(2 + GX) * c->fTS + (size_t)(3 + c->nloc) * c->fPS) * sizeof(double);
-    const size_t smemY = (size_t)4 * (c->ny + 2) * LW * sizeof(double);
-    const size_t smem = (std::max(smemX, smemY) + 15) & ~(size_t)15;
-    if (smem + 4096 > c->smem_optin) return NF_OK;               // lines too long for shared memory: separate kernels
-    int per_sm = 0;
-    { int r = fused_prepare(c, smem, &per_sm); if (r) return r; }
-    if (per_sm < 1) return NF_OK;
-    const int want = env_int("NF_FUSED_CTAS", 0);
-    if (want > 0) per_sm = std::min(per_sm, want);
-    c->fsmem = smem;
-    c->fgrid = per_sm * c->sm_count;
-    const int nX = c->ny, nY = ((c->nx + LW - 1) / LW) * c->nt, nz = c->nz;
-    c->fnX = nX; c->fnY = nY;
-    const int delay = env_int("NF_FUSED_DELAY", 1) ? 1 : 0;
-    int lag = env_int("NF_FUSED_LAG", nX / 2);
-    lag = std::max(0, std::min(lag, nX));
-    std::vector<int2> items;
-    items.reserve((size_t)nz * (nX + nY));
-    for (int r = 0; r < nz + delay; ++r) {
-        const int xs = (r < nz) ? nX : 0, yp = r - delay, ys = (yp >= 0 && yp < nz) ? nY : 0;
-        const int first = delay ? std::min(lag, xs) : xs;
-        int xi = 0, yi = 0;
-        for (; xi < first; ++xi) items.push_back(make_int2(r * 2, xi));
-        const int remx = xs - first;
-        while (xi < xs || yi < ys) {         // proportional merge of the remaining X items with the Y items
-            const bool takeY = (yi < ys) && (xi >= xs || (long long)yi * remx <= (long long)(xi - first) * ys);
-            if (takeY) { items.push_back(make_int2(yp * 2 + 1, yi)); ++yi; }
-            else { items.push_back(make_int2(r * 2, xi)); ++xi; }
-        }
-    }
-    c->fnitems = (int)items.size();
-    const size_t nxy = (size_t)c->nx * c->ny;
-    { int r = dalloc(c, &c->d_zs, (size_t)(nz + 1) * c->nt * nxy); if (r) return r; }
-    { int r = dalloc(c, &c->d_W, (size_t)2 * c->nt * nxy); if (r) return r; }
-    { int r = dalloc(c, &c->d_fpart, (size_t)c->fnitems); if (r) return r; }
-    { int r = dalloc(c, &c->d_fq, (size_t)nz + c->ny + 8); if (r) return r; }
-    { int r = dalloc(c, &c->d_items, items.size()); if (r) return r; }
-    CU(c, cudaMemsetAsync(c->d_fq, 0, ((size_t)nz + c->ny + 8) * sizeof(int), c->stream));
-    CU(c, cudaMemcpyAsync(c->d_items, items.data(), items.size() * sizeof(int2), cudaMemcpyHostToDevice, c->stream));
-    CU(c, cudaStreamSynchronize(c->stream));
-    c->fused = 1;
     return NF_OK;
 }
 
@@ -544,15 +495,12 @@ static void fill_fused_args(nf_ctx *c, FusedArgs &a, int g, double *x, const jac
         a.Fy[d] = c->d_F[d][1]; a.Fz[d] = c->d_F[d][2]; a.iFx[d] = c->d_iFx[d];
     }
     a.D = c->d_D + (size_t)g * c->ne; a.SigR = c->d_SigR + (size_t)g * c->ne; a.vol = c->d_vol;
-    a.zs = c->d_zs; a.W = c->d_W; a.st = c->d_cg;
-    a.qhead = c->d_fq; a.err = &c->d_cg->pad; a.ticket = (unsigned *)(c->d_fq + 2); a.xdone = c->d_fq + 4;
-    a.rowdone = c->d_fq + 4 + c->nz;
-    a.items = c->d_items; a.part = c->d_fpart;
+    a.zs = c->d_zs; a.st = c->d_cg;
+    if (c->slab) { a.s0 = c->d_s0[g]; a.vG = c->d_vG; }
     a.red_part = c->d_part + (size_t)4 * kRedBlocks; a.ticket2 = c->d_ticket + 4;
-    a.ne = c->ne; a.nxy = (long long)c->nx * c->ny; a.nitems = c->fnitems;
+    a.ne = c->ne; a.nxy = (long long)c->nx * c->ny;
     a.nx = c->nx; a.ny = c->ny; a.nz = c->nz; a.nt = c->nt; a.nloc = c->nloc;
-    a.LcX = c->fLcX; a.TS = c->fTS; a.PS = c->fPS; a.LcY = c->fLcY; a.nX = c->fnX; a.nY = c->fnY;
-    a.pcg = jac ? 1 : 0; a.fin = 1;
+    a.pcg = jac ? 1 : 0; a.fin = c->slab ? 0 : 1;
     for (int d = 0; d < 3; ++d)
         for (int t = 0; t < c->nt; ++t)
             for (int p = 0; p < c->M1; ++p) a.mode[d][t][p] = c->tmode[d][t][p];
@@ -561,99 +509,85 @@ static void fill_fused_args(nf_ctx *c, FusedArgs &a, int g, double *x, const jac
     memcpy(a.cb, c->cb, sizeof(a.cb));
 }
 
-// which: bit 0 = k_plane_fwd (direction update + x, y sweeps + z forward), bit 1 = k_zback_update
+// which: bit 2 = k_zfwd, bit 1 = k_zback_update (defer: the x update is left to the next k_xrow)
 template <int K, int M1>
-static int fused_launch_t(nf_ctx *c, const FusedArgs &a, int which)
+static int fused_launch_t(nf_ctx *c, const FusedArgs &a, int which, bool defer)
 {
-    if (which & 1) {
-        switch (c->fLW) {
-        case 2: LAUNCH(c, (k_plane_fwd<K, M1, 2>), c->fgrid, kFT, c->fsmem, a); break;
-        case 4: LAUNCH(c, (k_plane_fwd<K, M1, 4>), c->fgrid, kFT, c->fsmem, a); break;
-        case 8: LAUNCH(c, (k_plane_fwd<K, M1, 8>), c->fgrid, kFT, c->fsmem, a); break;
-        }
+    if (!c->zf_grid) {      // hybrid path: grids of whole waves, per context (the occupancy depends on the device)
+        int occ_zf = 0, occ_zb = 0;
+        CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_zf, k_zfwd<K, M1, false>, 128, 0));
+        CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_zb, k_zback_update<K, M1, false>, 128, 0));
+        const long long zitems = (long long)c->ny * c->nt * ((c->nx + 31) / 32);
+        auto wave_grid = [&](int occ) {
+            occ = std::max(occ, 1);
+            const int waves = std::max(1, kRedBlocks / (occ * c->sm_count));
+            return (int)std::max<long long>(1, std::min<long long>((long long)waves * occ * c->sm_count, (zitems + 3) / 4));
+        };
+        c->zf_grid = wave_grid(occ_zf); c->zb_grid = wave_grid(occ_zb);
     }
-    // the marching kernels are persistent grid-stride loops: whole waves of resident CTAs only (no ragged last wave)
-    static int occ_zf = 0, occ_zb = 0;
-    if (!occ_zf) {
-        CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_zf, k_zfwd<K, M1>, 128, 0));
-        CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_zb, k_zback_update<K, M1>, 128, 0));
-        occ_zf = std::max(occ_zf, 1); occ_zb = std::max(occ_zb, 1);
-    }
-    if (which & 4) {
-        const long long nitems = (long long)c->ny * c->nt * ((c->nx + 31) / 32);
-        const int waves = std::max(1, kRedBlocks / (occ_zf * c->sm_count));
-        const int grid = (int)std::max<long long>(1, std::min<long long>((long long)waves * occ_zf * c->sm_count, (nitems + 3) / 4));
-        LAUNCH(c, (k_zfwd<K, M1>), grid, 128, 0, a, c->d_part + (size_t)2 * kRedBlocks, c->d_ticket + 2, &c->d_cg->pAp[2]);
-    }
+    if (which & 4)
+        LAUNCH(c, (k_zfwd<K, M1, false>), c->zf_grid, 128, 0, a, c->d_part + (size_t)2 * kRedBlocks, c->d_ticket + 2, &c->d_cg->pAp[2]);
     if (which & 2) {
-        const long long nitems = (long long)c->ny * c->nt * ((c->nx + 31) / 32);
-        const int waves = std::max(1, kRedBlocks / (occ_zb * c->sm_count));
-        const int grid = (int)std::max<long long>(1, std::min<long long>((long long)waves * occ_zb * c->sm_count, (nitems + 3) / 4));
-        LAUNCH(c, (k_zback_update<K, M1>), grid, 128, 0, a);
+        if (defer) LAUNCH(c, (k_zback_update<K, M1, true>), c->zb_grid, 128, 0, a);
+        else LAUNCH(c, (k_zback_update<K, M1, false>), c->zb_grid, 128, 0, a);
     }
     CU(c, cudaGetLastError());
     return NF_OK;
 }
 
-static int fused_launch(nf_ctx *c, const FusedArgs &a, int which)
+static int fused_launch(nf_ctx *c, const FusedArgs &a, int which, bool defer)
 {
-#define CALL(KK, MM) fused_launch_t<KK, MM>(c, a, which)
+#define CALL(KK, MM) fused_launch_t<KK, MM>(c, a, which, defer)
     NF_ORDER_SWITCH(c, CALL);
 #undef CALL
 }
 
-// z-slab ranks, second half of a CG iteration: local z forward substitution | all-gather of the interface values |
-// interface solve (+ its share of p^T S p) | all-reduce of p^T S p | z back substitution fused with the x / r update |
-// all-reduce of the new residual norms | scalar recurrences. x rows and y columns (rows_launch) must have run before.
+// z-slab ranks, one CG iteration after the direction update: x rows | y columns, and beside them on a second stream the
+// local z forward substitution | all-gather of the interface values (both only need p); then interface solve (+ its share of
+// p^T S p) | all-reduce of p^T S p | z back substitution fused with the r update | all-reduce of the new residual norms |
+// scalar recurrences. which: 1 = x rows, 2 = y columns, 4 = z forward + all-gather, 8 = interface + back substitution + update.
 template <int K, int M1>
-static int slab_zupdate_t(nf_ctx *c, int g, double *x, const jac_t *jac, double tol)
+static int slab_iteration_t(nf_ctx *c, const FusedArgs &fa, int g, double tol, int which)
 {
-    SweepArgs a;
-    fill_sweep_args(c, a, g, 2, c->d_p, c->d_Ap, true);
-    MarchGeom mg;
-    mg.n = c->nz; mg.north = c->ny; mg.stride = (long long)c->nx * c->ny;
-    mg.ostride_cell = c->nx; mg.ostride_face = c->nx;
-    const int WPB = 4;
-    const long long nitems = (long long)mg.north * c->nt * ((c->nx + 31) / 32);
-    static int occ_f = 0, occ_b = 0;
-    if (!occ_f) {
-        CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, k_march_slab_fwd<K, M1>, WPB * 32, 0));
-        CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, k_slab_back_update<K, M1>, WPB * 32, 0));
-        occ_f = std::max(occ_f, 1); occ_b = std::max(occ_b, 1);
+    const bool overlap = c->stream2 != nullptr && (which & 7) == 7;
+    if (which & 1) { int r = rows_launch_t<K, M1>(c, fa, 1); if (r) return r; }
+    cudaStream_t zs = c->stream;
+    if (overlap) {
+        CU(c, cudaEventRecord(c->evx, c->stream));
+        CU(c, cudaStreamWaitEvent(c->stream2, c->evx, 0));
+        zs = c->stream2;
+    } else if (which & 2) { int r = rows_launch_t<K, M1>(c, fa, 2); if (r) return r; }
+    if (which & 4) {
+        k_zfwd<K, M1, true><<<c->zf_grid, 128, 0, zs>>>(fa, c->d_part + (size_t)2 * kRedBlocks, c->d_ticket + 2, &c->d_cg->pAp[2]);
+        ++g_launches; ++c->launches_call;
+        NC(c, ncclAllGather(c->d_vG, c->d_vGall, (size_t)2 * c->nt * c->nxy, ncclDouble, c->comm, zs));
     }
-    auto wave_grid = [&](int occ) {
-        const int waves = std::max(1, kRedBlocks / (occ * c->sm_count));
-        return (int)std::max<long long>(1, std::min<long long>((long long)waves * occ * c->sm_count, (nitems + WPB - 1) / WPB));
-    };
-    const size_t need = (size_t)nitems * (mg.n + 1) * 32 * sizeof(double);
-    if (need > c->zscratch_bytes) {
-        CU(c, cudaStreamSynchronize(c->stream));
-        if (c->d_zscratch) cudaFree(c->d_zscratch);
-        c->d_zscratch = nullptr; c->zscratch_bytes = 0;
-        CU(c, cudaMalloc((void **)&c->d_zscratch, need));
-        c->zscratch_bytes = need;
+    if (overlap) {
+        CU(c, cudaEventRecord(c->evz, c->stream2));
+        { int r = rows_launch_t<K, M1>(c, fa, 2); if (r) return r; }
+        CU(c, cudaStreamWaitEvent(c->stream, c->evz, 0));
     }
-    if (!c->d_lam) { int r = dalloc(c, &c->d_lam, (size_t)2 * c->nt * c->nxy); if (r) return r; }
-    a.zscratch = c->d_zscratch;
-    LAUNCH(c, (k_march_slab_fwd<K, M1>), wave_grid(occ_f), WPB * 32, 0, a, mg);
-    NC(c, ncclAllGather(c->d_vG, c->d_vGall, (size_t)2 * c->nt * c->nxy, ncclDouble, c->comm, c->stream));
-    SlabUpd u;
-    u.p = c->d_p; u.yp = c->d_Ap; u.x = x; u.r = c->d_r; u.jac = jac; u.lam = c->d_lam; u.st = c->d_cg;
-    u.red_part = c->d_part + (size_t)4 * kRedBlocks; u.ticket = c->d_ticket + 4; u.pcg = jac ? 1 : 0;
-    a.red_out = &c->d_cg->pAp[3];
-    a.red_part = c->d_part + (size_t)3 * kRedBlocks; a.ticket = c->d_ticket + 3;
-    LAUNCH(c, (k_slab_iface<K, M1>), (int)std::max<long long>(1, std::min<long long>(kRedBlocks, (c->nxy * c->nt + 127) / 128)), 128, 0, a, u);
-    { int r = allreduce_sum(c, c->d_cg->pAp, 4); if (r) return r; }
-    LAUNCH(c, (k_slab_back_update<K, M1>), wave_grid(occ_b), WPB * 32, 0, a, mg, u);
-    { int r = allreduce_sum(c, c->d_cg->tmp, 2); if (r) return r; }
-    LAUNCH(c, k_cg_finalize, 1, 1, 0, c->d_cg, 1, tol, jac ? 1 : 0);
+    if (which & 8) {
+        SweepArgs a;
+        fill_sweep_args(c, a, g, 2, c->d_p, c->d_Ap, true);
+        SlabUpd u;
+        u.lam = c->d_lam; u.st = c->d_cg;
+        u.red_part = c->d_part + (size_t)4 * kRedBlocks; u.ticket = c->d_ticket + 4; u.pcg = fa.pcg;
+        a.red_out = &c->d_cg->pAp[3];
+        a.red_part = c->d_part + (size_t)3 * kRedBlocks; a.ticket = c->d_ticket + 3;
+        LAUNCH(c, (k_slab_iface<K, M1>), (int)std::max<long long>(1, std::min<long long>(kRedBlocks, (c->nxy * c->nt + 127) / 128)), 128, 0, a, u);
+        { int r = allreduce_sum(c, c->d_cg->pAp, 4); if (r) return r; }
+        LAUNCH(c, (k_slab_back_update<K, M1>), c->zb_grid, 128, 0, fa, u);
+        { int r = allreduce_sum(c, c->d_cg->tmp, 2); if (r) return r; }
+        LAUNCH(c, k_cg_finalize, 1, 1, 0, c->d_cg, 1, tol, fa.pcg, 1);
+    }
     CU(c, cudaGetLastError());
     return NF_OK;
 }
 
-static int slab_zupdate(nf_ctx *c, int g, double *x, const jac_t *jac, double tol)
+static int slab_iteration(nf_ctx *c, const FusedArgs &fa, int g, double tol, int which)
 {
-#define CALL(KK, MM) slab_zupdate_t<KK, MM>(c, g, x, jac, tol)
+#define CALL(KK, MM) slab_iteration_t<KK, MM>(c, fa, g, tol, which)
     NF_ORDER_SWITCH(c, CALL);
 #undef CALL
 }
@@ -706,7 +640,7 @@ static int create_impl(nf_ctx **out, int rt_order, int p_order, int ng, const do
         return NF_ERR_NODEVICE;
     }
     nf_ctx *c = new nf_ctx();
-    auto fail = [&](int code) { g_create_error = c->err; delete c; return code; };
+    auto fail = [&](int code) { g_create_error = c->err; nf_destroy(c); return code; };
     if (device >= 0) { if (cudaSetDevice(device) != cudaSuccess) { c->err = "cudaSetDevice failed"; return fail(NF_ERR_CUDA); } }
     cudaGetDevice(&c->dev);
     cudaDeviceProp prop;
@@ -873,9 +807,9 @@ int nf_destroy(nf_ctx *c)
     for (int d = 0; d < 3; ++d) for (int ax = 0; ax < 3; ++ax) if (c->d_F[d][ax]) cudaFree(c->d_F[d][ax]);
     for (int d = 0; d < 3; ++d) if (c->d_iFx[d]) cudaFree(c->d_iFx[d]);
     for (double *p : c->d_s0) if (p) cudaFree(p);
-    for (double *p : {c->d_E, c->d_Eall, c->d_vG, c->d_vGall, c->d_lam, c->d_zs, c->d_W, c->d_fpart}) if (p) cudaFree(p);
-    if (c->d_fq) cudaFree(c->d_fq);
-    if (c->d_items) cudaFree(c->d_items);
+    for (double *p : {c->d_E, c->d_Eall, c->d_vG, c->d_vGall, c->d_lam, c->d_zs}) if (p) cudaFree(p);
+    if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
+    for (cudaEvent_t e : {c->evx, c->evz}) if (e) cudaEventDestroy(e);
     if (c->comm) ncclCommDestroy(c->comm);
     for (double *p : c->d_minv) if (p) cudaFree(p);
     for (double *p : c->d_u_base) if (p) cudaFree(p);
@@ -1091,11 +1025,14 @@ int nf_get_last_keff(const nf_ctx *c, double *keff, double *keff_adj, int *has_v
 static int solve_group(nf_ctx *c, int g, const double *b, double *x, int *iters_out, double *res_out, nf_stats *st)
 {
     const long long n = c->nphi;
+    // every decision that changes the sequence of collectives must be the same on all ranks of a z-slab job: derive it from
+    // the GLOBAL problem size (slabs may be uneven)
+    const long long n_glob = c->slab ? (c->nphi / c->nz) * (long long)c->nz_global : c->nphi;
     const int blocks = ew_blocks(n);
     double tol = c->inner_tol; int maxit = c->inner_max;
-    const bool direct = (c->solver_type <= NF_DIRECT_LLT) || (c->nphi < 200);
+    const bool direct = (c->solver_type <= NF_DIRECT_LLT) || (n_glob < 200);
     const bool fast = (c->mode == NF_MODE_FAST);
-    if (direct) { tol = std::min(tol, 1e-13); maxit = std::max(maxit, (int)std::min<long long>(20000, 4 * n + 100)); }
+    if (direct) { tol = std::min(tol, 1e-13); maxit = std::max(maxit, (int)std::min<long long>(20000, 4 * n_glob + 100)); }
     if (fast || direct) { int r = build_jacobi(c); if (r) return r; }
     const bool pcg = fast || direct;
     const int fin = c->slab ? 0 : 1;        // scalar recurrences inside the reducing kernel unless ranks must be summed first
@@ -1111,40 +1048,34 @@ static int solve_group(nf_ctx *c, int g, const double *b, double *x, int *iters_
     }
     if (!fin) {
         { int r = allreduce_sum(c, c->d_cg->tmp, 3); if (r) return r; }
-        LAUNCH(c, k_cg_finalize, 1, 1, 0, c->d_cg, 0, tol, pcg ? 1 : 0);
+        LAUNCH(c, k_cg_finalize, 1, 1, 0, c->d_cg, 0, tol, pcg ? 1 : 0, 0);
     }
     { int r = fused_setup(c); if (r) return r; }
-    const bool fused = (c->fused == 1), hybrid = (c->fused == 2), rows = (c->fused == 3), slabrows = (c->fused == 5);
+    const bool hybrid = (c->fused == 2), rows = (c->fused == 3), slabrows = (c->fused == 5);
     FusedArgs fa;
-    if (fused || hybrid || rows || slabrows) fill_fused_args(c, fa, g, x, jac);
+    if (hybrid || rows || slabrows) fill_fused_args(c, fa, g, x, jac);
     // poll the device-side done flag every few iterations; iterations after convergence are no-ops on the device
-    const double est_us = (double)n * 160.0 / 6.0e6 + 15.0;
+    const double est_us = (double)n_glob / std::max(1, c->nranks) * 160.0 / 6.0e6 + 15.0;
     int poll = (int)std::max(1.0, std::min(16.0, 200.0 / est_us));
     int k = 0;
     bool done = false;
     while (k < maxit && !done) {
         const int chunk = std::min(poll, maxit - k);
         for (int j = 0; j < chunk; ++j) {
-            if (fused) {          // two kernels: direction update + forward sweeps | z back substitution + update
-                int r = fused_launch(c, fa, 3);
-                if (r) return r;
+            if (rows) {           // solution + direction update + x rows | y columns | z forward | z back + residual update
+                { int r = rows_launch(c, fa, 3); if (r) return r; }
+                { int r = fused_launch(c, fa, 4 | 2, true); if (r) return r; }
                 continue;
             }
-            if (rows) {           // direction update + x rows | y columns | z forward | z back + update
-                { int r = rows_launch(c, fa, 3); if (r) return r; }
-                { int r = fused_launch(c, fa, 4 | 2); if (r) return r; }
-                continue;
-            }
-            if (slabrows) {       // z-slab rank: x rows (direction update fused) | y columns | substructured z sweep fused with the update
-                { int r = rows_launch(c, fa, 3); if (r) return r; }
-                { int r = slab_zupdate(c, g, x, jac, tol); if (r) return r; }
+            if (slabrows) {       // z-slab rank: the same x rows / y columns, substructured z sweep fused with the update
+                { int r = slab_iteration(c, fa, g, tol, 15); if (r) return r; }
                 continue;
             }
             if (hybrid) {         // direction update, x and y sweeps as separate kernels, then z forward | z back + update
                 if (!pcg) LAUNCH(c, k_cg_pupdate, blocks, 256, 0, c->d_r, c->d_p, n, c->d_cg);
                 else LAUNCH(c, k_pcg_pupdate, blocks, 256, 0, c->d_r, jac, c->d_p, n, c->d_cg);
                 { int r = apply_schur(c, g, c->d_p, c->d_Ap, true, 3); if (r) return r; }
-                { int r = fused_launch(c, fa, 4 | 2); if (r) return r; }
+                { int r = fused_launch(c, fa, 4 | 2, false); if (r) return r; }
                 continue;
             }
             { int r = apply_schur(c, g, c->d_p, c->d_Ap, true); if (r) return r; }
@@ -1153,7 +1084,7 @@ static int solve_group(nf_ctx *c, int g, const double *b, double *x, int *iters_
             else LAUNCH(c, k_pcg_update, blocks, 256, 0, c->d_p, c->d_Ap, jac, x, c->d_r, n, c->d_cg, c->d_part + 4 * kRedBlocks, c->d_ticket + 4, fin);
             if (!fin) {
                 { int r = allreduce_sum(c, c->d_cg->tmp, 2); if (r) return r; }
-                LAUNCH(c, k_cg_finalize, 1, 1, 0, c->d_cg, 1, tol, pcg ? 1 : 0);
+                LAUNCH(c, k_cg_finalize, 1, 1, 0, c->d_cg, 1, tol, pcg ? 1 : 0, 0);
             }
             if (!pcg) LAUNCH(c, k_cg_pupdate, blocks, 256, 0, c->d_r, c->d_p, n, c->d_cg);
             else LAUNCH(c, k_pcg_pupdate, blocks, 256, 0, c->d_r, jac, c->d_p, n, c->d_cg);
@@ -1163,15 +1094,12 @@ static int solve_group(nf_ctx *c, int g, const double *b, double *x, int *iters_
         CU(c, cudaStreamSynchronize(c->stream));
         done = c->h_cg->done != 0;
     }
-    if (!done) {   // max_iter reached: freeze further no-op semantics
-        CU(c, cudaMemcpyAsync(c->h_cg, c->d_cg, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
-        CU(c, cudaStreamSynchronize(c->stream));
-    }
+    // rows paths: the x update of the last iteration is still pending (x += alpha_prev p)
+    if (rows || slabrows) LAUNCH(c, k_x_pending, blocks, 256, 0, x, c->d_p, n, c->d_cg);
     CU(c, cudaEventRecord(c->ev3, c->stream));
     CU(c, cudaEventSynchronize(c->ev3));
     float ms = 0.f;
     cudaEventElapsedTime(&ms, c->ev2, c->ev3);
-    if (c->h_cg->pad) NF_FAIL(c, NF_ERR_STATE, "fused CG kernel: a work-item dependency timed out (internal error)");
     const int iters = c->h_cg->iters;
     const double res = (c->h_cg->bnorm_sq > 0) ? std::sqrt(c->h_cg->rr_true / c->h_cg->bnorm_sq) : 0.0;
     if (iters_out) *iters_out = iters;
@@ -1483,10 +1411,10 @@ int nf_time_kernels(nf_ctx *c, int g, int reps, int fast, double *ms_out)
 {
     // Average device time per launch of each hot-path kernel, CUDA events on the context stream, operands resident
     // in HBM. ms_out[0..2] = x / y / z sweep, [3] = CG update, [4] = CG direction update of the separate-kernel
-    // path, [8] = one CG iteration of that path (five launches); [6] = k_plane_fwd, [7] = k_zback_update of the fused
-    // path (0 if it does not apply), [5] = one CG iteration of the path the solver really uses, [9] = k_xrow,
-    // [10] = k_ycol of the rows path, [12] = id of the path in use. ms_out holds 16 doubles. Destroys the CG work
-    // vectors, not the flux.
+    // path, [8] = one CG iteration of that path (five launches); [6] = k_zfwd, [7] = k_zback_update (z-slab ranks: the
+    // whole substructured z phase), [9] = k_xrow, [10] = k_ycol of the rows paths (0 if they do not apply), [5] = one CG
+    // iteration of the path the solver really uses, [12] = id of that path. ms_out holds 16 doubles. Destroys the CG
+    // work vectors, not the flux.
     if (!c || !ms_out || g < 0 || g >= c->ng || reps < 1) return NF_ERR_ARG;
     if (!c->built) NF_FAIL(c, NF_ERR_STATE, "nf_time_kernels: call nf_build first");
     CU(c, cudaSetDevice(c->dev));
@@ -1497,7 +1425,7 @@ int nf_time_kernels(nf_ctx *c, int g, int reps, int fast, double *ms_out)
     LAUNCH(c, k_fill, blocks, 256, 0, c->d_rhs, n, 1.0);
     const int fin = c->slab ? 0 : 1;
     LAUNCH(c, k_cg_init, blocks, 256, 0, c->d_rhs, c->d_tot, c->d_r, c->d_p, n, 0.0, c->d_cg, c->d_part + 4 * kRedBlocks, c->d_ticket + 4, fin);
-    if (!fin) { { int r = allreduce_sum(c, c->d_cg->tmp, 3); if (r) return r; } LAUNCH(c, k_cg_finalize, 1, 1, 0, c->d_cg, 0, 0.0, 0); }
+    if (!fin) { { int r = allreduce_sum(c, c->d_cg->tmp, 3); if (r) return r; } LAUNCH(c, k_cg_finalize, 1, 1, 0, c->d_cg, 0, 0.0, 0, 0); }
     for (int i = 0; i < 16; ++i) ms_out[i] = 0.0;
     auto iteration = [&](int mask, bool upd, bool pupd) -> int {
         if (mask) { int r = apply_schur(c, g, c->d_p, c->d_Ap, true, mask); if (r) return r; }
@@ -1505,7 +1433,7 @@ int nf_time_kernels(nf_ctx *c, int g, int reps, int fast, double *ms_out)
             if (!fin) { int r = allreduce_sum(c, c->d_cg->pAp, 4); if (r) return r; }
             if (!fast) LAUNCH(c, k_cg_update, blocks, 256, 0, c->d_p, c->d_Ap, c->d_tot, c->d_r, n, c->d_cg, c->d_part + 4 * kRedBlocks, c->d_ticket + 4, fin);
             else LAUNCH(c, k_pcg_update, blocks, 256, 0, c->d_p, c->d_Ap, jac, c->d_tot, c->d_r, n, c->d_cg, c->d_part + 4 * kRedBlocks, c->d_ticket + 4, fin);
-            if (!fin) { { int r = allreduce_sum(c, c->d_cg->tmp, 2); if (r) return r; } LAUNCH(c, k_cg_finalize, 1, 1, 0, c->d_cg, 1, 0.0, fast ? 1 : 0); }
+            if (!fin) { { int r = allreduce_sum(c, c->d_cg->tmp, 2); if (r) return r; } LAUNCH(c, k_cg_finalize, 1, 1, 0, c->d_cg, 1, 0.0, fast ? 1 : 0, 0); }
         }
         if (pupd) {
             if (!fast) LAUNCH(c, k_cg_pupdate, blocks, 256, 0, c->d_r, c->d_p, n, c->d_cg);
@@ -1513,21 +1441,27 @@ int nf_time_kernels(nf_ctx *c, int g, int reps, int fast, double *ms_out)
         }
         return NF_OK;
     };
+    auto timed = [&](int slot, auto &&fn) -> int {
+        CU(c, cudaEventRecord(c->ev2, c->stream));
+        for (int i = 0; i < reps; ++i) { int r = fn(); if (r) return r; }
+        CU(c, cudaEventRecord(c->ev3, c->stream));
+        CU(c, cudaEventSynchronize(c->ev3));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, c->ev2, c->ev3);
+        ms_out[slot] = ms / reps;
+        return NF_OK;
+    };
     { int r = iteration(7, true, true); if (r) return r; }    // warm-up, also makes p.Ap non-zero
     struct { int mask; bool upd, pupd; } what[6] = {{1, false, false}, {2, false, false}, {4, false, false},
                                                     {0, true, false}, {0, false, true}, {7, true, true}};
     for (int w = 0; w < 6; ++w) {
         if (what[w].mask && what[w].mask != 7 && !(what[w].mask < (1 << c->dim))) continue;
-        CU(c, cudaEventRecord(c->ev2, c->stream));
-        for (int i = 0; i < reps; ++i) { int r = iteration(what[w].mask, what[w].upd, what[w].pupd); if (r) return r; }
-        CU(c, cudaEventRecord(c->ev3, c->stream));
-        CU(c, cudaEventSynchronize(c->ev3));
-        float ms = 0.f;
-        cudaEventElapsedTime(&ms, c->ev2, c->ev3);
-        ms_out[w] = ms / reps;
+        int r = timed(w, [&]() { return iteration(what[w].mask, what[w].upd, what[w].pupd); });
+        if (r) return r;
     }
     ms_out[8] = ms_out[5];                       // the separate-kernel iteration
     { int r = fused_setup(c); if (r) return r; }
+    ms_out[12] = (double)c->fused;
     if (c->fused == 2) {                          // hybrid path: separate direction update, x, y sweeps + k_zfwd + k_zback_update
         FusedArgs fa;
         fill_fused_args(c, fa, g, c->d_tot, jac);
@@ -1537,42 +1471,20 @@ int nf_time_kernels(nf_ctx *c, int g, int reps, int fast, double *ms_out)
                 else LAUNCH(c, k_pcg_pupdate, blocks, 256, 0, c->d_r, jac, c->d_p, n, c->d_cg);
                 int r = apply_schur(c, g, c->d_p, c->d_Ap, true, 3); if (r) return r;
             }
-            return fused_launch(c, fa, what & 6);
+            return fused_launch(c, fa, what & 6, false);
         };
         { int r = hyb(7); if (r) return r; }
         const int which[3] = {4, 2, 7};
         const int slot[3] = {6, 7, 5};
-        for (int w = 0; w < 3; ++w) {
-            CU(c, cudaEventRecord(c->ev2, c->stream));
-            for (int i = 0; i < reps; ++i) { int r = hyb(which[w]); if (r) return r; }
-            CU(c, cudaEventRecord(c->ev3, c->stream));
-            CU(c, cudaEventSynchronize(c->ev3));
-            float ms = 0.f;
-            cudaEventElapsedTime(&ms, c->ev2, c->ev3);
-            ms_out[slot[w]] = ms / reps;
-        }
+        for (int w = 0; w < 3; ++w) { int r = timed(slot[w], [&]() { return hyb(which[w]); }); if (r) return r; }
     }
-    ms_out[12] = (double)c->fused;
-    if (c->fused == 5) {                          // z-slab ranks: k_xrow | k_ycol | slab z sweep (+ all-gather) | update
+    if (c->fused == 5) {                          // z-slab ranks: k_xrow | k_ycol | z forward + all-gather | interface + update
         FusedArgs fa;
         fill_fused_args(c, fa, g, c->d_tot, jac);
-        auto slabit = [&](int what) -> int {       // 1: x rows, 2: y columns, 12: z sweep fused with the update
-            if (what & 3) { int r = rows_launch(c, fa, what & 3); if (r) return r; }
-            if (what & 12) { int r = slab_zupdate(c, g, c->d_tot, jac, 0.0); if (r) return r; }
-            return NF_OK;
-        };
-        { int r = slabit(15); if (r) return r; }
-        const int which[4] = {1, 2, 12, 15};
-        const int slot[4] = {9, 10, 7, 5};
-        for (int w = 0; w < 4; ++w) {
-            CU(c, cudaEventRecord(c->ev2, c->stream));
-            for (int i = 0; i < reps; ++i) { int r = slabit(which[w]); if (r) return r; }
-            CU(c, cudaEventRecord(c->ev3, c->stream));
-            CU(c, cudaEventSynchronize(c->ev3));
-            float ms = 0.f;
-            cudaEventElapsedTime(&ms, c->ev2, c->ev3);
-            ms_out[slot[w]] = ms / reps;
-        }
+        { int r = slab_iteration(c, fa, g, 0.0, 15); if (r) return r; }
+        const int which[5] = {1, 2, 4, 8, 15};
+        const int slot[5] = {9, 10, 6, 7, 5};
+        for (int w = 0; w < 5; ++w) { int r = timed(slot[w], [&]() { return slab_iteration(c, fa, g, 0.0, which[w]); }); if (r) return r; }
     }
     if (c->fused == 3) {                          // rows path: k_xrow | k_ycol | k_zfwd | k_zback_update
         FusedArgs fa;
@@ -1580,39 +1492,12 @@ int nf_time_kernels(nf_ctx *c, int g, int reps, int fast, double *ms_out)
         auto rowsit = [&](int what) -> int {       // 1: x rows, 8: y columns, 4: z forward, 2: z back + update
             if (what & 1) { int r = rows_launch(c, fa, 1); if (r) return r; }
             if (what & 8) { int r = rows_launch(c, fa, 2); if (r) return r; }
-            return (what & 6) ? fused_launch(c, fa, what & 6) : NF_OK;
+            return (what & 6) ? fused_launch(c, fa, what & 6, true) : NF_OK;
         };
         { int r = rowsit(15); if (r) return r; }
         const int which[5] = {1, 8, 4, 2, 15};
         const int slot[5] = {9, 10, 6, 7, 5};
-        for (int w = 0; w < 5; ++w) {
-            CU(c, cudaEventRecord(c->ev2, c->stream));
-            for (int i = 0; i < reps; ++i) { int r = rowsit(which[w]); if (r) return r; }
-            CU(c, cudaEventRecord(c->ev3, c->stream));
-            CU(c, cudaEventSynchronize(c->ev3));
-            float ms = 0.f;
-            cudaEventElapsedTime(&ms, c->ev2, c->ev3);
-            ms_out[slot[w]] = ms / reps;
-        }
-    }
-    if (c->fused == 1) {                          // product path on 3-D single-GPU contexts: two fused kernels
-        FusedArgs fa;
-        fill_fused_args(c, fa, g, c->d_tot, jac);
-        { int r = fused_launch(c, fa, 3); if (r) return r; }     // warm-up
-        const int which[3] = {1, 2, 3};
-        const int slot[3] = {6, 7, 5};
-        for (int w = 0; w < 3; ++w) {
-            CU(c, cudaEventRecord(c->ev2, c->stream));
-            for (int i = 0; i < reps; ++i) { int r = fused_launch(c, fa, which[w]); if (r) return r; }
-            CU(c, cudaEventRecord(c->ev3, c->stream));
-            CU(c, cudaEventSynchronize(c->ev3));
-            float ms = 0.f;
-            cudaEventElapsedTime(&ms, c->ev2, c->ev3);
-            ms_out[slot[w]] = ms / reps;
-        }
-        CU(c, cudaMemcpyAsync(c->h_cg, c->d_cg, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
-        CU(c, cudaStreamSynchronize(c->stream));
-        if (c->h_cg->pad) NF_FAIL(c, NF_ERR_STATE, "fused CG kernel: a work-item dependency timed out (internal error)");
+        for (int w = 0; w < 5; ++w) { int r = timed(slot[w], [&]() { return rowsit(which[w]); }); if (r) return r; }
     }
     return NF_OK;
 }

@@ -13,10 +13,21 @@
 
 namespace nf {
 
-// Storage type of the Jacobi preconditioner M^-1. Single precision would be admissible (any fixed SPD M leaves the PCG
-// limit unchanged) and was measured: k_xrow gains 5 %, k_zback_update loses 10 % (4-byte loads + F2F conversions in the
-// marching loop), a net loss -- so it stays fp64.
-typedef double jac_t;
+// Storage type of the Jacobi preconditioner M^-1: the UPPER 16 BITS of the fp64 value (sign, 11 exponent bits, 4 mantissa
+// bits, round to nearest). Any fixed SPD diagonal M leaves the PCG limit unchanged; what the preconditioner has to capture
+// is the 1e15 dynamic range of the cross-sections (full fp64 exponent kept) and the mode-to-mode weights, not digits:
+// measured on the synthetic IAEA-3D operator, 4 mantissa bits give the same CG iteration counts as the fp64 diagonal
+// (tools/jacobi_bits.py). Expanding to fp64 is one shift (no F2F conversion, which made fp32 storage a net loss in round 1),
+// and M^-1 costs 2 B per flux DOF per pass instead of 8.
+typedef unsigned short jac_t;
+__device__ __forceinline__ double jac_to_double(const jac_t v) { return __hiloint2double((int)((unsigned)v << 16), 0); }
+__device__ __forceinline__ jac_t jac_from_double(const double d)
+{
+    unsigned hi = (unsigned)__double2hiint(d);
+    hi += 0x8000u;                                  // round to nearest on the kept mantissa bits
+    return (jac_t)(hi >> 16);
+}
+__device__ __forceinline__ double jac_ld(const jac_t *p) { return jac_to_double(__ldg(p)); }
 
 constexpr int kMaxModes = 27;   // (m+1)^3, m <= 2
 constexpr int kMaxT = 9;        // transverse mode pairs per direction, (m+1)^2

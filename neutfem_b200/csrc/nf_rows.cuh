@@ -1,17 +1,20 @@
 // nf_rows.cuh -- register-resident line solvers for the x and y directions of a 3-D mesh.
 //
 // Reference: SchurSolver::SchurProduct (src/solvers.cpp:535-547), the B A^-1 B^T part of one direction, plus the
-// direction update p = M^-1 r + beta p of SolveSchurImplicit (src/solvers.cpp:626-631) fused into the x rows.
+// direction update p = M^-1 r + beta p and the solution update x += alpha p of SolveSchurImplicit
+// (src/solvers.cpp:601-631) fused into the x rows.
 //
-// The shared-memory tile solvers of nf_sweeps.cuh / nf_fused.cuh are instruction bound (ncu: ~200-480 instructions per
-// flux DOF, profiles/r01b_*). Here every thread owns a chunk of up to kLC = 33 consecutive faces of one condensed
-// tridiagonal system and keeps its right-hand side / solution in REGISTERS; the chunks of a line are stitched exactly
-// by composing affine maps (forward: z_out = A z_in + b, backward: J_out = B J_in + c), never by truncation.
+// Every thread owns a chunk of LCT (17 or 33) consecutive faces of one condensed tridiagonal system and keeps its
+// right-hand side / solution in REGISTERS; the chunks of a line are stitched exactly by composing affine maps
+// (forward: z_out = A z_in + b, backward: J_out = B J_in + c), never by truncation.
 //
-//   xrow_warp   one WARP owns one x line (iy, iz) with all its modes: it forms p (coalesced), stages it in its private
-//               shared-memory slice, transposes to chunk ownership (lane = pair slot * C + chunk), solves the pairs of
-//               the line side by side, transposes J back and writes yp = diag * p + w B_x J (coalesced). No block-level
-//               barrier anywhere: warps of a CTA run independently.
+//   xrow_warp   one WARP owns one x line (iy, iz) and walks its transverse pairs PW at a time. The rows of r, p_old and
+//               M^-1 of a pass are contiguous in memory (mode-major layout): one elected lane requests them with
+//               cp.async.bulk (TMA, 1-D) into the warp's private shared-memory slice and the warp waits on an mbarrier, so a
+//               whole pass of operands is in flight without holding a single register; x (for the deferred update
+//               x += alpha_prev p_old) is requested into registers meanwhile. The warp then forms p in place, switches to
+//               chunk ownership (lane = pair slot * C + chunk), solves the PW pairs side by side, transposes J back through
+//               shared memory and writes yp = diag * p + w B_x J (coalesced). No block-level barrier anywhere.
 //   ycol_block  one CTA owns colsY adjacent y lines (x positions) of one plane and one transverse pair: thread = (column,
 //               chunk of the y line). Loads are coalesced across the columns, p / yp go straight from L2 to registers;
 //               chunks are stitched through a few shared-memory words (three barriers per item).
@@ -20,17 +23,50 @@
 
 namespace nf {
 
-constexpr int kLC = 33;         // faces per thread chunk (odd: conflict-free shared-memory columns)
+constexpr int kLC = 33;         // longest chunk of faces a thread owns (odd: conflict-free shared-memory columns)
+constexpr int kLCs = 17;        // the short chunk (lines of up to 543 cells)
 
 // compiler-level fence: keeps nvcc from hoisting the loads of later batches above the work of earlier ones (register blow-up)
 #define NF_SCHED_FENCE() asm volatile("" ::: "memory")
 
 struct RowGeom {
-    int Cx, LcX, PWx;           // x lines: chunks per line (8 / 16 / 32 lanes), faces per chunk, pairs per pass (32 / Cx)
-    int NFx, pitchP, pitchJ;    // Cx * LcX; shared-memory row pitches (doubles) of the P and J tiles
+    int PWx, LcX, NFx;          // x lines: pairs per pass (1 / 2 / 4; 32 / PWx lanes per pair), faces per chunk, PWx-independent row length 32 / PWx * LcX
+    int pitchP, pitchJ;         // shared-memory row pitches (doubles) of the P and J tiles
+    int offPO, offJAC, offBAR;  // offsets (doubles) of the p_old / J tile, the M^-1 tile and the mbarrier inside a warp's slice
     int xsmemW;                 // doubles of shared memory per warp
+    int bulk;                   // 1: rows are requested with cp.async.bulk (nx % 8 == 0: 16-byte aligned rows of every array)
     int Cy, LcY, colsY, warpsY; // y lines: chunks per line, faces per chunk, columns per item, warps per CTA
 };
+
+// ---- mbarrier / bulk-copy primitives (PTX ISA: mbarrier, cp.async.bulk; SASS: SYNCS, UBLKCP) ------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    unsigned ok = 0, spins = 0;
+    const unsigned addr = smem_u32(bar);
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+        if (!ok && ++spins > (1u << 22)) __trap();      // a lost completion becomes a CUDA error, never a hung GPU
+    } while (!ok);
+}
+// global -> shared bulk copy of `bytes` (multiple of 16, both addresses 16-byte aligned), completion counted on `bar`
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// orders this thread's generic-proxy accesses to shared memory before later async-proxy (bulk copy) accesses
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
 // ---- the four passes over a register-resident chunk -------------------------------------------------------------------
 // um(j) = u_{f0+j-1} (0 at the first face of the line), uf(j) = u_{f0+j} (0 at the last face), mi(j) = 1/m_{f0+j}.
@@ -110,30 +146,33 @@ __device__ __forceinline__ void chunk_bwd_final(double (&T)[LCT], const int jn, 
 }
 
 // ---- x rows ------------------------------------------------------------------------------------------------------------
-// One warp, one x line (iy, iz), all modes. sm = this warp's private slice: UB[NF+2] | MINV[NF+2] | P[PW*M1][pitchP] |
-// J[PW][pitchJ]; the cells >= nx of the P rows must be zero on entry (they are never written).
-// NCL = compile-time bound on the cells a lane owns (ceil(nx / 32)): per-cell coefficients live in registers.
-constexpr int kCB = 8;          // cells per lane in one coalesced batch (256 cells)
-#ifndef NF_XROW_UB
-#define NF_XROW_UB 2
-#endif
-constexpr int kUB = NF_XROW_UB; // (mode, batch) units loaded together in the direction update: 24 * kUB independent loads per lane
+// One warp, one x line (iy, iz), all modes, PW transverse pairs per pass. sm = this warp's private slice:
+//   UB[NF+2] | MINV[NF+2] | P[PW*M1][pitchP] | PO[PW*M1][nx] (p_old, later J[PW][pitchJ]) | JAC[PW*M1][nx] (16 bit) | mbarrier
+// The cells >= nx of the P rows must be zero on entry (they are never written): every chunk then runs all LCT steps
+// without guards (T = 0, u = 0, 1/m = 0 past the end of the line leave every result unchanged).
+// NCL = compile-time bound on the cells a lane owns (ceil(nx / 32)): per-cell cross-sections live in registers.
+// DEFER: x += alpha_prev * p_old, the solution update the previous iteration left pending (nf_fused.cuh).
+constexpr int kCB = 8;          // cells per lane in one batch of the output pass
 
-template <int K, int M1, int NCL, int LCT, bool FULL>
+template <int K, int M1, int PW, int NCL, int LCT, bool DEFER>
 __device__ __forceinline__ void xrow_warp(const FusedArgs &a, const RowGeom &g, const int iz, const int iy, const double beta,
-                                          double *sm, double &acc)
+                                          const double alpha_prev, double *sm, unsigned &phase, double &acc)
 {
+    constexpr int C = 32 / PW, NF = C * LCT, NR = PW * M1;         // lanes per pair, faces per padded line, rows per pass
+    constexpr int LB = (LCT > 17 ? 11 : 9);
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    const int n = a.nx, C = g.Cx, Lc = g.LcX, PW = g.PWx, NF = g.NFx, PP = g.pitchP, PJ = g.pitchJ;
-    double *UB = sm, *MINV = UB + NF + 2, *P = MINV + NF + 2, *Jb = P + PW * M1 * PP;
-    // (letting J reuse the P tile -- 9 KB less per warp, p re-read from L2 for the output -- was measured: 12-25 % slower)
+    const int n = a.nx, PP = g.pitchP, PJ = g.pitchJ;
+    double *UB = sm, *MINV = UB + NF + 2, *P = MINV + NF + 2, *PO = sm + g.offPO, *Jb = PO;
+    jac_t *JAC = reinterpret_cast<jac_t *>(sm + g.offJAC);
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(sm + g.offBAR);
     const long long line = (long long)iz * a.ny + iy;
     const size_t e0 = (size_t)line * n;
-    const bool pcg = a.pcg != 0, hasb = (beta != 0.0);
-    const int ncb = (n + 32 * kCB - 1) / (32 * kCB);         // coalesced batches per mode
-    // ---- the factors are requested first (asynchronous copies)
-    {   // LDL^T factors of the line: UB[f] = u_{f-1}, MINV[f] = 1/m_f (asynchronous copies, waited for before the solve)
+    const bool pcg = a.pcg != 0, hasb = (beta != 0.0), xupd = DEFER && (alpha_prev != 0.0);
+    const bool need_po = hasb || xupd;
+    // ---- the factors of the line are requested first: UB[f] = u_{f-1}, MINV[f] = 1/m_f (asynchronous copies; the rows of
+    // the x factor arrays have nx + 1 entries, so they are only 8-byte aligned: per-lane cp.async, not bulk copies)
+    {
         const double *gm = a.minv[0] + line * (n + 1), *gu = a.u[0] + line * (n + 1);
         for (int f = lane; f <= NF; f += 32) {
             if (f <= n) cp_async8(MINV + f, gm + f); else MINV[f] = 0.0;
@@ -142,80 +181,79 @@ __device__ __forceinline__ void xrow_warp(const FusedArgs &a, const RowGeom &g, 
         if (lane == 0) UB[0] = 0.0;
         asm volatile("cp.async.commit_group;\n" ::: "memory");
     }
+    // per-cell cross-sections of the lane's cells: requested now, first used in the output pass of the first pair
+    double Dv[NCL], Sv[NCL];
+#pragma unroll
+    for (int c = 0; c < NCL; ++c) {
+        const int ixl = min(lane + 32 * c, n - 1);
+        Dv[c] = __ldg(a.D + e0 + ixl); Sv[c] = __ldg(a.SigR + e0 + ixl);
+    }
     const double fy0 = __ldg(a.Fy[0] + iy), fy1 = __ldg(a.Fy[1] + iy), fy2 = __ldg(a.Fy[2] + iy);
     const double fz0 = __ldg(a.Fz[0] + iz), fz1 = __ldg(a.Fz[1] + iz), fz2 = __ldg(a.Fz[2] + iz);
-    double ify0 = 0.0, ify1 = 0.0, ify2 = 0.0;
+    const double ify0 = 1.0 / (fy0 * fz0), ify1 = 1.0 / (fy1 * fz1), ify2 = 1.0 / (fy2 * fz2);
     const int s = lane / C, k = lane - s * C;
-    const int f0 = k * Lc;
-    const int jn = max(0, min(Lc, n + 1 - f0));
+    const int f0 = k * LCT;
     for (int t0 = 0; t0 < a.nt; t0 += PW) {
-        const int np = min(PW, a.nt - t0);
-        // ---- direction update p = M^-1 r + beta p for the modes of these pairs, staged in P (coalesced).
-        // Units of (mode, 256-cell batch) are processed kUB at a time: 24 * kUB independent loads per lane in flight.
-        {
-            const int nunits = np * M1 * ncb;
-            for (int u0 = 0; u0 < nunits; u0 += kUB) {
-                double rv[kUB][kCB], jv[kUB][kCB], po[kUB][kCB];
-                size_t off[kUB]; int mmu[kUB], ibu[kUB];
-                // loads are unconditional (indices clamped into the row): nothing may wait on a load before all are issued
-#pragma unroll
-                for (int h = 0; h < kUB; ++h) {
-                    const int u = min(u0 + h, nunits - 1);
-                    mmu[h] = u / ncb; ibu[h] = (u - mmu[h] * ncb) * (32 * kCB) + lane;
-                    off[h] = (size_t)a.mode[0][t0 + mmu[h] / M1][mmu[h] % M1] * a.ne + e0;
-#pragma unroll
-                    for (int i = 0; i < kCB; ++i) rv[h][i] = __ldg(a.r + off[h] + min(ibu[h] + 32 * i, n - 1));
+        const int np = min(PW, a.nt - t0), rows = np * M1;
+        // ---- request the rows of this pass: r -> P, p_old -> PO, M^-1 -> JAC
+        if (g.bulk) {
+            if (lane == 0) {
+                const unsigned bytes = (unsigned)rows * (unsigned)n * (8u * (need_po ? 2u : 1u) + (pcg ? 2u : 0u));
+                mbar_arrive_expect_tx(bar, bytes);
+            }
+            __syncwarp();
+            if (lane < rows) {
+                const size_t off = (size_t)a.mode[0][t0 + lane / M1][lane % M1] * a.ne + e0;
+                bulk_g2s(P + lane * PP, a.r + off, (unsigned)n * 8u, bar);
+                if (need_po) bulk_g2s(PO + lane * n, a.p + off, (unsigned)n * 8u, bar);
+                if (pcg) bulk_g2s(JAC + lane * n, a.jac + off, (unsigned)n * 2u, bar);
+            }
+        } else {
+            for (int m = 0; m < rows; ++m) {
+                const size_t off = (size_t)a.mode[0][t0 + m / M1][m % M1] * a.ne + e0;
+                for (int i = lane; i < n; i += 32) {
+                    cp_async8(P + m * PP + i, a.r + off + i);
+                    if (need_po) cp_async8(PO + m * n + i, a.p + off + i);
+                    if (pcg) JAC[m * n + i] = __ldg(a.jac + off + i);
                 }
-                if (pcg) {
+            }
+            asm volatile("cp.async.commit_group;\n" ::: "memory");
+        }
+        // ---- x of the lane's cells (deferred update): requested into registers while the rows are in flight
+        double xv[NR][NCL];
+        if (xupd) {
 #pragma unroll
-                    for (int h = 0; h < kUB; ++h)
+            for (int m = 0; m < NR; ++m) {
+                const size_t off = (size_t)a.mode[0][min(t0 + m / M1, a.nt - 1)][m % M1] * a.ne + e0;
 #pragma unroll
-                        for (int i = 0; i < kCB; ++i) jv[h][i] = (double)__ldg(a.jac + off[h] + min(ibu[h] + 32 * i, n - 1));
-                } else {
+                for (int c = 0; c < NCL; ++c) xv[m][c] = a.x[off + min(lane + 32 * c, n - 1)];
+            }
+        }
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");       // factors (first pass) and the rows of the fallback path
+        if (g.bulk) { mbar_wait(bar, phase); phase ^= 1u; }
+        __syncwarp();
+        // ---- direction update p = M^-1 r + beta p_old (in place in P, and to global memory); x += alpha_prev p_old
 #pragma unroll
-                    for (int h = 0; h < kUB; ++h)
+        for (int m = 0; m < NR; ++m) {
+            if (m < rows) {
+                const size_t off = (size_t)a.mode[0][t0 + m / M1][m % M1] * a.ne + e0;
+                double *Pm = P + m * PP;
+                const double *POm = PO + m * n;
+                const jac_t *Jm = JAC + m * n;
 #pragma unroll
-                        for (int i = 0; i < kCB; ++i) jv[h][i] = 1.0;
-                }
-                if (hasb) {
-#pragma unroll
-                    for (int h = 0; h < kUB; ++h)
-#pragma unroll
-                        for (int i = 0; i < kCB; ++i) po[h][i] = a.p[off[h] + min(ibu[h] + 32 * i, n - 1)];
-                } else {
-#pragma unroll
-                    for (int h = 0; h < kUB; ++h)
-#pragma unroll
-                        for (int i = 0; i < kCB; ++i) po[h][i] = 0.0;
-                }
-#pragma unroll
-                for (int h = 0; h < kUB; ++h) {
-                    const bool hv = (u0 + h < nunits);
-                    double *Pm = P + mmu[h] * PP;
-#pragma unroll
-                    for (int i = 0; i < kCB; ++i) {
-                        const int ix = ibu[h] + 32 * i;
-                        const double pn = jv[h][i] * rv[h][i] + beta * po[h][i];
-                        if (hv && ix < n) {
-                            Pm[ix] = pn;
-                            a.p[off[h] + ix] = pn;
-                        }
+                for (int c = 0; c < NCL; ++c) {
+                    const int ix = lane + 32 * c;
+                    if (ix < n) {
+                        const double rv = Pm[ix];
+                        const double jv = pcg ? jac_to_double(Jm[ix]) : 1.0;
+                        const double po = need_po ? POm[ix] : 0.0;
+                        const double pn = jv * rv + beta * po;
+                        Pm[ix] = pn;
+                        a.p[off + ix] = pn;
+                        if (xupd) a.x[off + ix] = xv[m][c] + alpha_prev * po;
                     }
                 }
             }
-        }
-        // per-cell coefficients of the lane's cells: requested now, first used after the solve
-        // (3-D only: 1/Fx of the y and z directions are both hx, and the cell volume is hx * hy * hz = hx * ify0)
-        double Dv[NCL], Sv[NCL], Hx[NCL], F0[NCL];
-#pragma unroll
-        for (int c = 0; c < NCL; ++c) {
-            const int ixl = min(lane + 32 * c, n - 1);
-            Dv[c] = __ldg(a.D + e0 + ixl); Sv[c] = __ldg(a.SigR + e0 + ixl);
-            Hx[c] = __ldg(a.iFx[1] + ixl); F0[c] = __ldg(a.iFx[0] + ixl);
-        }
-        if (t0 == 0) {     // first use of the factors requested at the top of the row
-            ify0 = 1.0 / (fy0 * fz0); ify1 = 1.0 / (fy1 * fz1); ify2 = 1.0 / (fy2 * fz2);
-            asm volatile("cp.async.wait_group 0;\n" ::: "memory");
         }
         __syncwarp();
         // ---- chunk ownership: lane = (pair slot s, chunk k)
@@ -228,55 +266,57 @@ __device__ __forceinline__ void xrow_warp(const FusedArgs &a, const RowGeom &g, 
             if (f0 > 0) cell_lo_hi<K, M1>(P0[-1], P1[-1], P2[-1], lop, dum);
 #pragma unroll
             for (int j = 0; j < LCT; ++j) {
-                T[j] = 0.0;
-                if (FULL || j < jn) {
-                    double lo, hi;
-                    cell_lo_hi<K, M1>(P0[j], P1[j], P2[j], lo, hi);     // cells >= n are zero pads: T_n = lo_{n-1}, T_f = 0 beyond
-                    T[j] = lop - hi;
-                    lop = lo;
-                }
+                double lo, hi;
+                cell_lo_hi<K, M1>(P0[j], P1[j], P2[j], lo, hi);     // cells >= n are zero pads: T_n = lo_{n-1}, T_f = 0 beyond
+                T[j] = lop - hi;
+                lop = lo;
             }
         }
         const double *ub = UB + f0, *mb = MINV + f0;
         auto um = [&](const int j) { return ub[j]; };
         auto uf = [&](const int j) { return ub[j + 1]; };
         auto mi = [&](const int j) { return mb[j]; };
+        const int jn = LCT;
         double A, z;
-        chunk_fwd_map<LCT, (LCT > 17 ? 11 : 9), FULL>(T, jn, um, A, z);
+        chunk_fwd_map<LCT, LB, true>(T, jn, um, A, z);
+#pragma unroll
         for (int d = 1; d < C; d <<= 1) {
             const double Ap = __shfl_up_sync(full, A, d, C), zp = __shfl_up_sync(full, z, d, C);
             if (k >= d) { z = A * zp + z; A = A * Ap; }
         }
         double zin = __shfl_up_sync(full, z, 1, C);
         if (k == 0) zin = 0.0;
-        const double q = chunk_fwd_final<LCT, (LCT > 17 ? 11 : 9), FULL>(T, jn, um, mi, zin);
+        const double q = chunk_fwd_final<LCT, LB, true>(T, jn, um, mi, zin);
         double Bp, J;
-        chunk_bwd_map<LCT, (LCT > 17 ? 11 : 9), FULL>(T, jn, uf, Bp, J);
+        chunk_bwd_map<LCT, LB, true>(T, jn, uf, Bp, J);
+#pragma unroll
         for (int d = 1; d < C; d <<= 1) {
             const double Bq = __shfl_down_sync(full, Bp, d, C), Jq = __shfl_down_sync(full, J, d, C);
             if (k + d < C) { J = Bp * Jq + J; Bp = Bp * Bq; }
         }
         double Jin = __shfl_down_sync(full, J, 1, C);
         if (k == C - 1) Jin = 0.0;
-        chunk_bwd_final<LCT, (LCT > 17 ? 11 : 9), FULL>(T, jn, uf, Jin);
+        chunk_bwd_final<LCT, LB, true>(T, jn, uf, Jin);
         if (tv) {
             acc += a.w[t0 + s] * q;
-            double *Jr = Jb + s * PJ + f0;
+            double *Jr = Jb + s * PJ + f0;           // p_old has been consumed: its tile now holds J
 #pragma unroll
-            for (int j = 0; j < LCT; ++j)
-                if (FULL || j < jn) Jr[j] = T[j];
+            for (int j = 0; j < LCT; ++j) Jr[j] = T[j];
         }
         __syncwarp();
-        // ---- yp = diag * p + w B_x J (coalesced): batches of 8 cells per lane, modes outside, cells inside
+        // ---- yp = diag * p + w B_x J (coalesced): batches of kCB cells per lane, modes outside, cells inside
+        // (3-D only: 1/Fx of the y and z directions are both hx, and the cell volume is hx * hy * hz = hx * ify0)
 #pragma unroll
         for (int cb = 0; cb < NCL; cb += kCB) {
             if (lane + 32 * cb < n) {
-                double G0[kCB], G1[kCB], G2[kCB], SV[kCB];
+                double G0[kCB], G1[kCB], SV[kCB];
 #pragma unroll
                 for (int c = 0; c < kCB; ++c) {
                     const int cc = (cb + c < NCL) ? cb + c : NCL - 1;
-                    G0[c] = Dv[cc] * F0[cc]; G1[c] = Dv[cc] * Hx[cc]; G2[c] = G1[c];
-                    SV[c] = Sv[cc] * (Hx[cc] * ify0);
+                    const int ixl = min(lane + 32 * cc, n - 1);
+                    const double hx = __ldg(a.iFx[1] + ixl), f0x = __ldg(a.iFx[0] + ixl);
+                    G0[c] = Dv[cc] * f0x; G1[c] = Dv[cc] * hx;
+                    SV[c] = Sv[cc] * (hx * ify0);
                 }
                 for (int s2 = 0; s2 < np; ++s2) {
                     const double w = a.w[t0 + s2];
@@ -284,7 +324,7 @@ __device__ __forceinline__ void xrow_warp(const FusedArgs &a, const RowGeom &g, 
 #pragma unroll
                     for (int p = 0; p < M1; ++p) {
                         const int md = a.mode[0][t0 + s2][p];
-                        const double cw = a.wC[md], c0 = a.cb[0][md] * ify0, c1 = a.cb[1][md] * ify1, c2 = a.cb[2][md] * ify2;
+                        const double cw = a.wC[md], c0 = a.cb[0][md] * ify0, c12 = a.cb[1][md] * ify1 + a.cb[2][md] * ify2;
                         const double *Pm = P + (s2 * M1 + p) * PP + lane + 32 * cb;
                         double *yo = a.yp + (size_t)md * a.ne + e0 + lane + 32 * cb;
 #pragma unroll
@@ -293,10 +333,10 @@ __device__ __forceinline__ void xrow_warp(const FusedArgs &a, const RowGeom &g, 
                                 const double JL = Js[32 * c], JR = Js[32 * c + 1];
                                 const double sol = (p == 0) ? w * (JR - JL) : (p == 1 ? ((K >= 1) ? w * (5.0 / 6.0) * (JL + JR) : 0.0)
                                                                                       : ((K >= 2) ? w * (7.0 / 10.0) * (JR - JL) : 0.0));
-                                const double xv = Pm[32 * c];
-                                const double dg = SV[c] * cw + G0[c] * c0 + G1[c] * c1 + G2[c] * c2;
-                                const double yv = dg * xv;
-                                acc += yv * xv;
+                                const double xv2 = Pm[32 * c];
+                                const double dg = SV[c] * cw + G0[c] * c0 + G1[c] * c12;
+                                const double yv = dg * xv2;
+                                acc += yv * xv2;
                                 yo[32 * c] = yv + sol;
                             }
                         }
@@ -304,33 +344,43 @@ __device__ __forceinline__ void xrow_warp(const FusedArgs &a, const RowGeom &g, 
                 }
             }
         }
+        // the next pass (or row) overwrites P / PO / JAC through the async proxy: order this lane's accesses before it
+        fence_proxy_async();
         __syncwarp();
     }
 }
 
-constexpr int kXW = 1;      // warps per CTA of the x-row kernel (every warp is autonomous)
+#ifndef NF_XW
+#define NF_XW 1
+#endif
+constexpr int kXW = NF_XW;      // warps per CTA of the x-row kernel (every warp is autonomous)
+#ifndef NF_XROW_MINB
+#define NF_XROW_MINB 8
+#endif
 
-// p = M^-1 r + beta p ; yp = diag p + (x part of S p) ; red_out = p^T (diag + x part) p.
-// (Letting the z-direction forward substitution ride along here -- rows in plane order, per-row flags for the carry -- was
-// measured and rejected: the nz-long chain of flag hand-overs costs more than the separate marching kernel k_zfwd.)
-template <int K, int M1, int NCL, int LCT, bool FULL>
-__global__ void __launch_bounds__(32 * kXW, 7) k_xrow(const FusedArgs a, const RowGeom g, double *red_part, unsigned *ticket,
-                                                      double *red_out)
+// x += alpha_prev p_old ; p = M^-1 r + beta p_old ; yp = diag p + (x part of S p) ; red_out = p^T (diag + x part) p.
+template <int K, int M1, int PW, int NCL, int LCT, bool DEFER>
+__global__ void __launch_bounds__(32 * kXW, NF_XROW_MINB / kXW) k_xrow(const FusedArgs a, const RowGeom g, double *red_part,
+                                                                      unsigned *ticket, double *red_out)
 {
     if (a.st->done) return;
     extern __shared__ __align__(16) double sm[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, WPB = blockDim.x >> 5;
     double *wsm = sm + (size_t)wib * g.xsmemW;
-    {   // zero pads of the P rows
-        double *P = wsm + 2 * (g.NFx + 2);
-        for (int i = lane; i < g.PWx * M1 * g.pitchP; i += 32) P[i] = 0.0;
+    {   // zero pads of the P rows; the warp's mbarrier
+        constexpr int C = 32 / PW, NF = C * LCT;
+        double *P = wsm + 2 * (NF + 2);
+        for (int i = lane; i < PW * M1 * g.pitchP; i += 32) P[i] = 0.0;
+        if (lane == 0) mbar_init(reinterpret_cast<unsigned long long *>(wsm + g.offBAR), 1u);
+        fence_proxy_async();
         __syncwarp();
     }
-    const double beta = a.st->beta;
+    const double beta = a.st->beta, alpha_prev = DEFER ? a.st->alpha_prev : 0.0;
     const long long nrows = (long long)a.ny * a.nz;
     double acc = 0.0;
+    unsigned phase = 0u;
     for (long long row = (long long)blockIdx.x * WPB + wib; row < nrows; row += (long long)gridDim.x * WPB)
-        xrow_warp<K, M1, NCL, LCT, FULL>(a, g, (int)(row / a.ny), (int)(row % a.ny), beta, wsm, acc);
+        xrow_warp<K, M1, PW, NCL, LCT, DEFER>(a, g, (int)(row / a.ny), (int)(row % a.ny), beta, alpha_prev, wsm, phase, acc);
     double v[1] = {acc};
     grid_reduce<1>(v, red_part, ticket, red_out);
 }

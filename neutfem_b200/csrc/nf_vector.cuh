@@ -17,6 +17,8 @@ struct CgState {
     double bnorm_sq;
     double rr_true;     // ||r||^2 (for the stopping test)
     double tmp[4];      // raw local sums of the last reduction (all-reduced across ranks in z-slab mode)
+    double alpha_prev;  // rows paths: step length of the last iteration whose x += alpha p is still pending (applied by the
+                        // next k_xrow from the p it reads anyway, or by k_x_pending once the iteration stops)
     int done;
     int iters;
     int breakdown;
@@ -39,7 +41,7 @@ __device__ inline void cg_init_fin(CgState *st, double tol, int pcg)
         st->done = (st->tmp[2] < st->tol_sq || st->tmp[1] == 0.0) ? 1 : 0;
     }
     st->pAp[0] = st->pAp[1] = st->pAp[2] = st->pAp[3] = 0.0;
-    st->beta = 0.0; st->iters = 0; st->breakdown = 0;
+    st->beta = 0.0; st->iters = 0; st->breakdown = 0; st->alpha_prev = 0.0;
 }
 
 __device__ inline void cg_update_fin(CgState *st, int pcg)
@@ -51,10 +53,26 @@ __device__ inline void cg_update_fin(CgState *st, int pcg)
     else { st->beta = num / st->rr; st->rr = num; }
 }
 
-__global__ void k_cg_finalize(CgState *st, int which, double tol, int pcg)
+// defer != 0 (rows paths): the x update of this iteration is pending, remember its step length (same expression as in the
+// updating kernel: bitwise the alpha that was applied to r)
+__global__ void k_cg_finalize(CgState *st, int which, double tol, int pcg, int defer)
 {
     if (which == 0) cg_init_fin(st, tol, pcg);
-    else if (!st->done) cg_update_fin(st, pcg);
+    else if (!st->done) {
+        if (defer) st->alpha_prev = st->rr / ((st->pAp[0] + st->pAp[1]) + (st->pAp[2] + st->pAp[3]));
+        cg_update_fin(st, pcg);
+    }
+}
+
+// x += alpha_prev p: the pending update of the rows paths, once the iteration has stopped (converged, broken down or out
+// of iterations). alpha_prev is reset by the next cg_init_fin.
+__global__ void __launch_bounds__(256) k_x_pending(double *__restrict__ x, const double *__restrict__ p, long long n,
+                                                   const CgState *st)
+{
+    const double alpha = st->alpha_prev;
+    if (alpha == 0.0) return;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        x[i] += alpha * p[i];
 }
 
 // ---- layout ---------------------------------------------------------------------------------------------------
@@ -157,7 +175,7 @@ __global__ void __launch_bounds__(256) k_pcg_init(const double *__restrict__ b, 
 {
     double acc[3] = {0.0, 0.0, 0.0};
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const double bv = b[i], rv = bv - Sx[i], zv = (double)minv[i] * rv;
+        const double bv = b[i], rv = bv - Sx[i], zv = jac_ld(minv + i) * rv;
         r[i] = rv; p[i] = zv;
         acc[0] += rv * zv; acc[1] += bv * bv; acc[2] += rv * rv;
     }
@@ -187,7 +205,7 @@ __global__ void __launch_bounds__(256) k_pcg_update(const double *__restrict__ p
         x[i] += alpha * p[i];
         const double rv = r[i] - alpha * Ap[i];
         r[i] = rv;
-        acc[0] += rv * rv * (double)minv[i];
+        acc[0] += rv * rv * jac_ld(minv + i);
         acc[1] += rv * rv;
     }
     __shared__ double out[2];
@@ -203,7 +221,7 @@ __global__ void __launch_bounds__(256) k_pcg_pupdate(const double *__restrict__ 
     if (st->done) return;
     const double beta = st->beta;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-        p[i] = (double)minv[i] * r[i] + beta * p[i];
+        p[i] = jac_ld(minv + i) * r[i] + beta * p[i];
 }
 
 // ---- outer iteration ----------------------------------------------------------------------------------------------
@@ -241,7 +259,7 @@ __global__ void __launch_bounds__(256) k_total_fission(const OuterArgs a, double
 
 // rhs_g = chi_g/k * total_fiss + sum_{g' != g} M_scatter[g' -> g] phi_g'        (NeutFEM.cpp:1713-1726)
 // adjoint: rhs_g = nsf_g/k * total + sum_{g' != g} M_scatter[g -> g'] phi_g'     (NeutFEM.cpp:1936-1950)
-// fixed source (src != nullptr): + SRC_g * mass weight
+// fixed source (src != nullptr): + int SRC_g phi_i (cell-wise constant source: only the mode-0 DOF of a cell sees it)
 __global__ void __launch_bounds__(256) k_group_rhs(const OuterArgs a, const double *__restrict__ tot, int g,
                                                    double inv_k, int adjoint, const double *__restrict__ src,
                                                    double *__restrict__ rhs)
@@ -258,7 +276,7 @@ __global__ void __launch_bounds__(256) k_group_rhs(const OuterArgs a, const doub
             const double sg = thr14(a.SigS[idx * a.ne + e]);
             if (sg != 0.0) s += sg * mw * a.phi[(size_t)gp * n + i];
         }
-        if (src) s += src[(size_t)g * a.ne + e] * mw;
+        if (src && mode == 0) s += src[(size_t)g * a.ne + e] * a.vol[e];     // load vector of a cell-wise constant source: int Q P_a = 0 for a != 0
         rhs[i] = s;
     }
 }
@@ -419,7 +437,7 @@ __global__ void k_build_jacobi(const JacobiArgs a)
     for (int mode = 0; mode < a.nloc; ++mode) {
         double dg = Sv * a.wC[mode];
         for (int d = 0; d < a.dim; ++d) dg += q[d] * a.cb[d][mode] + a.wface[d][mode] * face_sum[d];
-        a.minv[(size_t)mode * a.ne + e] = (jac_t)((dg > 0.0) ? 1.0 / dg : 1.0);
+        a.minv[(size_t)mode * a.ne + e] = jac_from_double((dg > 0.0) ? 1.0 / dg : 1.0);
     }
 }
 

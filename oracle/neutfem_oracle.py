@@ -48,12 +48,66 @@ DIRICHLET, NEUMANN, MIRROR, ROBIN, PERIODIC = range(5)
 
 
 def build_lib(force: bool = False) -> str:
-    """Compile oracle/fem_ref.c (gcc) into oracle/_build/liboracle_fem.so."""
+    """Compile oracle/fem_ref.c (gcc) into oracle/_build/liboracle_fem.so, and oracle/cg_lines.c (gcc -fopenmp; portable
+    x86-64 code, the .so travels to the GPU box) into oracle/_build/libcg_lines.so."""
+    os.makedirs(os.path.dirname(_LIB_PATH), exist_ok=True)
     src = os.path.join(_HERE, "fem_ref.c")
     if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
-        os.makedirs(os.path.dirname(_LIB_PATH), exist_ok=True)
         subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-fvisibility=hidden", "-o", _LIB_PATH, src, "-lm"])
+    src2 = os.path.join(_HERE, "cg_lines.c")
+    if force or not os.path.exists(_LINES_PATH) or os.path.getmtime(_LINES_PATH) < os.path.getmtime(src2):
+        subprocess.check_call(["gcc", "-O3", "-fopenmp", "-fPIC", "-shared", "-fvisibility=hidden", "-o", _LINES_PATH, src2, "-lm"])
     return _LIB_PATH
+
+
+_LINES_PATH = os.path.join(_HERE, "_build", "libcg_lines.so")
+_lines = None
+
+
+class LinesCG:
+    """ctypes face of oracle/cg_lines.c: the reference's inner solve (unpreconditioned CG from 0, src/solvers.cpp:577-636)
+    with A^-1 applied by exact per-line Thomas factorisations, OpenMP over the grid lines. 3-D meshes, RT_k-P_k."""
+
+    def __init__(self, hx, hy, hz, rt_order, p_order, dirichlet6):
+        global _lines
+        if _lines is None:
+            build_lib()
+            L = ctypes.CDLL(_LINES_PATH)
+            dp, ip = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int)
+            common = [ctypes.c_int] * 3 + [dp] * 3 + [ctypes.c_int] * 2 + [dp, dp, ip]
+            L.cgl_apply.argtypes = common + [dp, dp]
+            L.cgl_solve.argtypes = common + [dp, dp, ctypes.c_double, ctypes.c_int, dp]
+            L.cgl_solve.restype = ctypes.c_int
+            L.cgl_threads.restype = ctypes.c_int
+            _lines = L
+        self.hx, self.hy, self.hz = (np.ascontiguousarray(h, dtype=np.float64) for h in (hx, hy, hz))
+        self.k, self.m = int(rt_order), int(p_order)
+        self.fl = np.ascontiguousarray(dirichlet6, dtype=np.int32)       # [2*d + upper]
+        self.nloc = (min(self.k, self.m) + 1) ** 3
+
+    @staticmethod
+    def threads():
+        if _lines is None:
+            LinesCG(np.ones(1), np.ones(1), np.ones(1), 0, 0, np.zeros(6))
+        return int(_lines.cgl_threads())
+
+    def _args(self, D, SigR):
+        ip = ctypes.POINTER(ctypes.c_int)
+        return [self.hx.size, self.hy.size, self.hz.size, _dptr(self.hx), _dptr(self.hy), _dptr(self.hz), self.k, self.m,
+                _dptr(D), _dptr(SigR), self.fl.ctypes.data_as(ip)]
+
+    def apply(self, D, SigR, x):
+        D, SigR, x = (np.ascontiguousarray(a, dtype=np.float64) for a in (D, SigR, x))
+        y = np.empty_like(x)
+        _lines.cgl_apply(*self._args(D, SigR), _dptr(x), _dptr(y))
+        return y
+
+    def solve(self, D, SigR, b, tol, max_iter):
+        D, SigR, b = (np.ascontiguousarray(a, dtype=np.float64) for a in (D, SigR, b))
+        x = np.empty_like(b)
+        res = ctypes.c_double()
+        it = _lines.cgl_solve(*self._args(D, SigR), _dptr(b), _dptr(x), float(tol), int(max_iter), ctypes.byref(res))
+        return x, int(it), float(res.value)
 
 
 _lib = None

@@ -94,3 +94,30 @@ def test_order_clamp_and_defaults():
     assert (o.rt_order, o.p_order) == (1, 1)            # p forced down to rt (NeutFEM.cpp:149-169)
     assert np.all(o.D == 1.0) and np.all(o.SigR == 0.01) and np.all(o.Chi[:3] == 1.0) and np.all(o.Chi[3:] == 0.0)
     assert o.schur.solver_type == 0 and o.schur.tol == 1e-10   # SchurSolver keeps DIRECT_LU until set (solvers.cpp:67-76)
+
+
+@pytest.mark.parametrize("n,rt", [((5, 4, 3), 0), ((5, 4, 3), 1), ((4, 3, 3), 2)])
+def test_cg_lines_equals_oracle(n, rt):
+    """oracle/cg_lines.c (the multi-threaded CPU baseline of bench.py: reference CG + exact per-line Thomas solves for A^-1)
+    applies the same operator as the quadrature-assembled oracle (1e-13) and walks the same CG iterate sequence."""
+    from helpers import make_oracle, random_problem, relerr
+    from oracle.neutfem_oracle import CG, LinesCG, SchurSolverOracle
+    p = random_problem(7, 3, n, ng=1, bc="mixed")
+    o = make_oracle(p, rt, rt)
+    side = {3: 0, 4: 1, 6: 2, 5: 3, 1: 4, 2: 5}           # 3-D attribute -> [2*d + upper] (src/NeutFEM.cpp:2338-2347)
+    fl = np.zeros(6, dtype=np.int32)
+    for a, t, _ in p["bcs"]:
+        if t == 0:
+            fl[side[a]] = 1
+    lc = LinesCG(np.diff(p["xb"]), np.diff(p["yb"]), np.diff(p["zb"]), rt, rt, fl)
+    x = np.random.default_rng(1).uniform(0.5, 1.5, o.fes.n_Phi)
+    assert relerr(lc.apply(p["D"], p["SigR"], x), o.schur_product(0, x)) < 1e-13
+    b = np.random.default_rng(2).uniform(0.0, 1.0, o.fes.n_Phi)
+    s = SchurSolverOracle()
+    s.solver_type, s.tol, s.max_iter = CG, 1e-10, 3000
+    s.set_matrices(o.A[0], o.B, o.C[0])
+    ref = s.solve_implicit(b)
+    sol, it, res = lc.solve(p["D"], p["SigR"], b, 1e-10, 3000)
+    assert abs(it - s.last_iterations) <= 2 and res < 1e-10
+    assert relerr(sol, ref) < 1e-9
+    assert LinesCG.threads() >= 1
