@@ -39,7 +39,11 @@ enum { NF_DIRECT_LU = 0, NF_DIRECT_LDLT, NF_DIRECT_LLT, NF_CG, NF_CG_DIAG, NF_CG
  * ||r||^2 < tol^2 ||b||^2, solvers.cpp:577-636); FAST = Jacobi-preconditioned CG with warm start (the
  * preconditioner the reference's enum names but never reaches on the implicit path). */
 enum { NF_MODE_PARITY = 0, NF_MODE_FAST = 1 };
-enum { NF_ACCEL_NONE = 0, NF_ACCEL_CHEBYSHEV = 1 };
+/* outer-iteration accelerators: CHEBYSHEV = ChebyshevAccel(15, 0.98) exactly as the reference runs it (solvers.cpp:664-756);
+ * ANDERSON = type-II Anderson mixing with the parameters of the reference's AndersonAccel (m = 5, beta = 1, Tikhonov 1e-8,
+ * step clamp 0.3; solvers.cpp:772-891). The reference never instantiates that class and its formula returns the previous
+ * iterate (oracle/neutfem_oracle.py AndersonAccelReference): the standard formulation is implemented instead. Parity unpinned. */
+enum { NF_ACCEL_NONE = 0, NF_ACCEL_CHEBYSHEV = 1, NF_ACCEL_ANDERSON = 2 };
 
 enum { NF_OK = 0, NF_ERR_ARG = -1, NF_ERR_CUDA = -2, NF_ERR_STATE = -3, NF_ERR_NCCL = -4, NF_ERR_NODEVICE = -5 };
 
@@ -80,6 +84,12 @@ NF_API int nf_set_bc(nf_ctx *ctx, int attr, int bc_type, double value);
 /* NeutFEM::SetLinearSolver + SetTolerance (src/NeutFEM.cpp:322-335). */
 NF_API int nf_set_solver(nf_ctx *ctx, int solver_type, double tol_keff, double tol_flux, int max_outer, int max_inner,
                   int mode);
+
+/* Tuning knobs without a reference counterpart (fast mode only; parity mode ignores them):
+ *   "inner_reduction" eta in [0, 1): inexact inner solves -- a group solve also stops once its residual is eta times the
+ *                     residual it started from (warm start); 0 = off (stop on tol_flux ||b|| only, like the reference);
+ *   "anderson_depth"  history depth of NF_ACCEL_ANDERSON, 1..5 (memory: 2 depth + 2 vectors of ng * n_Phi). */
+NF_API int nf_set_option(nf_ctx *ctx, const char *key, double value);
 
 /* ---- operators -------------------------------------------------------------------------------------------
  * Host->device snapshot of the cross-sections (the reference's public Vec members, NeutFEM.hpp:373-379, that

@@ -20,7 +20,7 @@ LIB_PATH = os.environ.get("NF_LIB", os.path.join(_LIBDIR, "libneutfem_b200.so"))
 BC_DIRICHLET, BC_NEUMANN, BC_MIRROR, BC_ROBIN, BC_PERIODIC = range(5)
 (DIRECT_LU, DIRECT_LDLT, DIRECT_LLT, CG, CG_DIAG, CG_ICHOL, BICGSTAB, BICGSTAB_DIAG, BICGSTAB_ILU, LCG) = range(10)
 MODE_PARITY, MODE_FAST = 0, 1
-ACCEL_NONE, ACCEL_CHEBYSHEV = 0, 1
+ACCEL_NONE, ACCEL_CHEBYSHEV, ACCEL_ANDERSON = 0, 1, 2
 
 EXPORTED = [
     "nf_create", "nf_destroy", "nf_last_error", "nf_get_sizes", "nf_set_bc", "nf_set_solver", "nf_upload_xs",
@@ -28,7 +28,7 @@ EXPORTED = [
     "nf_get_current", "nf_solve_keff", "nf_solve_adjoint", "nf_solve_source", "nf_get_last_keff", "nf_schur_apply",
     "nf_schur_solve", "nf_current_from_flux", "nf_get_diagonal_cache", "nf_comm_unique_id", "nf_comm_init",
     "nf_create_slab",
-    "nf_version", "nf_kernel_launch_count", "nf_time_kernels",
+    "nf_version", "nf_kernel_launch_count", "nf_time_kernels", "nf_set_option",
 ]
 
 
@@ -71,6 +71,7 @@ def load():
     L.nf_set_bc.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_double]
     L.nf_set_solver.argtypes = [vp, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int]
     L.nf_upload_xs.argtypes = [vp, dp, dp, dp, dp, dp, dp]
+    L.nf_set_option.argtypes = [vp, ctypes.c_char_p, ctypes.c_double]
     L.nf_build.argtypes = [vp]
     L.nf_build_diagonal_cache.argtypes = [vp]
     L.nf_set_flux.argtypes = [vp, dp]
@@ -149,6 +150,9 @@ class Context:
     def set_solver(self, solver_type=-1, tol_keff=-1.0, tol_flux=-1.0, max_outer=-1, max_inner=-1, mode=-1):
         self._ck(self._L.nf_set_solver(self._h, int(solver_type), float(tol_keff), float(tol_flux), int(max_outer),
                                        int(max_inner), int(mode)), "nf_set_solver")
+
+    def set_option(self, key, value):
+        self._ck(self._L.nf_set_option(self._h, key.encode(), float(value)), "nf_set_option")
 
     def upload_xs(self, D=None, SigR=None, NSF=None, Chi=None, SigS=None, SRC=None):
         arrs = [_f64(a) for a in (D, SigR, NSF, Chi, SigS, SRC)]

@@ -169,6 +169,14 @@ public:
         else throw std::runtime_error("set_mode: expected 'parity' or 'fast'");
         push_solver();
     }
+    void SetAccelerator(const std::string &a)
+    {
+        if (a == "none") accel_ = NF_ACCEL_NONE;
+        else if (a == "chebyshev") accel_ = NF_ACCEL_CHEBYSHEV;
+        else if (a == "anderson") accel_ = NF_ACCEL_ANDERSON;
+        else throw std::runtime_error("set_accelerator: expected 'none', 'chebyshev' or 'anderson'");
+    }
+    void SetOption(const std::string &key, double value) { check(nf_set_option(ctx_, key.c_str(), value), "nf_set_option"); }
     void ResetFlux()
     {
         std::fill(Phi_.begin(), Phi_.end(), 1.0);
@@ -196,7 +204,7 @@ public:
     {
         Log(VerbosityLevel::NORMAL, "\n=== CALCUL DE K-EFFECTIF (DIRECT) ===");
         require_built("SolveKeff");
-        if (use_cmfd) Log(VerbosityLevel::NORMAL, "  Note: CMFD hors perimetre de ce portage, acceleration Chebyshev utilisee");
+        if (use_cmfd) Log(VerbosityLevel::NORMAL, "  Note: CMFD non porte (SURVEY 8(f).3); acceleration externe = ", accel_ == NF_ACCEL_ANDERSON ? "Anderson" : "Chebyshev");
         double k0 = -1.0;
         if (use_coarse && !factors.empty()) {
             auto r = SolveCoarse(factors);
@@ -206,7 +214,7 @@ public:
         }
         check(nf_set_flux(ctx_, Phi_.data()), "nf_set_flux");
         double k = 0.0;
-        check(nf_solve_keff(ctx_, use_diag ? 1 : 0, NF_ACCEL_CHEBYSHEV, k0, &k, &stats_), "nf_solve_keff");
+        check(nf_solve_keff(ctx_, use_diag ? 1 : 0, accel_, k0, &k, &stats_), "nf_solve_keff");
         check(nf_get_flux(ctx_, Phi_.data()), "nf_get_flux");
         has_valid_ = true; last_k_ = k; J_valid_ = false;
         if (stats_.converged) Log(VerbosityLevel::NORMAL, "  Convergence en ", stats_.outer_iterations, " iterations");
@@ -590,7 +598,7 @@ public:
     LinearSolverType solver_ = LinearSolverType::BICGSTAB;      // NeutFEM.cpp:126
     bool solver_set_ = false, tol_set_ = false, built_ = false, has_valid_ = false, has_valid_adj_ = false, J_valid_ = false;
     double tol_keff_ = 1e-5, tol_flux_ = 1e-5, tol_L2_ = 1e-5, cmfd_relax_ = 1.0;
-    int max_outer_ = 200, max_inner_ = 1000, mode_ = NF_MODE_PARITY;
+    int max_outer_ = 200, max_inner_ = 1000, mode_ = NF_MODE_PARITY, accel_ = NF_ACCEL_CHEBYSHEV;
     VerbosityLevel verbosity_ = VerbosityLevel::NORMAL;
     double last_k_ = 1.0, last_k_adj_ = 1.0;
     nf_stats stats_{}, coarse_stats_{};
@@ -692,6 +700,9 @@ PYBIND11_MODULE(_neutfem_eigen, m)
         .def("get_current", &NeutFEM::get_current, py::arg("adjoint") = false, "J = -A^-1 B^T phi, [ng * n_J] reference numbering (extension)")
         .def("get_stats", &NeutFEM::get_stats, "iteration counts and device timings of the last solve (extension)")
         .def("set_mode", &NeutFEM::SetMode, py::arg("mode"), "'parity' (reference CG) or 'fast' (Jacobi PCG, warm start) (extension)")
+        .def("set_accelerator", &NeutFEM::SetAccelerator, py::arg("name"),
+             "outer-iteration accelerator of SolveKeff: 'chebyshev' (the reference's, default), 'anderson' or 'none' (extension)")
+        .def("set_option", &NeutFEM::SetOption, py::arg("key"), py::arg("value"), "nf_set_option: 'inner_reduction', 'anderson_depth' (extension)")
         .def("reset_flux", &NeutFEM::ResetFlux)
         .def("GetNumElements", [](const NeutFEM &s) { return s.ne_; })
         .def("GetNumGroups", [](const NeutFEM &s) { return s.nphi_ / s.ne_; })      // sic: DOFs per cell (wrapper.cpp:953-955)

@@ -48,7 +48,7 @@ struct nf_ctx {
     CgState *d_cg = nullptr;
     double *d_part = nullptr; unsigned *d_ticket = nullptr; double *d_scal = nullptr;
     double *h_scal = nullptr; CgState *h_cg = nullptr;     // pinned
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, evp[2] = {nullptr, nullptr};
     std::map<int, int> bc_types; std::map<int, double> bc_values;
     int solver_type = NF_BICGSTAB; int mode = NF_MODE_PARITY;
     double tol_keff = 1e-5, tol_flux = 1e-5; int max_outer = 200, max_inner = 1000;
@@ -74,7 +74,11 @@ struct nf_ctx {
     int fused = -1;                        // -1: not yet decided, 0: separate kernels, 2: hybrid, 3: rows, 5: rows on a z-slab rank
     double *d_zs = nullptr;                // z-forward intermediates
     RowGeom rg; int xrow_grid = 0, ycol_grid = 0;   // register-resident x-row / y-column kernels (nf_rows.cuh)
+    int ycol3 = 1;                         // 1: three-phase y-column kernel (k_ycol3), 0: k_ycol (NF_YCOL=0, development knob)
     int zf_grid = 0, zb_grid = 0;          // whole waves of resident CTAs of the z marching kernels
+    double inner_eta = 0.0;                // fast mode: inexact inner solves (option "inner_reduction"), 0 = off
+    int and_m = kAndM;                     // Anderson depth (option "anderson_depth", 1..kAndM)
+    double *d_and[2 * kAndM + 2] = {nullptr};   // Anderson history: dF[0..m), dG[0..m), f_prev, g_prev (allocated on first use)
     cudaStream_t stream2 = nullptr;        // z-slab ranks: side stream (z forward substitution + all-gather beside the y columns)
     cudaEvent_t evx = nullptr, evz = nullptr;
 };
@@ -376,25 +380,29 @@ static int rows_prepare_t(nf_ctx *c)
     if (xcap > 0) per_sm = std::min(per_sm, xcap);
     const long long nrows = (long long)c->ny * c->nz;
     c->xrow_grid = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(kRedBlocks, (long long)per_sm * c->sm_count), (nrows + kXW - 1) / kXW));
-    if (ynt == 128) {
+    c->ycol3 = env_int("NF_YCOL", 3) != 0;
+    const size_t ysmem3 = (size_t)(2 * c->rg.LcY + 4) * ynt * sizeof(double2);
+    if (ysmem3 + 2048 > c->smem_optin) c->ycol3 = 0;
+    if (ynt != 128) NF_FAIL(c, NF_ERR_STATE, "y-column kernels are built for 128-thread CTAs");
+    if (c->ycol3) {
+        CU(c, cudaFuncSetAttribute(k_ycol3<K, M1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ysmem3));
+        CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ycol3<K, M1, 128>, 128, ysmem3));
+    } else {
         CU(c, cudaFuncSetAttribute(k_ycol<K, M1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ysmem));
         CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ycol<K, M1, 128>, 128, ysmem));
-    } else {
-        CU(c, cudaFuncSetAttribute(k_ycol<K, M1, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ysmem));
-        CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ycol<K, M1, 256>, 256, ysmem));
     }
     const long long nitems = (long long)c->nz * ((c->nx + c->rg.colsY - 1) / c->rg.colsY) * c->nt;
     c->ycol_grid = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(kRedBlocks, (long long)std::max(per_sm, 1) * c->sm_count), nitems));
     // the z marching kernels are persistent grid-stride loops: whole waves of resident CTAs only (no ragged last wave)
     int occ_zf = 0, occ_zb = 0;
     if (c->slab) {
-        CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_zf, k_zfwd<K, M1, true>, 128, 0));
-        CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_zb, k_slab_back_update<K, M1>, 128, 0));
+        CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_zf, k_zfwd2<K, M1, true>, 128, 0));
+        CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_zb, k_zback2<K, M1, true>, 128, 0));
     } else {
-        CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_zf, k_zfwd<K, M1, false>, 128, 0));
-        CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_zb, k_zback_update<K, M1, true>, 128, 0));
+        CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_zf, k_zfwd2<K, M1, false>, 128, 0));
+        CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_zb, k_zback2<K, M1, false>, 128, 0));
     }
-    const long long zitems = (long long)c->ny * c->nt * ((c->nx + 31) / 32);
+    const long long zitems = (long long)c->ny * c->nt * ((c->nx + 63) / 64);      // a warp owns 64 adjacent x positions
     auto wave_grid = [&](int occ) {
         occ = std::max(occ, 1);
         const int waves = std::max(1, kRedBlocks / (occ * c->sm_count));
@@ -425,8 +433,10 @@ static int rows_launch_t(nf_ctx *c, const FusedArgs &a, int which)
     if (which & 2) {
         const int ynt = 32 * c->rg.warpsY;
         const size_t ysmem = (size_t)(c->rg.LcY + 1 + 5) * ynt * sizeof(double2);
-        if (ynt == 128) LAUNCH(c, (k_ycol<K, M1, 128>), c->ycol_grid, 128, ysmem, a, c->rg, c->d_part + (size_t)1 * kRedBlocks, c->d_ticket + 1, &c->d_cg->pAp[1]);
-        else LAUNCH(c, (k_ycol<K, M1, 256>), c->ycol_grid, 256, ysmem, a, c->rg, c->d_part + (size_t)1 * kRedBlocks, c->d_ticket + 1, &c->d_cg->pAp[1]);
+        const size_t ysmem3 = (size_t)(2 * c->rg.LcY + 4) * ynt * sizeof(double2);
+        double *ypart = c->d_part + (size_t)1 * kRedBlocks;
+        if (c->ycol3) LAUNCH(c, (k_ycol3<K, M1, 128>), c->ycol_grid, 128, ysmem3, a, c->rg, ypart, c->d_ticket + 1, &c->d_cg->pAp[1]);
+        else LAUNCH(c, (k_ycol<K, M1, 128>), c->ycol_grid, 128, ysmem, a, c->rg, ypart, c->d_ticket + 1, &c->d_cg->pAp[1]);
     }
     CU(c, cudaGetLastError());
     return NF_OK;
@@ -515,8 +525,8 @@ static int fused_launch_t(nf_ctx *c, const FusedArgs &a, int which, bool defer)
 {
     if (!c->zf_grid) {      // hybrid path: grids of whole waves, per context (the occupancy depends on the device)
         int occ_zf = 0, occ_zb = 0;
-        CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_zf, k_zfwd<K, M1, false>, 128, 0));
-        CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_zb, k_zback_update<K, M1, false>, 128, 0));
+        CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_zf, k_zfwd<K, M1>, 128, 0));
+        CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_zb, k_zback_update<K, M1>, 128, 0));
         const long long zitems = (long long)c->ny * c->nt * ((c->nx + 31) / 32);
         auto wave_grid = [&](int occ) {
             occ = std::max(occ, 1);
@@ -525,11 +535,13 @@ static int fused_launch_t(nf_ctx *c, const FusedArgs &a, int which, bool defer)
         };
         c->zf_grid = wave_grid(occ_zf); c->zb_grid = wave_grid(occ_zb);
     }
-    if (which & 4)
-        LAUNCH(c, (k_zfwd<K, M1, false>), c->zf_grid, 128, 0, a, c->d_part + (size_t)2 * kRedBlocks, c->d_ticket + 2, &c->d_cg->pAp[2]);
+    if (which & 4) {
+        if (defer) LAUNCH(c, (k_zfwd2<K, M1, false>), c->zf_grid, 128, 0, a, c->d_part + (size_t)2 * kRedBlocks, c->d_ticket + 2, &c->d_cg->pAp[2]);
+        else LAUNCH(c, (k_zfwd<K, M1>), c->zf_grid, 128, 0, a, c->d_part + (size_t)2 * kRedBlocks, c->d_ticket + 2, &c->d_cg->pAp[2]);
+    }
     if (which & 2) {
-        if (defer) LAUNCH(c, (k_zback_update<K, M1, true>), c->zb_grid, 128, 0, a);
-        else LAUNCH(c, (k_zback_update<K, M1, false>), c->zb_grid, 128, 0, a);
+        if (defer) LAUNCH(c, (k_zback2<K, M1, false>), c->zb_grid, 128, 0, a, (const double *)nullptr);
+        else LAUNCH(c, (k_zback_update<K, M1>), c->zb_grid, 128, 0, a);
     }
     CU(c, cudaGetLastError());
     return NF_OK;
@@ -558,7 +570,7 @@ static int slab_iteration_t(nf_ctx *c, const FusedArgs &fa, int g, double tol, i
         zs = c->stream2;
     } else if (which & 2) { int r = rows_launch_t<K, M1>(c, fa, 2); if (r) return r; }
     if (which & 4) {
-        k_zfwd<K, M1, true><<<c->zf_grid, 128, 0, zs>>>(fa, c->d_part + (size_t)2 * kRedBlocks, c->d_ticket + 2, &c->d_cg->pAp[2]);
+        k_zfwd2<K, M1, true><<<c->zf_grid, 128, 0, zs>>>(fa, c->d_part + (size_t)2 * kRedBlocks, c->d_ticket + 2, &c->d_cg->pAp[2]);
         ++g_launches; ++c->launches_call;
         NC(c, ncclAllGather(c->d_vG, c->d_vGall, (size_t)2 * c->nt * c->nxy, ncclDouble, c->comm, zs));
     }
@@ -577,9 +589,9 @@ static int slab_iteration_t(nf_ctx *c, const FusedArgs &fa, int g, double tol, i
         a.red_part = c->d_part + (size_t)3 * kRedBlocks; a.ticket = c->d_ticket + 3;
         LAUNCH(c, (k_slab_iface<K, M1>), (int)std::max<long long>(1, std::min<long long>(kRedBlocks, (c->nxy * c->nt + 127) / 128)), 128, 0, a, u);
         { int r = allreduce_sum(c, c->d_cg->pAp, 4); if (r) return r; }
-        LAUNCH(c, (k_slab_back_update<K, M1>), c->zb_grid, 128, 0, fa, u);
+        LAUNCH(c, (k_zback2<K, M1, true>), c->zb_grid, 128, 0, fa, (const double *)c->d_lam);
         { int r = allreduce_sum(c, c->d_cg->tmp, 2); if (r) return r; }
-        LAUNCH(c, k_cg_finalize, 1, 1, 0, c->d_cg, 1, tol, fa.pcg, 1);
+        LAUNCH(c, k_cg_finalize, 1, 1, 0, c->d_cg, 1, tol, fa.pcg, 1, 0.0);
     }
     CU(c, cudaGetLastError());
     return NF_OK;
@@ -690,12 +702,13 @@ static int create_impl(nf_ctx **out, int rt_order, int p_order, int ng, const do
     const size_t rowpad = (size_t)kRowPad * c->nx;           // the y-column kernels read (and mask) a few rows past the end
     CK(dalloc(c, &c->d_p, np + rowpad)); CK(dalloc(c, &c->d_Ap, np + rowpad));
     CKU(cudaMemset(c->d_p + np, 0, rowpad * sizeof(double))); CKU(cudaMemset(c->d_Ap + np, 0, rowpad * sizeof(double)));
-    CK(dalloc(c, &c->d_cg, 1)); CK(dalloc(c, &c->d_part, (size_t)8 * kRedBlocks)); CK(dalloc(c, &c->d_ticket, 16));
-    CK(dalloc(c, &c->d_scal, 16));
+    CK(dalloc(c, &c->d_cg, 1)); CK(dalloc(c, &c->d_part, (size_t)32 * kRedBlocks)); CK(dalloc(c, &c->d_ticket, 16));
+    CK(dalloc(c, &c->d_scal, 64));
     CKU(cudaMemset(c->d_ticket, 0, 16 * sizeof(unsigned)));
     CKU(cudaMemset(c->d_cg, 0, sizeof(CgState)));
-    CKU(cudaMallocHost((void **)&c->h_scal, 16 * sizeof(double)));
-    CKU(cudaMallocHost((void **)&c->h_cg, sizeof(CgState)));
+    CKU(cudaMallocHost((void **)&c->h_scal, 64 * sizeof(double)));
+    CKU(cudaMallocHost((void **)&c->h_cg, 2 * sizeof(CgState)));
+    CKU(cudaEventCreateWithFlags(&c->evp[0], cudaEventDisableTiming)); CKU(cudaEventCreateWithFlags(&c->evp[1], cudaEventDisableTiming));
     c->d_minv.assign(G * 3, nullptr); c->d_u.assign(G * 3, nullptr); c->d_u_base.assign(G * 3, nullptr);
     for (size_t g = 0; g < G; ++g)
         for (int d = 0; d < c->dim; ++d) {
@@ -808,6 +821,7 @@ int nf_destroy(nf_ctx *c)
     for (int d = 0; d < 3; ++d) if (c->d_iFx[d]) cudaFree(c->d_iFx[d]);
     for (double *p : c->d_s0) if (p) cudaFree(p);
     for (double *p : {c->d_E, c->d_Eall, c->d_vG, c->d_vGall, c->d_lam, c->d_zs}) if (p) cudaFree(p);
+    for (double *p : c->d_and) if (p) cudaFree(p);
     if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
     for (cudaEvent_t e : {c->evx, c->evz}) if (e) cudaEventDestroy(e);
     if (c->comm) ncclCommDestroy(c->comm);
@@ -817,7 +831,7 @@ int nf_destroy(nf_ctx *c)
     if (c->d_ticket) cudaFree(c->d_ticket);
     if (c->h_scal) cudaFreeHost(c->h_scal);
     if (c->h_cg) cudaFreeHost(c->h_cg);
-    for (cudaEvent_t e : {c->ev0, c->ev1, c->ev2, c->ev3}) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : {c->ev0, c->ev1, c->ev2, c->ev3, c->evp[0], c->evp[1]}) if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return NF_OK;
@@ -853,6 +867,15 @@ int nf_set_solver(nf_ctx *c, int solver_type, double tol_keff, double tol_flux, 
     if (max_inner > 0) { c->max_inner = max_inner; c->inner_max = max_inner; }
     if (mode == NF_MODE_PARITY || mode == NF_MODE_FAST) c->mode = mode;
     return NF_OK;
+}
+
+int nf_set_option(nf_ctx *c, const char *key, double value)
+{
+    if (!c || !key) return NF_ERR_ARG;
+    const std::string k(key);
+    if (k == "inner_reduction") { if (value < 0.0 || value >= 1.0) NF_FAIL(c, NF_ERR_ARG, "inner_reduction must be in [0, 1)"); c->inner_eta = value; return NF_OK; }
+    if (k == "anderson_depth") { if (value < 1 || value > kAndM) NF_FAIL(c, NF_ERR_ARG, "anderson_depth must be in 1..%d", kAndM); c->and_m = (int)value; return NF_OK; }
+    NF_FAIL(c, NF_ERR_ARG, "nf_set_option: unknown option '%s'", key);
 }
 
 int nf_upload_xs(nf_ctx *c, const double *D, const double *SigR, const double *NSF, const double *Chi, const double *SigS,
@@ -1035,6 +1058,7 @@ static int solve_group(nf_ctx *c, int g, const double *b, double *x, int *iters_
     if (direct) { tol = std::min(tol, 1e-13); maxit = std::max(maxit, (int)std::min<long long>(20000, 4 * n_glob + 100)); }
     if (fast || direct) { int r = build_jacobi(c); if (r) return r; }
     const bool pcg = fast || direct;
+    const double eta = (fast && !direct) ? c->inner_eta : 0.0;
     const int fin = c->slab ? 0 : 1;        // scalar recurrences inside the reducing kernel unless ranks must be summed first
     const jac_t *jac = pcg ? c->d_jac + (size_t)g * c->nphi : nullptr;
     CU(c, cudaEventRecord(c->ev2, c->stream));
@@ -1044,21 +1068,24 @@ static int solve_group(nf_ctx *c, int g, const double *b, double *x, int *iters_
         if (!fast) LAUNCH(c, k_fill, blocks, 256, 0, x, n, 0.0);      // "direct": x0 = 0
         { int r = apply_schur(c, g, x, c->d_Ap, false); if (r) return r; }
         LAUNCH(c, k_pcg_init, blocks, 256, 0, b, c->d_Ap, jac, c->d_r, c->d_p, n, tol, c->d_cg, c->d_part + 4 * kRedBlocks,
-               c->d_ticket + 4, fin);
+               c->d_ticket + 4, fin, eta);
     }
     if (!fin) {
         { int r = allreduce_sum(c, c->d_cg->tmp, 3); if (r) return r; }
-        LAUNCH(c, k_cg_finalize, 1, 1, 0, c->d_cg, 0, tol, pcg ? 1 : 0, 0);
+        LAUNCH(c, k_cg_finalize, 1, 1, 0, c->d_cg, 0, tol, pcg ? 1 : 0, 0, eta);
     }
     { int r = fused_setup(c); if (r) return r; }
     const bool hybrid = (c->fused == 2), rows = (c->fused == 3), slabrows = (c->fused == 5);
     FusedArgs fa;
     if (hybrid || rows || slabrows) fill_fused_args(c, fa, g, x, jac);
-    // poll the device-side done flag every few iterations; iterations after convergence are no-ops on the device
-    const double est_us = (double)n_glob / std::max(1, c->nranks) * 160.0 / 6.0e6 + 15.0;
-    int poll = (int)std::max(1.0, std::min(16.0, 200.0 / est_us));
-    int k = 0;
-    bool done = false;
+    // The device-side done flag is polled every `poll` iterations, ONE CHUNK BEHIND: the state of chunk j is copied to pinned
+    // memory asynchronously and only waited for after chunk j+1 has been queued, so the GPU never idles on the host round
+    // trip (at the bench size a blocking poll per iteration cost 3.4 % of the solve). Iterations after convergence are no-ops
+    // on the device (every kernel returns on st->done), so the extra chunk costs a few empty launches.
+    const double est_us = (double)n_glob / std::max(1, c->nranks) * 110.0 / 6.0e6 + 15.0;
+    const int poll = (int)std::max(2.0, std::min(16.0, 400.0 / est_us));
+    int k = 0, slot = 0;
+    bool done = false, pending = false;
     while (k < maxit && !done) {
         const int chunk = std::min(poll, maxit - k);
         for (int j = 0; j < chunk; ++j) {
@@ -1084,18 +1111,24 @@ static int solve_group(nf_ctx *c, int g, const double *b, double *x, int *iters_
             else LAUNCH(c, k_pcg_update, blocks, 256, 0, c->d_p, c->d_Ap, jac, x, c->d_r, n, c->d_cg, c->d_part + 4 * kRedBlocks, c->d_ticket + 4, fin);
             if (!fin) {
                 { int r = allreduce_sum(c, c->d_cg->tmp, 2); if (r) return r; }
-                LAUNCH(c, k_cg_finalize, 1, 1, 0, c->d_cg, 1, tol, pcg ? 1 : 0, 0);
+                LAUNCH(c, k_cg_finalize, 1, 1, 0, c->d_cg, 1, tol, pcg ? 1 : 0, 0, 0.0);
             }
             if (!pcg) LAUNCH(c, k_cg_pupdate, blocks, 256, 0, c->d_r, c->d_p, n, c->d_cg);
             else LAUNCH(c, k_pcg_pupdate, blocks, 256, 0, c->d_r, jac, c->d_p, n, c->d_cg);
         }
         k += chunk;
-        CU(c, cudaMemcpyAsync(c->h_cg, c->d_cg, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
-        CU(c, cudaStreamSynchronize(c->stream));
-        done = c->h_cg->done != 0;
+        CU(c, cudaMemcpyAsync(c->h_cg + slot, c->d_cg, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaEventRecord(c->evp[slot], c->stream));
+        if (pending) {
+            CU(c, cudaEventSynchronize(c->evp[slot ^ 1]));
+            done = c->h_cg[slot ^ 1].done != 0;
+        }
+        pending = true;
+        slot ^= 1;
     }
     // rows paths: the x update of the last iteration is still pending (x += alpha_prev p)
     if (rows || slabrows) LAUNCH(c, k_x_pending, blocks, 256, 0, x, c->d_p, n, c->d_cg);
+    CU(c, cudaMemcpyAsync(c->h_cg, c->d_cg, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaEventRecord(c->ev3, c->stream));
     CU(c, cudaEventSynchronize(c->ev3));
     float ms = 0.f;
@@ -1146,6 +1179,20 @@ static int power_iteration(nf_ctx *c, bool adjoint, int use_diag, int accel, dou
     OuterArgs oa;
     fill_outer(c, oa, phi);
     const int blocks = ew_blocks(np), blocks_all = ew_blocks(ntot);
+    // Anderson mixing: history of 2 m + 2 vectors of ng * n_phi, allocated on first use (at the full bench mesh this
+    // only fits on z-slab ranks)
+    AndersonArgs aa;
+    memset(&aa, 0, sizeof(aa));
+    int and_count = 0;
+    const int and_m = std::max(1, std::min(c->and_m, kAndM));
+    if (accel == NF_ACCEL_ANDERSON) {
+        for (int j = 0; j < 2 * kAndM + 2; ++j) {
+            const bool need = (j >= 2 * kAndM) || (j % kAndM) < and_m;
+            if (need && !c->d_and[j]) { int r = dalloc(c, &c->d_and[j], (size_t)ntot); if (r) return r; }
+        }
+        for (int j = 0; j < kAndM; ++j) { aa.dF[j] = c->d_and[j]; aa.dG[j] = c->d_and[kAndM + j]; }
+        aa.fprev = c->d_and[2 * kAndM]; aa.gprev = c->d_and[2 * kAndM + 1];
+    }
     for (int it = 0; it < c->max_outer; ++it) {
         CU(c, cudaMemcpyAsync(c->d_old, phi, ntot * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
         LAUNCH(c, k_total_fission, blocks, 256, 0, oa, c->d_tot, adjoint ? 1 : 0, c->d_part + 5 * kRedBlocks, c->d_ticket + 5, c->d_scal + 0);
@@ -1180,6 +1227,52 @@ static int power_iteration(nf_ctx *c, bool adjoint, int use_diag, int accel, dou
         int step = -1; double ca = 0.0, cb = 0.0;
         if (accel == NF_ACCEL_CHEBYSHEV && it >= cheb_from) cheb.next(step, ca, cb);
         LAUNCH(c, k_scale_chebyshev, blocks_all, 256, 0, phi, c->d_h0, c->d_h1, ntot, scale, step, ca, cb);
+        if (accel == NF_ACCEL_ANDERSON && it >= cheb_from) {
+            // x = d_old (the iterate this outer iteration started from), g = phi (normalised result)
+            aa.newest = (and_count > 0) ? (and_count - 1) % and_m : -1;
+            aa.ncol = std::min(and_count, and_m);
+            LAUNCH(c, k_and_push, blocks_all, 256, 0, aa, (const double *)phi, (const double *)c->d_old, ntot);
+            ++and_count;
+            if (aa.ncol > 0) {
+                constexpr int NV = kAndM * (kAndM + 1) / 2 + kAndM;
+                LAUNCH(c, k_and_gram, blocks_all, 256, 0, aa, ntot, c->d_part + 8 * kRedBlocks, c->d_ticket + 6, c->d_scal + 16);
+                { int r = allreduce_sum(c, c->d_scal + 16, NV); if (r) return r; }
+                CU(c, cudaMemcpyAsync(c->h_scal + 16, c->d_scal + 16, NV * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+                CU(c, cudaStreamSynchronize(c->stream));
+                // normal equations (dF^T dF + reg * max diag * I) gamma = dF^T f, solved by Gaussian elimination (<= 5 x 5, SPD)
+                const int m = aa.ncol;
+                double A[kAndM][kAndM], b[kAndM];
+                int q = 0;
+                for (int r = 0; r < kAndM; ++r)
+                    for (int j = r; j < kAndM; ++j) { A[r][j] = A[j][r] = c->h_scal[16 + q]; ++q; }
+                for (int j = 0; j < kAndM; ++j) b[j] = c->h_scal[16 + q + j];
+                double dmax = 0.0;
+                for (int j = 0; j < m; ++j) dmax = std::max(dmax, A[j][j]);
+                for (int j = 0; j < m; ++j) A[j][j] += 1e-8 * std::max(dmax, 1e-300);
+                for (int k2 = 0; k2 < m; ++k2)
+                    for (int r = k2 + 1; r < m; ++r) {
+                        const double l = A[r][k2] / A[k2][k2];
+                        for (int j = k2; j < m; ++j) A[r][j] -= l * A[k2][j];
+                        b[r] -= l * b[k2];
+                    }
+                AndersonGamma gm;
+                memset(&gm, 0, sizeof(gm));
+                for (int r = m - 1; r >= 0; --r) {
+                    double v = b[r];
+                    for (int j = r + 1; j < m; ++j) v -= A[r][j] * gm.g[j];
+                    gm.g[r] = v / A[r][r];
+                }
+                LAUNCH(c, k_and_corr, blocks_all, 256, 0, aa, gm, (const double *)phi, c->d_tmp, ntot, c->d_part + 8 * kRedBlocks,
+                       c->d_ticket + 6, c->d_scal + 40);
+                { int r = allreduce_sum(c, c->d_scal + 40, 2); if (r) return r; }
+                CU(c, cudaMemcpyAsync(c->h_scal + 40, c->d_scal + 40, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+                CU(c, cudaStreamSynchronize(c->stream));
+                const double cn = std::sqrt(c->h_scal[40]), gn = std::sqrt(c->h_scal[41]);
+                double sc = 1.0;
+                if (gn > 0 && cn / gn > 0.3) sc = 0.3 * gn / cn;                     // relative step clamp
+                LAUNCH(c, k_axpy, blocks_all, 256, 0, phi, (const double *)c->d_tmp, ntot, -sc);
+            }
+        }
         if (st) { st->outer_iterations = it + 1; st->last_dk = diff_k; st->last_dphi = diff_flux; }
         const bool conv = diff_flux < c->tol_flux && (!check_k || diff_k < c->tol_keff);
         if (conv) { if (st) st->converged = 1; break; }
@@ -1425,7 +1518,7 @@ int nf_time_kernels(nf_ctx *c, int g, int reps, int fast, double *ms_out)
     LAUNCH(c, k_fill, blocks, 256, 0, c->d_rhs, n, 1.0);
     const int fin = c->slab ? 0 : 1;
     LAUNCH(c, k_cg_init, blocks, 256, 0, c->d_rhs, c->d_tot, c->d_r, c->d_p, n, 0.0, c->d_cg, c->d_part + 4 * kRedBlocks, c->d_ticket + 4, fin);
-    if (!fin) { { int r = allreduce_sum(c, c->d_cg->tmp, 3); if (r) return r; } LAUNCH(c, k_cg_finalize, 1, 1, 0, c->d_cg, 0, 0.0, 0, 0); }
+    if (!fin) { { int r = allreduce_sum(c, c->d_cg->tmp, 3); if (r) return r; } LAUNCH(c, k_cg_finalize, 1, 1, 0, c->d_cg, 0, 0.0, 0, 0, 0.0); }
     for (int i = 0; i < 16; ++i) ms_out[i] = 0.0;
     auto iteration = [&](int mask, bool upd, bool pupd) -> int {
         if (mask) { int r = apply_schur(c, g, c->d_p, c->d_Ap, true, mask); if (r) return r; }
@@ -1433,7 +1526,7 @@ int nf_time_kernels(nf_ctx *c, int g, int reps, int fast, double *ms_out)
             if (!fin) { int r = allreduce_sum(c, c->d_cg->pAp, 4); if (r) return r; }
             if (!fast) LAUNCH(c, k_cg_update, blocks, 256, 0, c->d_p, c->d_Ap, c->d_tot, c->d_r, n, c->d_cg, c->d_part + 4 * kRedBlocks, c->d_ticket + 4, fin);
             else LAUNCH(c, k_pcg_update, blocks, 256, 0, c->d_p, c->d_Ap, jac, c->d_tot, c->d_r, n, c->d_cg, c->d_part + 4 * kRedBlocks, c->d_ticket + 4, fin);
-            if (!fin) { { int r = allreduce_sum(c, c->d_cg->tmp, 2); if (r) return r; } LAUNCH(c, k_cg_finalize, 1, 1, 0, c->d_cg, 1, 0.0, fast ? 1 : 0, 0); }
+            if (!fin) { { int r = allreduce_sum(c, c->d_cg->tmp, 2); if (r) return r; } LAUNCH(c, k_cg_finalize, 1, 1, 0, c->d_cg, 1, 0.0, fast ? 1 : 0, 0, 0.0); }
         }
         if (pupd) {
             if (!fast) LAUNCH(c, k_cg_pupdate, blocks, 256, 0, c->d_r, c->d_p, n, c->d_cg);

@@ -7,13 +7,14 @@
 //   k_xrow          (nf_rows.cuh)  x += alpha_prev p_old (the x update of the PREVIOUS iteration, deferred to the one place
 //                   where p_old is read anyway) ; p = M^-1 r + beta p_old ; yp = diag p + (x part of S p)
 //   k_ycol          (nf_rows.cuh)  yp += (y part of S p)
-//   k_zfwd          z-direction forward substitution marching up in z, writes the intermediates zs
-//   k_zback_update  z-direction back substitution marching down; completes Ap = yp + (z part) in registers and applies
+//   k_zfwd2         z-direction forward substitution marching up in z, writes the intermediates zs
+//   k_zback2        z-direction back substitution marching down; completes Ap = yp + (z part) in registers and applies
 //                   r -= alpha Ap, r.M^-1 r, r.r, stop test / beta in the same pass.
 //
 // p^T S p is accumulated on the fly from the quadratic forms (diag p^2 + w z^2/m) of the three directions, so alpha is
 // known before the last kernel starts. z-slab ranks (multi-GPU) use the same x / y kernels and the substructured
-// variants k_zfwd<SLAB> / k_slab_iface / k_slab_back_update of the z kernels.
+// variants k_zfwd2<SLAB> / k_slab_iface / k_zback2<SLAB> of the z kernels; the hybrid path (odd nx) keeps the scalar
+// k_zfwd / k_zback_update.
 #pragma once
 #include "nf_common.cuh"
 #include "nf_sweeps.cuh"
@@ -55,17 +56,21 @@ __device__ __forceinline__ void cell_lo_hi(double x0, double x1, double x2, doub
 }
 
 // ---- z forward substitution ----------------------------------------------------------------------------------------------
-// One thread per (ix, iy, transverse pair), marching up in z; writes zs and accumulates w * sum_f z_f^2 / m_f.
-// SLAB (z-slab ranks): the line is the local part of a global z line; additionally v_0 = sum_f G_{0f} T_f (s0 = column 0 of
-// the local inverse) and v_n = z_n / m_n, the local solution at the two interface faces, go to vG for the all-gather
-// (exact substructuring, tests/slab_model.py).
+// Writes zs and accumulates w * sum_f z_f^2 / m_f, marching up in z.
+//   k_zfwd    one thread per (ix, iy, transverse pair): the hybrid path (any nx).
+//   k_zfwd2   one thread per (PAIR of adjacent x positions, iy, transverse pair): every load / store is a 16-byte vector. The z
+//             kernels are bound by the number of outstanding memory requests, not by bytes (measured: 2-byte loads of the
+//             16-bit preconditioner cost as much as 8-byte loads), so halving the requests per DOF is what speeds them up.
+//             Rows paths (nx even). SLAB (z-slab ranks): the line is the local part of a global z line; additionally
+//             v_0 = sum_f G_{0f} T_f (s0 = column 0 of the local inverse) and v_n = z_n / m_n, the local solution at the two
+//             interface faces, go to vG for the all-gather (exact substructuring, tests/slab_model.py).
 #ifndef NF_ZF_UNR
 #define NF_ZF_UNR 2
 #endif
 #ifndef NF_ZF_MINB
 #define NF_ZF_MINB 8
 #endif
-template <int K, int M1, bool SLAB>
+template <int K, int M1>
 __global__ void __launch_bounds__(128, NF_ZF_MINB) k_zfwd(const FusedArgs a, double *red_part, unsigned *ticket, double *red_out)
 {
     if (a.st->done) return;
@@ -87,26 +92,22 @@ __global__ void __launch_bounds__(128, NF_ZF_MINB) k_zfwd(const FusedArgs a, dou
         double *__restrict__ zp = a.zs + (size_t)t * sxy + c0;
         const double *__restrict__ um = a.u[2] + c0;
         const double *__restrict__ mi = a.minv[2] + c0;
-        const double *__restrict__ sp = SLAB ? a.s0 + c0 : nullptr;
         const double *__restrict__ p0 = a.p + (size_t)a.mode[2][t][0] * a.ne + c0;
         const double *__restrict__ p1 = a.p + (size_t)a.mode[2][t][M1 >= 2 ? 1 : 0] * a.ne + c0;
         const double *__restrict__ p2 = a.p + (size_t)a.mode[2][t][M1 >= 3 ? 2 : 0] * a.ne + c0;
-        double lop = 0.0, uz = 0.0, q = 0.0, v0 = 0.0, vn = 0.0;          // lo(f-1) and u_{f-1} z_{f-1}
+        double lop = 0.0, uz = 0.0, q = 0.0;          // lo(f-1) and u_{f-1} z_{f-1}
         for (int fb = 0; fb <= nz; fb += UNR) {
-            double l0[UNR], l1[UNR], l2[UNR], lu[UNR], lm[UNR], ls[UNR];
+            double l0[UNR], l1[UNR], l2[UNR], lu[UNR], lm[UNR];
 #pragma unroll
             for (int j = 0; j < UNR; ++j) {
                 const int f = fb + j;
-                l0[j] = l1[j] = l2[j] = lu[j] = lm[j] = ls[j] = 0.0;
+                l0[j] = l1[j] = l2[j] = lu[j] = lm[j] = 0.0;
                 if (f < nz) {
                     l0[j] = __ldg(p0 + (size_t)f * sxy);
                     if (K >= 1 && M1 >= 2) l1[j] = __ldg(p1 + (size_t)f * sxy);
                     if (K >= 2 && M1 >= 3) l2[j] = __ldg(p2 + (size_t)f * sxy);
                 }
-                if (f <= nz) {
-                    lu[j] = __ldg(um + (size_t)f * sxy); lm[j] = __ldg(mi + (size_t)f * sxy);
-                    if (SLAB) ls[j] = __ldg(sp + (size_t)f * sxy);
-                }
+                if (f <= nz) { lu[j] = __ldg(um + (size_t)f * sxy); lm[j] = __ldg(mi + (size_t)f * sxy); }
             }
 #pragma unroll
             for (int j = 0; j < UNR; ++j) {
@@ -114,9 +115,7 @@ __global__ void __launch_bounds__(128, NF_ZF_MINB) k_zfwd(const FusedArgs a, dou
                 if (f <= nz) {
                     double lo = 0.0, hi = 0.0;
                     if (f < nz) cell_lo_hi<K, M1>(l0[j], l1[j], l2[j], lo, hi);
-                    const double T = lop - hi;
-                    const double z = T - uz;
-                    if (SLAB) { v0 += ls[j] * T; if (f == nz) vn = z * lm[j]; }
+                    const double z = (lop - hi) - uz;
                     q += z * z * lm[j];
                     zp[(size_t)f * nt * sxy] = z;
                     lop = lo; uz = lu[j] * z;
@@ -124,9 +123,89 @@ __global__ void __launch_bounds__(128, NF_ZF_MINB) k_zfwd(const FusedArgs a, dou
             }
         }
         acc += a.w[t] * q;
+    }
+    double v[1] = {acc};
+    grid_reduce<1>(v, red_part, ticket, red_out);
+}
+
+__device__ __forceinline__ double2 ldg2(const double *p) { return __ldg(reinterpret_cast<const double2 *>(p)); }
+__device__ __forceinline__ void st2(double *p, const double2 v) { *reinterpret_cast<double2 *>(p) = v; }
+
+#ifndef NF_ZF2_UNR
+#define NF_ZF2_UNR 2
+#endif
+#ifndef NF_ZF2_MINB
+#define NF_ZF2_MINB 6
+#endif
+template <int K, int M1, bool SLAB>
+__global__ void __launch_bounds__(128, NF_ZF2_MINB) k_zfwd2(const FusedArgs a, double *red_part, unsigned *ticket, double *red_out)
+{
+    if (a.st->done) return;
+    constexpr int UNR = NF_ZF2_UNR;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, WPB = blockDim.x >> 5;
+    const int nz = a.nz, nt = a.nt;
+    const int nxb = (a.nx + 63) >> 6;
+    const long long nitems = (long long)a.ny * nt * nxb;
+    const long long sxy = a.nxy;
+    const double2 zero2 = make_double2(0.0, 0.0);
+    double acc = 0.0;
+    for (long long item = (long long)blockIdx.x * WPB + wib; item < nitems; item += (long long)gridDim.x * WPB) {
+        const int xb = (int)(item % nxb);
+        const long long rr = item / nxb;
+        const int t = (int)(rr % nt);
+        const int iy = (int)(rr / nt);
+        const int ix = xb * 64 + 2 * lane;
+        if (ix >= a.nx) continue;
+        const long long c0 = (long long)iy * a.nx + ix;
+        double *__restrict__ zp = a.zs + (size_t)t * sxy + c0;
+        const double *__restrict__ um = a.u[2] + c0;
+        const double *__restrict__ mi = a.minv[2] + c0;
+        const double *__restrict__ sp = SLAB ? a.s0 + c0 : nullptr;
+        const double *__restrict__ p0 = a.p + (size_t)a.mode[2][t][0] * a.ne + c0;
+        const double *__restrict__ p1 = a.p + (size_t)a.mode[2][t][M1 >= 2 ? 1 : 0] * a.ne + c0;
+        const double *__restrict__ p2 = a.p + (size_t)a.mode[2][t][M1 >= 3 ? 2 : 0] * a.ne + c0;
+        double2 lop = zero2, uz = zero2, q = zero2, v0 = zero2, vn = zero2;
+        for (int fb = 0; fb <= nz; fb += UNR) {
+            double2 l0[UNR], l1[UNR], l2[UNR], lu[UNR], lm[UNR], ls[UNR];
+#pragma unroll
+            for (int j = 0; j < UNR; ++j) {
+                const int f = fb + j;
+                l0[j] = l1[j] = l2[j] = lu[j] = lm[j] = ls[j] = zero2;
+                if (f < nz) {
+                    l0[j] = ldg2(p0 + (size_t)f * sxy);
+                    if (K >= 1 && M1 >= 2) l1[j] = ldg2(p1 + (size_t)f * sxy);
+                    if (K >= 2 && M1 >= 3) l2[j] = ldg2(p2 + (size_t)f * sxy);
+                }
+                if (f <= nz) {
+                    lu[j] = ldg2(um + (size_t)f * sxy); lm[j] = ldg2(mi + (size_t)f * sxy);
+                    if (SLAB) ls[j] = ldg2(sp + (size_t)f * sxy);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < UNR; ++j) {
+                const int f = fb + j;
+                if (f <= nz) {
+                    double2 lo = zero2, hi = zero2;
+                    if (f < nz) {
+                        cell_lo_hi<K, M1>(l0[j].x, l1[j].x, l2[j].x, lo.x, hi.x);
+                        cell_lo_hi<K, M1>(l0[j].y, l1[j].y, l2[j].y, lo.y, hi.y);
+                    }
+                    const double2 T = make_double2(lop.x - hi.x, lop.y - hi.y);
+                    const double2 z = make_double2(T.x - uz.x, T.y - uz.y);
+                    if (SLAB) {
+                        v0.x += ls[j].x * T.x; v0.y += ls[j].y * T.y;
+                        if (f == nz) vn = make_double2(z.x * lm[j].x, z.y * lm[j].y);
+                    }
+                    q.x += z.x * z.x * lm[j].x; q.y += z.y * z.y * lm[j].y;
+                    st2(zp + (size_t)f * nt * sxy, z);
+                    lop = lo; uz = make_double2(lu[j].x * z.x, lu[j].y * z.y);
+                }
+            }
+        }
+        acc += a.w[t] * (q.x + q.y);
         if (SLAB) {
-            a.vG[((size_t)0 * nt + t) * sxy + c0] = v0;
-            a.vG[((size_t)1 * nt + t) * sxy + c0] = vn;
+            st2(a.vG + ((size_t)0 * nt + t) * sxy + c0, v0);
+            st2(a.vG + ((size_t)1 * nt + t) * sxy + c0, vn);
         }
     }
     double v[1] = {acc};
@@ -134,20 +213,20 @@ __global__ void __launch_bounds__(128, NF_ZF_MINB) k_zfwd(const FusedArgs a, dou
 }
 
 // ---- z back substitution + CG update ------------------------------------------------------------------------------------
-// One thread per (ix, iy, transverse pair of the z direction), marching from the top plane down. For every cell:
-// Ap = yp + w B_z J ; r -= alpha Ap ; accumulates r.M^-1 r and r.r (solvers.cpp:601-631).
-// DEFER (rows paths): x += alpha p is left to the next k_xrow (or k_x_pending), so that neither p nor x is touched here:
-// 32 B per flux DOF instead of 56. !DEFER (hybrid path): the x update happens here.
+// Marching from the top plane down. For every cell: Ap = yp + w B_z J ; r -= alpha Ap ; accumulates r.M^-1 r and r.r
+// (solvers.cpp:601-631).
+//   k_zback_update   one thread per (ix, iy, pair); also applies x += alpha p (hybrid path, any nx).
+//   k_zback2         rows paths: one thread per (pair of adjacent x positions, iy, pair), 16-byte vectors; x += alpha p is
+//                    left to the next k_xrow (or k_x_pending), so that neither p nor x is touched: 32 B per flux DOF
+//                    instead of 56. SLAB: the local back substitution of a z-slab rank with the interface corrections,
+//                    J_f = v_f + s0_f lam_0 + sn_f lam_n (lam from k_slab_iface below).
 #ifndef NF_ZB_UNR
 #define NF_ZB_UNR 3
-#endif
-#ifndef NF_ZB_UNR_D
-#define NF_ZB_UNR_D 4
 #endif
 #ifndef NF_ZB_MINB
 #define NF_ZB_MINB 4
 #endif
-template <int K, int M1, bool DEFER>
+template <int K, int M1>
 __global__ void __launch_bounds__(128, NF_ZB_MINB) k_zback_update(const FusedArgs a)
 {
     CgState *st = a.st;
@@ -155,10 +234,10 @@ __global__ void __launch_bounds__(128, NF_ZB_MINB) k_zback_update(const FusedArg
     const double pAp = (st->pAp[0] + st->pAp[1]) + (st->pAp[2] + st->pAp[3]);
     if (fabs(pAp) < (a.pcg ? 1e-300 : 1e-30)) {        // breakdown guard, solvers.cpp:605
         __syncthreads();
-        if (blockIdx.x == 0 && threadIdx.x == 0) { st->breakdown = 1; st->done = 1; st->alpha_prev = 0.0; }
+        if (blockIdx.x == 0 && threadIdx.x == 0) { st->breakdown = 1; st->done = 1; }
         return;
     }
-    constexpr int UNR = DEFER ? NF_ZB_UNR_D : NF_ZB_UNR;
+    constexpr int UNR = NF_ZB_UNR;
     const double alpha = st->rr / pAp;
     const bool pcg = a.pcg != 0;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, WPB = blockDim.x >> 5;
@@ -195,10 +274,9 @@ __global__ void __launch_bounds__(128, NF_ZB_MINB) k_zback_update(const FusedArg
 #pragma unroll
                         for (int p = 0; p < M1; ++p) {
                             const size_t o = mo[p] + (size_t)f * sxy;
-                            ly[j][p] = __ldg(a.yp + o);
-                            lr[j][p] = a.rw[o];
+                            ly[j][p] = __ldg(a.yp + o); lp[j][p] = __ldg(a.p + o);
+                            lx[j][p] = a.x[o]; lr[j][p] = a.rw[o];
                             lj[j][p] = pcg ? jac_ld(a.jac + o) : 1.0;
-                            if (!DEFER) { lp[j][p] = __ldg(a.p + o); lx[j][p] = a.x[o]; }
                         }
                     }
                 }
@@ -217,7 +295,7 @@ __global__ void __launch_bounds__(128, NF_ZB_MINB) k_zback_update(const FusedArg
                         for (int p = 0; p < M1; ++p) {
                             const size_t o = mo[p] + (size_t)f * sxy;
                             const double Apv = ly[j][p] + sol[p];
-                            if (!DEFER) a.x[o] = lx[j][p] + alpha * lp[j][p];
+                            a.x[o] = lx[j][p] + alpha * lp[j][p];
                             const double rv = lr[j][p] - alpha * Apv;
                             a.rw[o] = rv;
                             acc[0] += rv * rv * lj[j][p];
@@ -233,19 +311,131 @@ __global__ void __launch_bounds__(128, NF_ZB_MINB) k_zback_update(const FusedArg
     if (grid_reduce<2>(acc, a.red_part, a.ticket2, out) && threadIdx.x == 0) {
         if (pcg) { st->tmp[0] = out[0]; st->tmp[1] = out[1]; }
         else { st->tmp[0] = out[1]; }
+        if (a.fin) cg_update_fin(st, a.pcg);
+    }
+}
+
+__device__ __forceinline__ double2 jac_ld2(const jac_t *p)
+{
+    const unsigned v = __ldg(reinterpret_cast<const unsigned *>(p));          // two adjacent 16-bit entries
+    return make_double2(__hiloint2double((int)(v << 16), 0), __hiloint2double((int)(v & 0xffff0000u), 0));
+}
+
+#ifndef NF_ZB2_UNR
+#define NF_ZB2_UNR 2
+#endif
+#ifndef NF_ZB2_MINB
+#define NF_ZB2_MINB 4
+#endif
+template <int K, int M1, bool SLAB>
+__global__ void __launch_bounds__(128, NF_ZB2_MINB) k_zback2(const FusedArgs a, const double *__restrict__ lam)
+{
+    CgState *st = a.st;
+    if (st->done) return;
+    const double pAp = (st->pAp[0] + st->pAp[1]) + (st->pAp[2] + st->pAp[3]);
+    if (fabs(pAp) < (a.pcg ? 1e-300 : 1e-30)) {        // breakdown guard, solvers.cpp:605
+        __syncthreads();
+        if (blockIdx.x == 0 && threadIdx.x == 0) { st->breakdown = 1; st->done = 1; st->alpha_prev = 0.0; }
+        return;
+    }
+    constexpr int UNR = NF_ZB2_UNR;
+    const double alpha = st->rr / pAp;
+    const bool pcg = a.pcg != 0;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, WPB = blockDim.x >> 5;
+    const int nz = a.nz, nt = a.nt;
+    const int nxb = (a.nx + 63) >> 6;
+    const long long nitems = (long long)a.ny * nt * nxb;
+    const long long sxy = a.nxy, nl = sxy * nt;
+    const double2 zero2 = make_double2(0.0, 0.0), one2 = make_double2(1.0, 1.0);
+    double acc[2] = {0.0, 0.0};
+    for (long long item = (long long)blockIdx.x * WPB + wib; item < nitems; item += (long long)gridDim.x * WPB) {
+        const int xb = (int)(item % nxb);
+        const long long rr = item / nxb;
+        const int t = (int)(rr % nt);
+        const int iy = (int)(rr / nt);
+        const int ix = xb * 64 + 2 * lane;
+        if (ix >= a.nx) continue;
+        const double w = a.w[t];
+        const long long c0 = (long long)iy * a.nx + ix;
+        const double *__restrict__ zp = a.zs + (size_t)t * sxy + c0;       // + f * nt * sxy
+        const double *__restrict__ um = a.u[2] + c0;                       // + f * sxy
+        const double *__restrict__ mi = a.minv[2] + c0;
+        const double *__restrict__ sp = SLAB ? a.s0 + c0 : nullptr;
+        double2 lam0 = zero2, lamn = zero2;
+        if (SLAB) { lam0 = ldg2(lam + (size_t)t * sxy + c0); lamn = ldg2(lam + nl + (size_t)t * sxy + c0); }
+        size_t mo[3];
+#pragma unroll
+        for (int p = 0; p < 3; ++p) mo[p] = (size_t)a.mode[2][t][p < M1 ? p : 0] * a.ne + c0;
+        double2 Jn = zero2, vnx = zero2, snx = zero2;
+        for (int fb = nz; fb >= 0; fb -= UNR) {
+            double2 lz[UNR], lu[UNR], lm[UNR], ls[UNR], ly[UNR][3], lr[UNR][3], lj[UNR][3];
+#pragma unroll
+            for (int j = 0; j < UNR; ++j) {
+                const int f = fb - j;
+                lz[j] = lu[j] = lm[j] = ls[j] = zero2;
+                if (f >= 0) {
+                    lz[j] = ldg2(zp + (size_t)f * nt * sxy); lu[j] = ldg2(um + (size_t)f * sxy); lm[j] = ldg2(mi + (size_t)f * sxy);
+                    if (SLAB) ls[j] = ldg2(sp + (size_t)f * sxy);
+                    if (f < nz) {
+#pragma unroll
+                        for (int p = 0; p < M1; ++p) {
+                            const size_t o = mo[p] + (size_t)f * sxy;
+                            ly[j][p] = ldg2(a.yp + o);
+                            lr[j][p] = *reinterpret_cast<const double2 *>(a.rw + o);
+                            lj[j][p] = pcg ? jac_ld2(a.jac + o) : one2;
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < UNR; ++j) {
+                const int f = fb - j;
+                if (f >= 0) {
+                    double2 J;
+                    if (SLAB) {
+                        const double2 v = make_double2(lm[j].x * lz[j].x - lu[j].x * vnx.x, lm[j].y * lz[j].y - lu[j].y * vnx.y);
+                        const double2 sn = (f == nz) ? lm[j] : make_double2(-lu[j].x * snx.x, -lu[j].y * snx.y);
+                        J = make_double2(v.x + ls[j].x * lam0.x + sn.x * lamn.x, v.y + ls[j].y * lam0.y + sn.y * lamn.y);
+                        vnx = v; snx = sn;
+                    } else {
+                        J = make_double2(lm[j].x * lz[j].x - lu[j].x * Jn.x, lm[j].y * lz[j].y - lu[j].y * Jn.y);
+                    }
+                    if (f < nz) {
+                        double2 sol[3];
+                        sol[0] = make_double2(w * (Jn.x - J.x), w * (Jn.y - J.y));
+                        sol[1] = (K >= 1) ? make_double2(w * (5.0 / 6.0) * (J.x + Jn.x), w * (5.0 / 6.0) * (J.y + Jn.y)) : zero2;
+                        sol[2] = (K >= 2) ? make_double2(w * (7.0 / 10.0) * (Jn.x - J.x), w * (7.0 / 10.0) * (Jn.y - J.y)) : zero2;
+#pragma unroll
+                        for (int p = 0; p < M1; ++p) {
+                            const size_t o = mo[p] + (size_t)f * sxy;
+                            const double2 rv = make_double2(lr[j][p].x - alpha * (ly[j][p].x + sol[p].x), lr[j][p].y - alpha * (ly[j][p].y + sol[p].y));
+                            st2(a.rw + o, rv);
+                            acc[0] += rv.x * rv.x * lj[j][p].x + rv.y * rv.y * lj[j][p].y;
+                            acc[1] += rv.x * rv.x + rv.y * rv.y;
+                        }
+                    }
+                    Jn = J;
+                }
+            }
+        }
+    }
+    __shared__ double out[2];
+    if (grid_reduce<2>(acc, a.red_part, a.ticket2, out) && threadIdx.x == 0) {
+        if (pcg) { st->tmp[0] = out[0]; st->tmp[1] = out[1]; }
+        else { st->tmp[0] = out[1]; }
         if (a.fin) {
-            if (DEFER) st->alpha_prev = alpha;
+            st->alpha_prev = alpha;
             cg_update_fin(st, a.pcg);
         }
     }
 }
 
 // ---- z-slab ranks: interface solve and back substitution fused with the CG update ---------------------------------------
-// After k_zfwd<SLAB> and the all-gather of the interface values, k_slab_iface solves the reduced interface system of every
+// After k_zfwd2<SLAB> and the all-gather of the interface values, k_slab_iface solves the reduced interface system of every
 // (x, y, pair) line redundantly, keeps this rank's two multipliers and adds the interface share of p^T S p (so that alpha
-// is known before the update). k_slab_back_update then marches the local back substitution
+// is known before the update). k_zback2<SLAB> then marches the local back substitution
 // J_f = v_f + s0_f lam_0 + sn_f lam_n down the slab, completes Ap = yp + w B_z J in registers and applies the CG update in
-// the same pass (the slab counterpart of k_zback_update<DEFER>; Ap is never written, x is updated by the next k_xrow).
+// the same pass (k_zback2<SLAB> above; Ap is never written, x is updated by the next k_xrow).
 struct SlabUpd {
     double *lam;            // [2][nt][nxy] interface multipliers of this rank
     CgState *st;
@@ -306,99 +496,6 @@ __global__ void __launch_bounds__(128) k_slab_iface(const SweepArgs a, const Sla
     }
     double v[1] = {acc};
     grid_reduce<1>(v, a.red_part, a.ticket, a.red_out);
-}
-
-template <int K, int M1>
-__global__ void __launch_bounds__(128, NF_ZB_MINB) k_slab_back_update(const FusedArgs a, const SlabUpd u)
-{
-    CgState *st = u.st;
-    if (st->done) return;
-    const double pAp = (st->pAp[0] + st->pAp[1]) + (st->pAp[2] + st->pAp[3]);
-    if (fabs(pAp) < (u.pcg ? 1e-300 : 1e-30)) {        // breakdown guard, solvers.cpp:605
-        __syncthreads();
-        if (blockIdx.x == 0 && threadIdx.x == 0) { st->breakdown = 1; st->done = 1; st->alpha_prev = 0.0; }
-        return;
-    }
-    constexpr int UNR = NF_ZB_UNR_D;
-    const double alpha = st->rr / pAp;
-    const bool pcg = u.pcg != 0;
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, WPB = blockDim.x >> 5;
-    const int n = a.nz, nt = a.nt;
-    const int nxb = (a.nx + 31) >> 5;
-    const long long nitems = (long long)a.ny * nt * nxb;
-    const long long sxy = a.nxy;
-    const long long nl = sxy * nt;
-    double acc[2] = {0.0, 0.0};
-    for (long long item = (long long)blockIdx.x * WPB + wib; item < nitems; item += (long long)gridDim.x * WPB) {
-        const int xb = (int)(item % nxb);
-        const long long r = item / nxb;
-        const int t = (int)(r % nt);
-        const int iy = (int)(r / nt);
-        const int ix = xb * 32 + lane;
-        if (ix >= a.nx) continue;
-        const double w = a.w[t];
-        const long long c0 = (long long)iy * a.nx + ix;
-        const double lam0 = __ldg(u.lam + (size_t)t * sxy + c0), lamn = __ldg(u.lam + nl + (size_t)t * sxy + c0);
-        const double *__restrict__ zp = a.zs + (size_t)t * sxy + c0;
-        const double *__restrict__ um = a.u[2] + c0;
-        const double *__restrict__ mi = a.minv[2] + c0;
-        const double *__restrict__ sp = a.s0 + c0;
-        size_t mo[3];
-#pragma unroll
-        for (int p = 0; p < 3; ++p) mo[p] = (size_t)a.mode[2][t][p < M1 ? p : 0] * a.ne + c0;
-        double vnx = 0.0, snx = 0.0, Jn = 0.0;
-        for (int fb = n; fb >= 0; fb -= UNR) {
-            double lz[UNR], lu[UNR], lm[UNR], ls[UNR], ly[UNR][3], lr[UNR][3], lj[UNR][3];
-#pragma unroll
-            for (int j = 0; j < UNR; ++j) {
-                const int f = fb - j;
-                lz[j] = lu[j] = lm[j] = ls[j] = 0.0;
-                if (f >= 0) {
-                    const size_t o = (size_t)f * sxy;
-                    lz[j] = __ldg(zp + (size_t)f * nt * sxy); lu[j] = __ldg(um + o); lm[j] = __ldg(mi + o); ls[j] = __ldg(sp + o);
-                    if (f < n) {
-#pragma unroll
-                        for (int p = 0; p < M1; ++p) {
-                            const size_t oo = mo[p] + o;
-                            ly[j][p] = __ldg(a.yp + oo);
-                            lr[j][p] = a.rw[oo];
-                            lj[j][p] = pcg ? jac_ld(a.jac + oo) : 1.0;
-                        }
-                    }
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < UNR; ++j) {
-                const int f = fb - j;
-                if (f >= 0) {
-                    const double v = lm[j] * lz[j] - lu[j] * vnx;
-                    const double sn = (f == n) ? lm[j] : -lu[j] * snx;
-                    const double J = v + ls[j] * lam0 + sn * lamn;
-                    if (f < n) {
-                        double sol[3];
-                        sol[0] = w * (Jn - J);
-                        sol[1] = (K >= 1) ? w * (5.0 / 6.0) * (J + Jn) : 0.0;
-                        sol[2] = (K >= 2) ? w * (7.0 / 10.0) * (Jn - J) : 0.0;
-#pragma unroll
-                        for (int p = 0; p < M1; ++p) {
-                            const size_t oo = mo[p] + (size_t)f * sxy;
-                            const double Apv = ly[j][p] + sol[p];
-                            const double rv = lr[j][p] - alpha * Apv;
-                            a.rw[oo] = rv;
-                            acc[0] += rv * rv * lj[j][p];
-                            acc[1] += rv * rv;
-                        }
-                    }
-                    vnx = v; snx = sn; Jn = J;
-                }
-            }
-        }
-    }
-    __shared__ double out[2];
-    if (grid_reduce<2>(acc, u.red_part, u.ticket, out) && threadIdx.x == 0) {
-        if (pcg) { st->tmp[0] = out[0]; st->tmp[1] = out[1]; }
-        else { st->tmp[0] = out[1]; }
-    }
 }
 
 }  // namespace nf

@@ -639,4 +639,190 @@ __global__ void __launch_bounds__(NT) k_ycol(const FusedArgs a, const RowGeom g,
     grid_reduce<1>(v, red_part, ticket, red_out);
 }
 
+// ---- y columns, three-phase variant --------------------------------------------------------------------------------------
+// Same ownership as ycol_block (thread = pair of adjacent columns x chunk of LcY cells), but every chunk is walked with global
+// loads only THREE times instead of six (k_ycol is bound by the latency of its dependent load rounds: 12 warps per SM, L1 hit
+// rate < 1 %, profiles/r01g):
+//   1. forward: p, u and 1/m of the chunk are requested together; the right-hand side T_f is consumed on the fly by the local
+//      forward substitution from z_in = 0, together with the homogeneous response h_f = prod(-u): the chunk keeps
+//      zm0_f = z0_f / m_f and hm_f = h_f / m_f (so that d_f = z_f / m_f = zm0_f + hm_f z_in needs no further load) and three
+//      scalars that give sum_f z_f^2 / m_f for any z_in;                                   [stitch: z_in of every chunk]
+//   2. backward: only u is requested; J0_f (from J_in = 0) and g_f = prod(-u) replace zm0 / hm;   [stitch: J_in]
+//   3. output: yp is requested and updated with J_f = J0_f + g_f J_in; J of the first face of the next chunk IS J_in.
+// The chunk state lives in two thread-private shared-memory columns of LcY rows; the top face of the line (last chunk only)
+// stays in registers, so that three CTAs of 128 threads fit an SM at LcY = 16.
+#ifndef NF_YB3
+#define NF_YB3 4
+#endif
+constexpr int kYB3 = NF_YB3;    // rows of loads issued ahead of each stretch of work
+
+template <int K, int M1, int NT>
+__device__ __forceinline__ void ycol_block3(const FusedArgs &a, const RowGeom &g, const int iz, const int xb, const int t,
+                                            double2 *sC0, double2 *sC1, double2 *sS, double &acc)
+{
+    const int tid = threadIdx.x;
+    const int CPI = g.colsY >> 1, CY = g.Cy, Lc = g.LcY;           // column pairs per item; NT == CPI * CY
+    const int cp = tid % CPI, kc = tid / CPI;
+    const int n = a.ny, nx = a.nx;
+    const int ix = xb * g.colsY + 2 * cp;
+    const bool cv = ix < nx;
+    const int ixc = cv ? ix : nx - 2;            // column pairs past the mesh redo the last one; nothing of theirs is stored
+    const int f0 = min(kc * Lc, n + 1);
+    const int ncell = max(0, min(Lc, n - f0));   // cells f0 .. f0+ncell-1, faces f0 .. f0+ncell-1 (+ the top face: last chunk)
+    const bool top = (ncell > 0 && f0 + ncell == n);
+    double2 *sA = sS, *sZ = sS + NT, *sB = sS + 2 * NT, *sJ = sS + 3 * NT;
+    double2 *C0 = sC0 + tid, *C1 = sC1 + tid;    // thread-private columns: row j at [j * NT]
+    const double w = a.w[t];
+    const size_t S = (size_t)nx;                 // row stride (doubles)
+    const size_t cell0 = (size_t)iz * n * nx + ixc + (size_t)f0 * nx;
+    const double *gp0 = a.p + (size_t)a.mode[1][t][0] * a.ne + cell0;
+    const double *gp1 = a.p + (size_t)a.mode[1][t][M1 >= 2 ? 1 : 0] * a.ne + cell0;
+    const double *gp2 = a.p + (size_t)a.mode[1][t][M1 >= 3 ? 2 : 0] * a.ne + cell0;
+    double *gy0 = a.yp + (size_t)a.mode[1][t][0] * a.ne + cell0;
+    double *gy1 = a.yp + (size_t)a.mode[1][t][M1 >= 2 ? 1 : 0] * a.ne + cell0;
+    double *gy2 = a.yp + (size_t)a.mode[1][t][M1 >= 3 ? 2 : 0] * a.ne + cell0;
+    const double *gu = a.u[1] + (size_t)iz * (n + 1) * nx + ixc + (size_t)f0 * nx;       // u_f at gu + j*S, u_{f-1} at gu + (j-1)*S
+    const double *gm = a.minv[1] + (size_t)iz * (n + 1) * nx + ixc + (size_t)f0 * nx;
+    const double2 zero2 = make_double2(0.0, 0.0), one2 = make_double2(1.0, 1.0);
+    const int slot = kc * CPI + cp;
+    // ---- phase 1: forward substitution from z_in = 0 and homogeneous response, rhs consumed on the fly
+    double2 z0 = zero2, h = one2, qa = zero2, qb = zero2, qc = zero2, tzm = zero2, thm = zero2;
+    {
+        double2 lop = zero2, dum;
+        if (f0 > 0 && f0 <= n) lohi2<K, M1>(ld2cg(gp0 - S), (K >= 1 && M1 >= 2) ? ld2cg(gp1 - S) : zero2, (K >= 2 && M1 >= 3) ? ld2cg(gp2 - S) : zero2, lop, dum);
+        auto face = [&](const double2 hi, const double2 uu, const double2 mm, double2 &zm, double2 &hm) {
+            z0.x = (lop.x - hi.x) - uu.x * z0.x; z0.y = (lop.y - hi.y) - uu.y * z0.y;
+            h.x *= -uu.x; h.y *= -uu.y;
+            zm = make_double2(mm.x * z0.x, mm.y * z0.y);
+            hm = make_double2(mm.x * h.x, mm.y * h.y);
+            qa.x += z0.x * zm.x; qa.y += z0.y * zm.y;
+            qb.x += z0.x * hm.x; qb.y += z0.y * hm.y;
+            qc.x += h.x * hm.x; qc.y += h.y * hm.y;
+        };
+        int j = 0;
+        for (; j + kYB3 <= ncell; j += kYB3) {
+            double2 x0[kYB3], x1[kYB3], x2[kYB3], uu[kYB3], mm[kYB3];
+            const double *q0 = gp0 + j * S, *q1 = gp1 + j * S, *q2 = gp2 + j * S, *qu = gu + j * S - S, *qm = gm + j * S;
+#pragma unroll
+            for (int i = 0; i < kYB3; ++i) {
+                x0[i] = ld2cg(q0 + i * S);
+                x1[i] = (K >= 1 && M1 >= 2) ? ld2cg(q1 + i * S) : zero2;
+                x2[i] = (K >= 2 && M1 >= 3) ? ld2cg(q2 + i * S) : zero2;
+                uu[i] = ld2g(qu + i * S); mm[i] = ld2g(qm + i * S);
+            }
+#pragma unroll
+            for (int i = 0; i < kYB3; ++i) {
+                double2 lo, hi, zm, hm;
+                lohi2<K, M1>(x0[i], x1[i], x2[i], lo, hi);
+                face(hi, uu[i], mm[i], zm, hm);
+                C0[(j + i) * NT] = zm; C1[(j + i) * NT] = hm;
+                lop = lo;
+            }
+        }
+        for (; j < ncell; ++j) {
+            double2 lo, hi, zm, hm;
+            lohi2<K, M1>(ld2cg(gp0 + j * S), (K >= 1 && M1 >= 2) ? ld2cg(gp1 + j * S) : zero2, (K >= 2 && M1 >= 3) ? ld2cg(gp2 + j * S) : zero2, lo, hi);
+            face(hi, ld2g(gu + j * S - S), ld2g(gm + j * S), zm, hm);
+            C0[j * NT] = zm; C1[j * NT] = hm;
+            lop = lo;
+        }
+        if (top) face(zero2, ld2g(gu + ncell * S - S), ld2g(gm + ncell * S), tzm, thm);      // top face of the line: hi = 0
+    }
+    sA[slot] = h; sZ[slot] = z0;
+    __syncthreads();
+    double2 zin = zero2;
+    for (int kk = 0; kk < kc; ++kk) {
+        const double2 Ak = sA[kk * CPI + cp], zk = sZ[kk * CPI + cp];
+        zin.x = Ak.x * zin.x + zk.x; zin.y = Ak.y * zin.y + zk.y;
+    }
+    if (cv) acc += w * ((qa.x + zin.x * (2.0 * qb.x + zin.x * qc.x)) + (qa.y + zin.y * (2.0 * qb.y + zin.y * qc.y)));
+    // ---- phase 2: backward substitution from J_in = 0 and homogeneous response; J0 / g replace zm0 / hm
+    double2 J0 = zero2, gg = one2;
+    {
+        if (top) {          // u of the top face is 0 by construction: J0 = d, g = 0
+            J0 = make_double2(tzm.x + thm.x * zin.x, tzm.y + thm.y * zin.y);
+            gg = zero2;
+            tzm = J0; thm = gg;
+        }
+        auto face = [&](const int j, const double2 uu) {
+            const double2 zm = C0[j * NT], hm = C1[j * NT];
+            J0.x = (zm.x + hm.x * zin.x) - uu.x * J0.x; J0.y = (zm.y + hm.y * zin.y) - uu.y * J0.y;
+            gg.x *= -uu.x; gg.y *= -uu.y;
+            C0[j * NT] = J0; C1[j * NT] = gg;
+        };
+        int j = ncell - 1;
+        const int nfull = (ncell / kYB3) * kYB3;
+        for (; j >= nfull; --j) face(j, ld2g(gu + j * S));
+        for (j = nfull - kYB3; j >= 0; j -= kYB3) {
+            double2 uu[kYB3];
+            const double *qu = gu + j * S;
+#pragma unroll
+            for (int i = kYB3 - 1; i >= 0; --i) uu[i] = ld2g(qu + i * S);
+#pragma unroll
+            for (int i = kYB3 - 1; i >= 0; --i) face(j + i, uu[i]);
+        }
+    }
+    sB[slot] = gg; sJ[slot] = J0;
+    __syncthreads();
+    double2 Jin = zero2;
+    for (int kk = CY - 1; kk > kc; --kk) {
+        const double2 Bk = sB[kk * CPI + cp], Jk = sJ[kk * CPI + cp];
+        Jin.x = Bk.x * Jin.x + Jk.x; Jin.y = Bk.y * Jin.y + Jk.y;
+    }
+    // ---- phase 3: yp += w B_y J for the cells f0 .. f0+ncell-1 of this column pair, J_f = J0_f + g_f J_in
+    if (cv) {
+        auto Jat = [&](const int j) {            // j in [0, ncell]: face f0 + j
+            if (j < ncell) { const double2 a0 = C0[j * NT], a1 = C1[j * NT]; return make_double2(a0.x + a1.x * Jin.x, a0.y + a1.y * Jin.y); }
+            return top ? make_double2(tzm.x + thm.x * Jin.x, tzm.y + thm.y * Jin.y) : Jin;
+        };
+        auto put = [&](double *y0p, double *y1p, double *y2p, const double2 y0, const double2 y1, const double2 y2, const double2 JL,
+                       const double2 JR) {
+            *reinterpret_cast<double2 *>(y0p) = make_double2(y0.x + w * (JR.x - JL.x), y0.y + w * (JR.y - JL.y));
+            if (M1 >= 2)
+                *reinterpret_cast<double2 *>(y1p) = (K >= 1) ? make_double2(y1.x + w * (5.0 / 6.0) * (JL.x + JR.x), y1.y + w * (5.0 / 6.0) * (JL.y + JR.y)) : y1;
+            if (M1 >= 3)
+                *reinterpret_cast<double2 *>(y2p) = (K >= 2) ? make_double2(y2.x + w * (7.0 / 10.0) * (JR.x - JL.x), y2.y + w * (7.0 / 10.0) * (JR.y - JL.y)) : y2;
+        };
+        int j = 0;
+        for (; j + kYB3 <= ncell; j += kYB3) {
+            double2 y0[kYB3], y1[kYB3], y2[kYB3], jj[kYB3 + 1];
+            double *q0 = gy0 + j * S, *q1 = gy1 + j * S, *q2 = gy2 + j * S;
+#pragma unroll
+            for (int i = 0; i < kYB3; ++i) {
+                y0[i] = ld2cg(q0 + i * S);
+                y1[i] = (M1 >= 2) ? ld2cg(q1 + i * S) : zero2;
+                y2[i] = (M1 >= 3) ? ld2cg(q2 + i * S) : zero2;
+            }
+#pragma unroll
+            for (int i = 0; i <= kYB3; ++i) jj[i] = Jat(j + i);
+#pragma unroll
+            for (int i = 0; i < kYB3; ++i) put(q0 + i * S, q1 + i * S, q2 + i * S, y0[i], y1[i], y2[i], jj[i], jj[i + 1]);
+        }
+        for (; j < ncell; ++j)
+            put(gy0 + j * S, gy1 + j * S, gy2 + j * S, ld2cg(gy0 + j * S), (M1 >= 2) ? ld2cg(gy1 + j * S) : zero2,
+                (M1 >= 3) ? ld2cg(gy2 + j * S) : zero2, Jat(j), Jat(j + 1));
+    }
+    __syncthreads();        // sS is reused by the next item
+}
+
+// yp += (y part of S p) ; red_out = p^T (y part) p.   Dynamic shared memory: (2 LcY + 4) * NT double2.
+template <int K, int M1, int NT>
+__global__ void __launch_bounds__(NT, (NT == 128 ? 3 : 1)) k_ycol3(const FusedArgs a, const RowGeom g, double *red_part, unsigned *ticket,
+                                                                   double *red_out)
+{
+    if (a.st->done) return;
+    extern __shared__ __align__(16) double sm[];
+    double2 *sC0 = reinterpret_cast<double2 *>(sm), *sC1 = sC0 + (size_t)g.LcY * NT, *sS = sC1 + (size_t)g.LcY * NT;
+    const int nxb = (a.nx + g.colsY - 1) / g.colsY;
+    const long long nitems = (long long)a.nz * nxb * a.nt;
+    double acc = 0.0;
+    for (long long item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const int t = (int)(item % a.nt);
+        const long long r = item / a.nt;
+        ycol_block3<K, M1, NT>(a, g, (int)(r / nxb), (int)(r % nxb), t, sC0, sC1, sS, acc);
+    }
+    double v[1] = {acc};
+    grid_reduce<1>(v, red_part, ticket, red_out);
+}
+
 }  // namespace nf

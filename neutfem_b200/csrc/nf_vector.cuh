@@ -29,7 +29,10 @@ __device__ __forceinline__ double thr14(double v) { return (fabs(v) > 1e-14) ? v
 
 // Scalar part of the CG recurrences (solvers.cpp:587-589, 615-631). Runs in the last block of the reducing kernel on
 // one GPU, or in k_cg_finalize after the NCCL all-reduce of st->tmp in z-slab mode.
-__device__ inline void cg_init_fin(CgState *st, double tol, int pcg)
+// eta > 0 (fast mode option "inner_reduction"): inexact inner solves -- stop once the residual is below tol ||b|| OR has been
+// reduced by the factor eta relative to the warm-started initial residual, whichever comes first. As the outer iteration
+// converges the initial residual itself drops to the tol ||b|| level, where the strict test takes over.
+__device__ inline void cg_init_fin(CgState *st, double tol, int pcg, double eta = 0.0)
 {
     if (!pcg) {
         st->rr = st->bnorm_sq = st->rr_true = st->tmp[0];
@@ -39,6 +42,7 @@ __device__ inline void cg_init_fin(CgState *st, double tol, int pcg)
         st->rr = st->tmp[0]; st->bnorm_sq = st->tmp[1]; st->rr_true = st->tmp[2];
         st->tol_sq = tol * tol * st->tmp[1];
         st->done = (st->tmp[2] < st->tol_sq || st->tmp[1] == 0.0) ? 1 : 0;
+        if (eta > 0.0) st->tol_sq = fmax(st->tol_sq, eta * eta * st->tmp[2]);
     }
     st->pAp[0] = st->pAp[1] = st->pAp[2] = st->pAp[3] = 0.0;
     st->beta = 0.0; st->iters = 0; st->breakdown = 0; st->alpha_prev = 0.0;
@@ -55,9 +59,9 @@ __device__ inline void cg_update_fin(CgState *st, int pcg)
 
 // defer != 0 (rows paths): the x update of this iteration is pending, remember its step length (same expression as in the
 // updating kernel: bitwise the alpha that was applied to r)
-__global__ void k_cg_finalize(CgState *st, int which, double tol, int pcg, int defer)
+__global__ void k_cg_finalize(CgState *st, int which, double tol, int pcg, int defer, double eta)
 {
-    if (which == 0) cg_init_fin(st, tol, pcg);
+    if (which == 0) cg_init_fin(st, tol, pcg, eta);
     else if (!st->done) {
         if (defer) st->alpha_prev = st->rr / ((st->pAp[0] + st->pAp[1]) + (st->pAp[2] + st->pAp[3]));
         cg_update_fin(st, pcg);
@@ -171,7 +175,7 @@ __global__ void __launch_bounds__(256) k_cg_pupdate(const double *__restrict__ r
 __global__ void __launch_bounds__(256) k_pcg_init(const double *__restrict__ b, const double *__restrict__ Sx,
                                                   const jac_t *__restrict__ minv, double *__restrict__ r,
                                                   double *__restrict__ p, long long n, double tol, CgState *st,
-                                                  double *part, unsigned *ticket, int fin)
+                                                  double *part, unsigned *ticket, int fin, double eta)
 {
     double acc[3] = {0.0, 0.0, 0.0};
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -182,7 +186,7 @@ __global__ void __launch_bounds__(256) k_pcg_init(const double *__restrict__ b, 
     __shared__ double out[3];
     if (grid_reduce<3>(acc, part, ticket, out) && threadIdx.x == 0) {
         st->tmp[0] = out[0]; st->tmp[1] = out[1]; st->tmp[2] = out[2];
-        if (fin) cg_init_fin(st, tol, 1);
+        if (fin) cg_init_fin(st, tol, 1, eta);
     }
 }
 
@@ -480,6 +484,76 @@ __global__ void __launch_bounds__(256) k_flux_integral(const double *__restrict_
         }
     }
     grid_reduce<3>(acc, part, ticket, out);
+}
+
+// ---- Anderson mixing of the outer (power) iteration ------------------------------------------------------------------------
+// Standard type-II Anderson acceleration of x -> g(x) with the parameters of the reference's AndersonAccel (m = 5, beta = 1,
+// Tikhonov 1e-8, relative step clamp 0.3; src/solvers.cpp:772-891 -- whose own formula returns the previous iterate, see
+// oracle AndersonAccelReference). Restated on the CPU by oracle AndersonAccel.step. x = the iterate the outer iteration
+// started from (d_old), g = its normalised result (phi). History: dF / dG columns (ring of m), f_prev, g_prev.
+constexpr int kAndM = 5;
+struct AndersonArgs {
+    double *dF[kAndM], *dG[kAndM];
+    double *fprev, *gprev;
+    int ncol;               // filled columns
+    int newest;             // ring slot written by this push (-1: no previous residual yet)
+};
+
+// f = g - x ; dF[newest] = f - f_prev ; dG[newest] = g - g_prev ; f_prev = f ; g_prev = g
+__global__ void __launch_bounds__(256) k_and_push(const AndersonArgs a, const double *__restrict__ g, const double *__restrict__ x,
+                                                  long long n)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double gv = g[i], f = gv - x[i];
+        if (a.newest >= 0) { a.dF[a.newest][i] = f - a.fprev[i]; a.dG[a.newest][i] = gv - a.gprev[i]; }
+        a.fprev[i] = f; a.gprev[i] = gv;
+    }
+}
+
+// out[i*kAndM + j] = dF_i . dF_j (i <= j < ncol), out[kAndM*kAndM + i] = dF_i . f   (f = f_prev after the push)
+__global__ void __launch_bounds__(256) k_and_gram(const AndersonArgs a, long long n, double *part, unsigned *ticket, double *out)
+{
+    constexpr int NV = kAndM * (kAndM + 1) / 2 + kAndM;
+    double acc[NV];
+#pragma unroll
+    for (int q = 0; q < NV; ++q) acc[q] = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        double c[kAndM];
+#pragma unroll
+        for (int j = 0; j < kAndM; ++j) c[j] = (j < a.ncol) ? a.dF[j][i] : 0.0;
+        const double f = a.fprev[i];
+        int q = 0;
+#pragma unroll
+        for (int r = 0; r < kAndM; ++r)
+#pragma unroll
+            for (int j = r; j < kAndM; ++j) acc[q++] += c[r] * c[j];
+#pragma unroll
+        for (int j = 0; j < kAndM; ++j) acc[q++] += c[j] * f;
+    }
+    grid_reduce<NV>(acc, part, ticket, out);
+}
+
+struct AndersonGamma { double g[kAndM]; };
+
+// corr = sum_j gamma_j dG_j ; out = (||corr||^2, ||g||^2)
+__global__ void __launch_bounds__(256) k_and_corr(const AndersonArgs a, const AndersonGamma gm, const double *__restrict__ g,
+                                                  double *__restrict__ corr, long long n, double *part, unsigned *ticket, double *out)
+{
+    double acc[2] = {0.0, 0.0};
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        double c = 0.0;
+#pragma unroll
+        for (int j = 0; j < kAndM; ++j) if (j < a.ncol) c += gm.g[j] * a.dG[j][i];
+        corr[i] = c;
+        const double gv = g[i];
+        acc[0] += c * c; acc[1] += gv * gv;
+    }
+    grid_reduce<2>(acc, part, ticket, out);
+}
+
+__global__ void __launch_bounds__(256) k_axpy(double *__restrict__ y, const double *__restrict__ x, long long n, double a)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) y[i] += a * x[i];
 }
 
 }  // namespace nf

@@ -259,6 +259,81 @@ class SolveStats:
     converged: bool = False
 
 
+class AndersonAccelReference:
+    """LITERAL restatement of the reference's AndersonAccel::operator() (src/solvers.cpp:772-891; m = 5, beta = 1,
+    Tikhonov 1e-8, step clamp 0.3). The reference never instantiates this class -- and the formula is
+    defective: its right-hand side f_new - f_history[m-2] IS the last column of F, so the least-squares solution is
+    alpha = e_last up to the regularisation, delta_x = x_new - x_old, and the "accelerated" vector is the PREVIOUS iterate
+    (tests/test_oracle.py::test_reference_anderson_formula_returns_the_previous_iterate). Kept as the record of what the
+    reference computes; the product implements the standard type-II Anderson mixing below with the same parameters."""
+
+    def __init__(self, m=5, beta=1.0):
+        self.m_max, self.beta, self.reg, self.max_rel = int(m), float(beta), 1e-8, 0.3
+        self.x_hist, self.f_hist = [], []
+
+    def __call__(self, phi):
+        if not self.x_hist:
+            self.x_hist.append(phi.copy())
+            self.f_hist.append(np.zeros_like(phi))
+            return phi
+        f_new = phi - self.x_hist[-1]
+        self.x_hist.append(phi.copy())
+        self.f_hist.append(f_new)
+        if len(self.x_hist) > self.m_max:
+            self.x_hist.pop(0)
+            self.f_hist.pop(0)
+        m = len(self.f_hist)
+        if m == 1:
+            return phi
+        F = np.stack([self.f_hist[i + 1] - self.f_hist[i] for i in range(m - 1)], axis=1)
+        rhs = f_new - self.f_hist[m - 2]
+        A = F.T @ F + self.reg * np.eye(m - 1)
+        alpha = np.linalg.solve(A, F.T @ rhs)
+        dx = np.zeros_like(phi)
+        for i in range(m - 1):
+            dx += alpha[i] * (self.x_hist[i + 1] - self.x_hist[i])
+        pn, dn = np.linalg.norm(phi), np.linalg.norm(dx)
+        if pn > 0 and dn / pn > self.max_rel:
+            dx *= self.max_rel * pn / dn
+        return (1.0 - self.beta) * phi + self.beta * (phi - dx)
+
+
+class AndersonAccel:
+    """Standard type-II Anderson mixing of the fixed-point map x -> g(x) (Walker & Ni 2011) with the reference's parameters
+    (depth m = 5, beta = 1, Tikhonov 1e-8 on the normal equations scaled by their largest diagonal entry, relative step
+    clamp 0.3). step(x, g) is called with the iterate the outer iteration started from and the (normalised) result:
+        f = g - x ;  gamma = argmin || f - dF gamma ||  ;  x_next = g - dG gamma
+    where the columns of dF / dG are the differences of the last <= m residuals / results. This is the restatement the CUDA
+    path (NF_ACCEL_ANDERSON) is tested against."""
+
+    def __init__(self, m=5, beta=1.0):
+        self.m, self.beta, self.reg, self.max_rel = int(m), float(beta), 1e-8, 0.3
+        self.dF, self.dG, self.f_prev, self.g_prev = [], [], None, None
+
+    def step(self, x, g):
+        f = g - x
+        if self.f_prev is not None:
+            self.dF.append(f - self.f_prev)
+            self.dG.append(g - self.g_prev)
+            if len(self.dF) > self.m:
+                self.dF.pop(0)
+                self.dG.pop(0)
+        self.f_prev, self.g_prev = f.copy(), g.copy()
+        if not self.dF:
+            return g
+        F = np.stack(self.dF, axis=1)
+        A = F.T @ F
+        A = A + self.reg * max(float(np.max(np.diag(A))), 1e-300) * np.eye(A.shape[0])
+        gamma = np.linalg.solve(A, F.T @ f)
+        corr = np.zeros_like(g)
+        for j, dg in enumerate(self.dG):
+            corr += gamma[j] * (dg - (1.0 - self.beta) * self.dF[j])
+        gn, cn = np.linalg.norm(g), np.linalg.norm(corr)
+        if gn > 0 and cn / gn > self.max_rel:
+            corr *= self.max_rel * gn / cn
+        return (x + self.beta * f if self.beta != 1.0 else g) - corr
+
+
 class SchurSolverOracle:
     """reference include/solvers.hpp:251-483, src/solvers.cpp:67-240, 259-314, 535-636."""
 
@@ -564,7 +639,7 @@ class OracleNeutFEM:
 
     # ---- SolveKeff (NeutFEM.cpp:1627-1815)
     def SolveKeff(self, use_coarse_init=False, coarse_factors=(), use_diagonal_solver=False, use_cmfd=False,
-                  max_outer_override=None):
+                  max_outer_override=None, accel_kind="chebyshev"):
         assert not use_cmfd, "CMFD is out of scope (SURVEY section 2)"
         f, ng, nP, nJ = self.fes, self.ng, self.fes.n_Phi, self.fes.n_J
         st = self.stats = SolveStats()
@@ -579,6 +654,7 @@ class OracleNeutFEM:
             self.Sol_Phi = flux_c
             keff = keff_c
         accel = ChebyshevAccel(15, 0.98)
+        anderson = AndersonAccel(5, 1.0) if accel_kind == "anderson" else None
         n_outer = self.max_outer if max_outer_override is None else int(max_outer_override)
         for it in range(n_outer):
             old = self.Sol_Phi.copy()
@@ -615,7 +691,10 @@ class OracleNeutFEM:
             if norm > 1e-14:
                 self.Sol_Phi /= norm
             if it >= 2:
-                self.Sol_Phi = accel(self.Sol_Phi)
+                if accel_kind == "chebyshev":
+                    self.Sol_Phi = accel(self.Sol_Phi)
+                elif anderson is not None:
+                    self.Sol_Phi = anderson.step(old, self.Sol_Phi)
             st.outer_iterations = it + 1
             if diff_k < self.tol_keff and diff_flux < self.tol_flux:
                 st.converged = True

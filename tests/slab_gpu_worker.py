@@ -21,7 +21,8 @@ def main():
     ok = True
     msgs = []
     for (n, rt, pp) in [((9, 7, 11), 1, 1), ((6, 5, 2 * world), 2, 2), ((33, 4, 3 * world + 1), 0, 0), ((5, 6, 7), 2, 1),
-                        ((16, 9, 3 * world + 2), 1, 1), ((264, 6, 2 * world), 1, 0), ((12, 40, 2 * world + 1), 2, 2)]:   # even nx: x-row / y-column kernels
+                        ((16, 9, 3 * world + 2), 1, 1), ((264, 6, 2 * world), 1, 0), ((12, 40, 2 * world + 1), 2, 2),    # even nx: x-row / y-column kernels
+                        ((96, 96, 12 * world + 2), 1, 1)]:   # mid-size, UNEVEN slabs: every collective-affecting decision must be rank-invariant
         p = random_problem(17, 3, n, ng=2, bc="mixed")
         p["NSF"] *= 3.0
         nx, ny, nz = n

@@ -121,3 +121,49 @@ def test_cg_lines_equals_oracle(n, rt):
     assert abs(it - s.last_iterations) <= 2 and res < 1e-10
     assert relerr(sol, ref) < 1e-9
     assert LinesCG.threads() >= 1
+
+
+def test_reference_anderson_formula_returns_the_previous_iterate():
+    """The reference's AndersonAccel::operator() (src/solvers.cpp:772-891, never instantiated) solves a least-squares problem whose
+    right-hand side is the last column of its own matrix: alpha = e_last, the correction is x_new - x_old and the 'accelerated'
+    vector is the previous iterate (up to the 1e-8 Tikhonov term). This is why the product implements the standard type-II
+    formulation with the reference's parameters instead (oracle AndersonAccel, NF_ACCEL_ANDERSON)."""
+    from oracle.neutfem_oracle import AndersonAccelReference
+    rng = np.random.default_rng(0)
+    M = rng.uniform(-1.0, 1.0, (30, 30))
+    M = 0.5 * (M + M.T)
+    M *= 0.9 / np.max(np.abs(np.linalg.eigvalsh(M)))
+    b = rng.uniform(0.0, 1.0, 30)
+    acc = AndersonAccelReference(5, 1.0)
+    x = np.zeros(30)
+    raw = []
+    for it in range(6):
+        g = M @ x + b                    # one fixed-point step from the vector the accelerator returned
+        raw.append(g.copy())
+        x = acc(g)
+        if it >= 1:
+            # relative step 0.3 clamp aside, what comes back is (up to the Tikhonov damping of nearly collinear columns) the
+            # PREVIOUS raw iterate: the step just taken is undone instead of being extrapolated
+            d_prev, d_new = np.linalg.norm(x - raw[it - 1]), np.linalg.norm(x - raw[it])
+            step = np.linalg.norm(raw[it] - raw[it - 1])
+            if step / np.linalg.norm(raw[it]) <= 0.3:
+                assert d_prev < 0.25 * step and d_new > 0.8 * step
+
+
+def test_anderson_restatement_accelerates_the_power_iteration():
+    """oracle AndersonAccel (type-II, m = 5, beta = 1, Tikhonov 1e-8, clamp 0.3) inside the oracle's SolveKeff: same k as the
+    Chebyshev run, fewer outer iterations."""
+    from neutfem_b200 import benchmarks as bm
+    from oracle.neutfem_oracle import BICGSTAB
+    p = bm.problem_2d("iaea2d", 1)
+    out = {}
+    for kind in ("chebyshev", "anderson"):
+        o = OracleNeutFEM(0, 0, p.ng, p.x_breaks, p.y_breaks, p.z_breaks)
+        o.set_linear_solver(BICGSTAB)
+        o.set_tol(1e-8, 1e-8, 1e-8, 1000, 5000)
+        p.apply(o)
+        o.BuildMatrices()
+        out[kind] = (o.SolveKeff(accel_kind=kind), o.stats.outer_iterations, o.stats.converged)
+    assert out["anderson"][2] and out["chebyshev"][2]
+    assert abs(out["anderson"][0] - out["chebyshev"][0]) < 5e-8
+    assert out["anderson"][1] < out["chebyshev"][1]
