@@ -380,13 +380,17 @@ static int rows_prepare_t(nf_ctx *c)
     if (xcap > 0) per_sm = std::min(per_sm, xcap);
     const long long nrows = (long long)c->ny * c->nz;
     c->xrow_grid = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(kRedBlocks, (long long)per_sm * c->sm_count), (nrows + kXW - 1) / kXW));
-    c->ycol3 = env_int("NF_YCOL", 3) != 0;
+    c->ycol3 = env_int("NF_YCOL", 0) != 0;        // default: k_ycol (k_ycol3 measured slower at 3 CTAs / SM: its shared-memory columns leave the SM ~7 KB of L1)
     const size_t ysmem3 = (size_t)(2 * c->rg.LcY + 4) * ynt * sizeof(double2);
     if (ysmem3 + 2048 > c->smem_optin) c->ycol3 = 0;
     if (ynt != 128) NF_FAIL(c, NF_ERR_STATE, "y-column kernels are built for 128-thread CTAs");
     if (c->ycol3) {
         CU(c, cudaFuncSetAttribute(k_ycol3<K, M1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ysmem3));
+        const int carve = env_int("NF_YCOL3_CARVE", 0);      // % of the unified L1 / shared memory given to shared memory
+        if (carve > 0) CU(c, cudaFuncSetAttribute(k_ycol3<K, M1, 128>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
         CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ycol3<K, M1, 128>, 128, ysmem3));
+        const int ycap = env_int("NF_YCOL3_CTAS", 0);
+        if (ycap > 0) per_sm = std::min(per_sm, ycap);
     } else {
         CU(c, cudaFuncSetAttribute(k_ycol<K, M1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ysmem));
         CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ycol<K, M1, 128>, 128, ysmem));
@@ -1194,16 +1198,17 @@ static int power_iteration(nf_ctx *c, bool adjoint, int use_diag, int accel, dou
         aa.fprev = c->d_and[2 * kAndM]; aa.gprev = c->d_and[2 * kAndM + 1];
     }
     for (int it = 0; it < c->max_outer; ++it) {
-        CU(c, cudaMemcpyAsync(c->d_old, phi, ntot * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-        LAUNCH(c, k_total_fission, blocks, 256, 0, oa, c->d_tot, adjoint ? 1 : 0, c->d_part + 5 * kRedBlocks, c->d_ticket + 5, c->d_scal + 0);
+        // one sweep: Phi_old = Phi, total fission source (+ prod_old), right-hand side of the first group
+        LAUNCH(c, k_total_fission, blocks, 256, 0, oa, c->d_tot, adjoint ? 1 : 0, c->d_part + 5 * kRedBlocks, c->d_ticket + 5, c->d_scal + 0,
+               c->d_old, use_diag ? (double *)nullptr : c->d_rhs, 1.0 / keff, (const double *)nullptr);
         for (int g = 0; g < c->ng; ++g) {
-            LAUNCH(c, k_group_rhs, blocks, 256, 0, oa, c->d_tot, g, 1.0 / keff, adjoint ? 1 : 0, (const double *)nullptr, c->d_rhs);
-            if (use_diag) {
-                LAUNCH(c, k_diag_solve, ew_blocks(c->ne), 256, 0, c->d_sinv + (size_t)g * c->ne, c->d_rhs, phi + (size_t)g * np, c->ne);
-            } else {
-                int r = solve_group(c, g, c->d_rhs, phi + (size_t)g * np, nullptr, nullptr, st);
-                if (r) return r;
+            if (use_diag) {       // diagonal RT0-P0 path: source build + divide in one stencil kernel per group
+                LAUNCH(c, k_diag_group, ew_blocks(c->ne), 256, 0, oa, c->d_tot, g, 1.0 / keff, c->d_sinv + (size_t)g * c->ne, phi + (size_t)g * np);
+                continue;
             }
+            if (g > 0) LAUNCH(c, k_group_rhs, blocks, 256, 0, oa, c->d_tot, g, 1.0 / keff, adjoint ? 1 : 0, (const double *)nullptr, c->d_rhs);
+            int r = solve_group(c, g, c->d_rhs, phi + (size_t)g * np, nullptr, nullptr, st);
+            if (r) return r;
         }
         LAUNCH(c, k_outer_post, blocks, 256, 0, oa, c->d_old, adjoint ? 1 : 0, c->d_part + 5 * kRedBlocks, c->d_ticket + 5, c->d_scal + 1);
         { int r = allreduce_sum(c, c->d_scal, 4); if (r) return r; }
@@ -1370,10 +1375,10 @@ int nf_solve_source(nf_ctx *c, double *amplification, nf_stats *stats)
         LAUNCH(c, k_fill, ew_blocks(ntot), 256, 0, c->d_phi, ntot, 0.0);
         double prev = -1.0;
         for (int it = 0; it < c->max_outer; ++it) {
-            CU(c, cudaMemcpyAsync(c->d_old, c->d_phi, ntot * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-            LAUNCH(c, k_total_fission, blocks, 256, 0, oa, c->d_tot, 0, c->d_part + 5 * kRedBlocks, c->d_ticket + 5, c->d_scal + 0);
+            LAUNCH(c, k_total_fission, blocks, 256, 0, oa, c->d_tot, 0, c->d_part + 5 * kRedBlocks, c->d_ticket + 5, c->d_scal + 0,
+                   c->d_old, c->d_rhs, pass ? 1.0 : 0.0, (const double *)c->d_SRC);
             for (int g = 0; g < c->ng; ++g) {
-                LAUNCH(c, k_group_rhs, blocks, 256, 0, oa, c->d_tot, g, pass ? 1.0 : 0.0, 0, (const double *)c->d_SRC, c->d_rhs);
+                if (g > 0) LAUNCH(c, k_group_rhs, blocks, 256, 0, oa, c->d_tot, g, pass ? 1.0 : 0.0, 0, (const double *)c->d_SRC, c->d_rhs);
                 int r = solve_group(c, g, c->d_rhs, c->d_phi + (size_t)g * np, nullptr, nullptr, &st);
                 if (r) return r;
             }

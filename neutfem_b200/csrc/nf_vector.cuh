@@ -238,10 +238,16 @@ struct OuterArgs {
     double wM[kMaxModes];   // mass weight of a mode / 2^dim (P0: 1)
 };
 
-// total_fiss = sum_g M_fiss[g] phi_g, prod = sum(total_fiss)      (NeutFEM.cpp:1700-1707; matrices :1204-1252)
-// adjoint != 0: total = sum_g M_chi[g] phi_g, prod = sum_e (sum_g NSF_g) total[mode 0]   (NeutFEM.cpp:1919-1932)
+// First pass of an outer iteration, one sweep over the flux (NeutFEM.cpp:1694-1726):
+//   old = phi (the copy the reference makes at :1696, written here instead of by a separate device-to-device copy);
+//   total_fiss = sum_g M_fiss[g] phi_g, prod = sum(total_fiss)                    (:1700-1707; matrices :1204-1252);
+//   rhs of the FIRST group: chi_0/k * total_fiss + sum_{g' != 0} M_scatter[g' -> 0] phi_g' (+ fixed source)   (:1713-1726) --
+//   no group has been updated yet, so this is exactly what k_group_rhs(g = 0) would compute from the same data.
+// adjoint != 0: total = sum_g M_chi[g] phi_g, prod = sum_e (sum_g NSF_g) total[mode 0]   (NeutFEM.cpp:1919-1932), rhs with
+// the transposed scatter and nsf_0/k (:1936-1950). old / rhs0 may be nullptr (only the source is wanted).
 __global__ void __launch_bounds__(256) k_total_fission(const OuterArgs a, double *__restrict__ tot, int adjoint,
-                                                       double *part, unsigned *ticket, double *out)
+                                                       double *part, unsigned *ticket, double *out, double *__restrict__ old,
+                                                       double *__restrict__ rhs0, double inv_k, const double *__restrict__ src)
 {
     const long long n = a.ne * a.nloc;
     double acc = 0.0;
@@ -250,11 +256,23 @@ __global__ void __launch_bounds__(256) k_total_fission(const OuterArgs a, double
         const double mw = a.vol[e] * a.wM[mode];
         double s = 0.0, nsf_tot = 0.0;
         for (int g = 0; g < a.ng; ++g) {
+            const double ph = a.phi[(size_t)g * n + i];
+            if (old) old[(size_t)g * n + i] = ph;
             const double c = thr14(adjoint ? a.Chi[(size_t)g * a.ne + e] : a.NSF[(size_t)g * a.ne + e]);
-            s += c * mw * a.phi[(size_t)g * n + i];
+            s += c * mw * ph;
             if (adjoint) nsf_tot += a.NSF[(size_t)g * a.ne + e];
         }
         tot[i] = s;
+        if (rhs0) {         // same operations in the same order as k_group_rhs(g = 0)
+            double r = (adjoint ? a.NSF[e] : a.Chi[e]) * inv_k * s;
+            for (int gp = 1; gp < a.ng; ++gp) {
+                const size_t idx = adjoint ? ((size_t)gp * a.ng) : (size_t)gp;        // [0 -> gp] transposed / [gp -> 0]
+                const double sg = thr14(a.SigS[idx * a.ne + e]);
+                if (sg != 0.0) r += sg * mw * a.phi[(size_t)gp * n + i];
+            }
+            if (src && mode == 0) r += src[e] * a.vol[e];
+            rhs0[i] = r;
+        }
         acc += adjoint ? ((mode == 0) ? nsf_tot * s : 0.0) : s;
     }
     double v[1] = {acc};
@@ -386,6 +404,24 @@ __global__ void k_diag_solve(const double *__restrict__ sinv, const double *__re
 {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         phi[i] = sinv[i] * rhs[i];
+}
+
+// Diagonal RT0-P0 path, one group as ONE stencil kernel: source build (k_group_rhs, RT0-P0: one DOF per cell,
+// mass weight = cell volume) and phi_g = rhs / S_ee (NeutFEM.cpp:607-617) in registers; the rhs vector is never written.
+__global__ void __launch_bounds__(256) k_diag_group(const OuterArgs a, const double *__restrict__ tot, int g, double inv_k,
+                                                    const double *__restrict__ sinv, double *__restrict__ phi_g)
+{
+    const long long n = a.ne;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const double mw = a.vol[e];
+        double s = a.Chi[(size_t)g * a.ne + e] * inv_k * tot[e];
+        for (int gp = 0; gp < a.ng; ++gp) {
+            if (gp == g) continue;
+            const double sg = thr14(a.SigS[((size_t)g * a.ng + gp) * a.ne + e]);
+            if (sg != 0.0) s += sg * mw * a.phi[(size_t)gp * n + e];
+        }
+        phi_g[e] = sinv[e] * s;
+    }
 }
 
 // Jacobi preconditioner: 1/diag(S) per flux DOF, SoA. diag(S)_mode(e) = C + local bubble terms

@@ -4,7 +4,8 @@
    profiles/<tag>_launches.csv   the raw ncu launch list
    profiles/<tag>_full_<kernel>.raw.csv   the raw metric pages
    profiles/traffic.json         DRAM bytes per DOF of one CG iteration (read by bench.py for roofline.traffic)
-usage: tools/summarize_profiles.py TAG [--full-dofs N]   (N = DOFs per group of the mesh the --set full captures ran on)"""
+usage: tools/summarize_profiles.py TAG [--full-dofs N]   (N = DOFs per group of the mesh the --set full captures ran on)
+Also extracts the SASS evidence (UBLKCP / SYNCS / LDGSTS counts of the x-row kernel) from the built library with cuobjdump."""
 import collections
 import csv
 import json
@@ -86,7 +87,7 @@ elif bench:
 tot_bytes = 0.0
 tot_ms = 0.0
 table = []
-for k in ("k_xrow", "k_ycol", "k_zfwd", "k_zback_update"):
+for k in ("k_xrow", "k_ycol3", "k_zfwd2", "k_zback2"):
     f = os.path.join(G, f"{tag}_full_{k}.raw.csv")
     if not os.path.exists(f):
         continue
@@ -113,6 +114,27 @@ if table:
     with open(os.path.join(P, "traffic.json"), "w") as fh:
         json.dump({"tag": tag, "path": 3, "dofs_per_launch": full_dofs, "dram_bytes_per_dof_per_cg_iteration": tot_bytes / full_dofs,
                    "kernels": {k: {"ms": ms, "dram_read": rd, "dram_write": wr} for k, _, ms, rd, wr, _, _ in table}}, fh, indent=1)
+try:
+    import re
+    import subprocess
+    lib = os.path.join(ROOT, "neutfem_b200", "lib", "libneutfem_b200.so")
+    sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True, timeout=600).stdout
+    cur, counts = None, collections.OrderedDict()
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            continue
+        if cur and "k_xrowILi1ELi2ELi1ELi17ELi17" in cur:
+            for op in ("UBLKCP", "SYNCS", "LDGSTS", "DFMA", "SHFL"):
+                if re.search(r"\b" + op, line):
+                    counts[op] = counts.get(op, 0) + 1
+    if counts:
+        out += ["## SASS of the bench variant of k_xrow (cuobjdump -sass, sm_100a cubin)", "",
+                "`cp.async.bulk` -> `UBLKCP`, `mbarrier.*` -> `SYNCS`, per-lane `cp.async` (line factors) -> `LDGSTS`:", "",
+                ", ".join(f"{k}: {v}" for k, v in counts.items()), ""]
+except Exception as e:      # cuobjdump missing: skip the section
+    out += [f"(SASS section skipped: {e})", ""]
 with open(os.path.join(P, f"{tag}_summary.md"), "w") as fh:
     fh.write("\n".join(out) + "\n")
 print("\n".join(out))
