@@ -188,10 +188,49 @@ def cpu_port(args, mesh, outers):
                       f"{int(sum(st.cg_iterations))} CG iterations, {dt:.1f} s"}
 
 
+def cpu_real_reference(args, mesh, outers, port):
+    """The REAL reference module (oracle/_ref, built by oracle/ref_build/build_ref.py on a box that has Eigen), timed on the same
+    sample as the single-thread port. Its binding does not expose CG iteration counts (SchurSolver::GetLastIterations is not
+    bound), so the DOF-iteration count of the oracle port -- the same algorithm on the same inputs -- is used for the rate.
+    Returns None when oracle/_ref does not exist (this container: no Eigen headers)."""
+    try:
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("build_ref", os.path.join(ROOT, "oracle", "ref_build", "build_ref.py"))
+        br = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(br)
+        ref = br.load()
+        if ref is None:
+            return None
+        from neutfem_b200 import benchmarks as bm
+        p = bm.problem_iaea3d_synthetic(*mesh)
+        s = ref.NeutFEM(args.rt, args.p, p.ng, p.x_breaks, p.y_breaks, p.z_breaks) if args.rt != args.p else ref.NeutFEM(
+            args.rt, p.ng, p.x_breaks, p.y_breaks, p.z_breaks)
+        s.set_verbosity(ref.VerbosityLevel.SILENT)
+        s.set_linear_solver(ref.LinearSolverType.BICGSTAB)
+        for a, t, v in p.bcs:
+            s.set_bc(int(a), ref.BCType(int(t)), float(v))
+        p.apply(s)
+        s.BuildMatrices()
+        s.set_tol(1e-5, 1e-4, 1e-4, int(outers), 1000)
+        t0 = time.perf_counter()
+        k = s.SolveKeff()
+        dt = time.perf_counter() - t0
+        dof_its = port["cg_iterations"] * port["n_phi_per_group"]
+        return {"value": dof_its / dt / 1e9, "unit": UNIT, "cores": 1, "kind": "reference", "mesh": list(mesh), "seconds": dt, "keff": k,
+                "sample": f"the reference's own module (oracle/_ref, Eigen SparseLU + CG, 1 thread) on synthetic IAEA-3D {mesh[0]}x{mesh[1]}x{mesh[2]}, "
+                          f"{outers} outer iterations, {dt:.1f} s; CG iterations counted by the oracle port"}
+    except Exception as e:      # never let the optional arm break the bench line
+        return {"unavailable": f"{type(e).__name__}: {e}"}
+
+
 def cpu_baseline(args):
-    """cpu_baseline block of the GPU arm: the all-cores restatement (headline: `value`, `cores`) and the single-thread port."""
+    """cpu_baseline block of the GPU arm: the all-cores restatement (headline: `value`, `cores`), the single-thread port and,
+    when oracle/_ref exists, the real reference on the same single-thread sample."""
     out = cpu_lines(args, tuple(args.cpu_mesh), 40, 12.0)
     out["single_thread_port"] = cpu_port(args, tuple(args.cpu_port_mesh), 2)
+    real = cpu_real_reference(args, tuple(args.cpu_port_mesh), 2, out["single_thread_port"])
+    if real is not None:
+        out["real_reference"] = real
     return out
 
 
@@ -215,6 +254,9 @@ def run_reference(args):
     cb = cpu_lines(args, mesh, 40, 20.0 * max(args.steps, 1))
     dt = time.perf_counter() - t0
     cb["single_thread_port"] = cpu_port(args, tuple(args.cpu_port_mesh), 2)
+    real = cpu_real_reference(args, tuple(args.cpu_port_mesh), 2, cb["single_thread_port"])
+    if real is not None:
+        cb["real_reference"] = real
     if not args.no_ladder:
         cb.update({k: v for k, v in cpu_baseline_ladder(args).items()})
     cfg = workload_config(args, tuple(args.mesh))

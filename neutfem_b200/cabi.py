@@ -239,7 +239,7 @@ class Context:
         self._ck(self._L.nf_time_kernels(self._h, int(g), int(reps), int(fast), _dp(out)), "nf_time_kernels")
         return dict(sweep_x=out[0], sweep_y=out[1], sweep_z=out[2], cg_update=out[3], cg_pupdate=out[4], cg_iteration=out[5],
                     zfwd=out[6], zback_update=out[7], cg_iteration_separate=out[8], xrow=out[9], ycol=out[10],
-                    path=out[12])
+                    path=out[12], slab_neighbour_mode=out[13], slab_coupling=out[14])
 
     def comm_init(self, id_bytes, rank, nranks):
         self._ck(self._L.nf_comm_init(self._h, id_bytes, int(rank), int(nranks)), "nf_comm_init")

@@ -70,6 +70,10 @@ struct nf_ctx {
     double *d_E = nullptr, *d_Eall = nullptr;      // [g][3][nxy], [g][nranks][3][nxy]
     double *d_vG = nullptr, *d_vGall = nullptr;    // [2][nt][nxy], [nranks][2][nt][nxy]
     double *d_lam = nullptr;                       // [2][nt][nxy] interface multipliers of this rank (fused slab update)
+    double *d_vGnb = nullptr;                      // [2][nt][nxy] neighbour mode: v_n of the rank below, v_0 of the rank above
+    std::vector<int> s0cut;                        // [g] planes beyond which column 0 of the local z-line inverses is below rounding
+    int slab_nb = 0;                               // 1: interface coupling across a slab is below rounding: neighbour exchange only
+    double slab_coupling = 0.0;                    // max |G_0n| / sqrt(G_00 G_nn) over lines, groups and ranks
     // ---- CG-iteration path of 3-D contexts (nf_rows.cuh, nf_fused.cuh)
     int fused = -1;                        // -1: not yet decided, 0: separate kernels, 2: hybrid, 3: rows, 5: rows on a z-slab rank
     double *d_zs = nullptr;                // z-forward intermediates
@@ -337,8 +341,14 @@ static bool rows_geometry(const nf_ctx *c, RowGeom &g)
     g.pitchJ = pj;
     const int rows = g.PWx * c->M1;
     g.offPO = 2 * (g.NFx + 2) + rows * g.pitchP;
-    const int po = std::max(rows * c->nx, g.PWx * g.pitchJ);
-    g.offJAC = g.offPO + ((po + 1) & ~1);
+    const int jd = g.PWx * g.pitchJ;
+    if (kXPF) {                                   // p_old / M^-1 of the next pass are prefetched: J needs its own tile
+        g.offJ = g.offPO + ((rows * c->nx + 1) & ~1);
+        g.offJAC = g.offJ + ((jd + 1) & ~1);
+    } else {                                      // J reuses the consumed p_old tile
+        g.offJ = g.offPO;
+        g.offJAC = g.offPO + ((std::max(rows * c->nx, jd) + 1) & ~1);
+    }
     const int jacd = (rows * c->nx * (int)sizeof(jac_t) + 7) / 8;
     g.offBAR = g.offJAC + ((jacd + 1) & ~1);
     g.xsmemW = g.offBAR + 2;
@@ -510,7 +520,7 @@ static void fill_fused_args(nf_ctx *c, FusedArgs &a, int g, double *x, const jac
     }
     a.D = c->d_D + (size_t)g * c->ne; a.SigR = c->d_SigR + (size_t)g * c->ne; a.vol = c->d_vol;
     a.zs = c->d_zs; a.st = c->d_cg;
-    if (c->slab) { a.s0 = c->d_s0[g]; a.vG = c->d_vG; }
+    if (c->slab) { a.s0 = c->d_s0[g]; a.vG = c->d_vG; a.s0cut = c->s0cut.empty() ? c->nz + 1 : c->s0cut[g]; }
     a.red_part = c->d_part + (size_t)4 * kRedBlocks; a.ticket2 = c->d_ticket + 4;
     a.ne = c->ne; a.nxy = (long long)c->nx * c->ny;
     a.nx = c->nx; a.ny = c->ny; a.nz = c->nz; a.nt = c->nt; a.nloc = c->nloc;
@@ -576,7 +586,21 @@ static int slab_iteration_t(nf_ctx *c, const FusedArgs &fa, int g, double tol, i
     if (which & 4) {
         k_zfwd2<K, M1, true><<<c->zf_grid, 128, 0, zs>>>(fa, c->d_part + (size_t)2 * kRedBlocks, c->d_ticket + 2, &c->d_cg->pAp[2]);
         ++g_launches; ++c->launches_call;
-        NC(c, ncclAllGather(c->d_vG, c->d_vGall, (size_t)2 * c->nt * c->nxy, ncclDouble, c->comm, zs));
+        const size_t half = (size_t)c->nt * c->nxy;
+        if (c->slab_nb) {           // neighbour mode: v_0 goes down, v_n goes up
+            NC(c, ncclGroupStart());
+            if (c->rank > 0) {
+                NC(c, ncclSend(c->d_vG, half, ncclDouble, c->rank - 1, c->comm, zs));
+                NC(c, ncclRecv(c->d_vGnb, half, ncclDouble, c->rank - 1, c->comm, zs));
+            }
+            if (c->rank < c->nranks - 1) {
+                NC(c, ncclSend(c->d_vG + half, half, ncclDouble, c->rank + 1, c->comm, zs));
+                NC(c, ncclRecv(c->d_vGnb + half, half, ncclDouble, c->rank + 1, c->comm, zs));
+            }
+            NC(c, ncclGroupEnd());
+        } else {
+            NC(c, ncclAllGather(c->d_vG, c->d_vGall, 2 * half, ncclDouble, c->comm, zs));
+        }
     }
     if (overlap) {
         CU(c, cudaEventRecord(c->evz, c->stream2));
@@ -591,7 +615,9 @@ static int slab_iteration_t(nf_ctx *c, const FusedArgs &fa, int g, double tol, i
         u.red_part = c->d_part + (size_t)4 * kRedBlocks; u.ticket = c->d_ticket + 4; u.pcg = fa.pcg;
         a.red_out = &c->d_cg->pAp[3];
         a.red_part = c->d_part + (size_t)3 * kRedBlocks; a.ticket = c->d_ticket + 3;
-        LAUNCH(c, (k_slab_iface<K, M1>), (int)std::max<long long>(1, std::min<long long>(kRedBlocks, (c->nxy * c->nt + 127) / 128)), 128, 0, a, u);
+        const int igrid = (int)std::max<long long>(1, std::min<long long>(kRedBlocks, (c->nxy * c->nt + 127) / 128));
+        if (c->slab_nb) LAUNCH(c, (k_slab_iface_nb<K, M1>), igrid, 128, 0, a, u, (const double *)c->d_vGnb);
+        else LAUNCH(c, (k_slab_iface<K, M1>), igrid, 128, 0, a, u);
         { int r = allreduce_sum(c, c->d_cg->pAp, 4); if (r) return r; }
         LAUNCH(c, (k_zback2<K, M1, true>), c->zb_grid, 128, 0, fa, (const double *)c->d_lam);
         { int r = allreduce_sum(c, c->d_cg->tmp, 2); if (r) return r; }
@@ -824,7 +850,7 @@ int nf_destroy(nf_ctx *c)
     for (int d = 0; d < 3; ++d) for (int ax = 0; ax < 3; ++ax) if (c->d_F[d][ax]) cudaFree(c->d_F[d][ax]);
     for (int d = 0; d < 3; ++d) if (c->d_iFx[d]) cudaFree(c->d_iFx[d]);
     for (double *p : c->d_s0) if (p) cudaFree(p);
-    for (double *p : {c->d_E, c->d_Eall, c->d_vG, c->d_vGall, c->d_lam, c->d_zs}) if (p) cudaFree(p);
+    for (double *p : {c->d_E, c->d_Eall, c->d_vG, c->d_vGall, c->d_lam, c->d_vGnb, c->d_zs}) if (p) cudaFree(p);
     for (double *p : c->d_and) if (p) cudaFree(p);
     if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
     for (cudaEvent_t e : {c->evx, c->evz}) if (e) cudaEventDestroy(e);
@@ -926,6 +952,34 @@ int nf_build(nf_ctx *c)
         for (int g = 0; g < c->ng; ++g)
             NC(c, ncclAllGather(c->d_E + (size_t)g * 3 * c->nxy, c->d_Eall + (size_t)g * c->nranks * 3 * c->nxy,
                                 (size_t)3 * c->nxy, ncclDouble, c->comm, c->stream));
+        // coupling between the two interfaces of a slab, max over lines, groups and ranks (identical on every rank)
+        unsigned long long *d_max = (unsigned long long *)(c->d_scal + 48);
+        CU(c, cudaMemsetAsync(d_max, 0, sizeof(unsigned long long), c->stream));
+        for (int g = 0; g < c->ng; ++g)
+            LAUNCH(c, k_slab_coupling, ew_blocks(c->nxy), 256, 0, c->d_E + (size_t)g * 3 * c->nxy, c->nxy, d_max);
+        NC(c, ncclAllReduce(c->d_scal + 48, c->d_scal + 48, 1, ncclDouble, ncclMax, c->comm, c->stream));
+        CU(c, cudaMemcpyAsync(c->h_scal + 48, c->d_scal + 48, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+        c->slab_coupling = c->h_scal[48];
+        c->slab_nb = (c->slab_coupling < 1e-20 && env_int("NF_SLAB_NB", 1)) ? 1 : 0;
+        // decay of column 0 of the local inverses: the z kernels stop loading it where it is below 1e-22 of its first entry
+        c->s0cut.assign(c->ng, c->nz + 1);
+        if (env_int("NF_SLAB_S0CUT", 1)) {
+            unsigned long long *d_dec = nullptr;
+            CU(c, cudaMalloc((void **)&d_dec, (size_t)(c->nz + 1) * sizeof(unsigned long long)));
+            std::vector<double> dec(c->nz + 1);
+            for (int g = 0; g < c->ng; ++g) {
+                CU(c, cudaMemsetAsync(d_dec, 0, (size_t)(c->nz + 1) * sizeof(unsigned long long), c->stream));
+                LAUNCH(c, k_slab_s0_decay, c->nz + 1, 256, 0, c->d_s0[g], c->nxy, d_dec);
+                CU(c, cudaMemcpyAsync(dec.data(), d_dec, (size_t)(c->nz + 1) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+                CU(c, cudaStreamSynchronize(c->stream));
+                int cut = c->nz + 1;
+                while (cut > 1 && dec[cut - 1] < 1e-22) --cut;          // every plane >= cut is below the threshold
+                c->s0cut[g] = cut;
+            }
+            cudaFree(d_dec);
+        }
+        if (c->slab_nb && !c->d_vGnb) { int r = dalloc(c, &c->d_vGnb, (size_t)2 * c->nt * c->nxy); if (r) return r; }
     }
     CU(c, cudaStreamSynchronize(c->stream));
     c->built = true; c->diag_valid = false; c->jac_valid = false;
@@ -1560,6 +1614,7 @@ int nf_time_kernels(nf_ctx *c, int g, int reps, int fast, double *ms_out)
     ms_out[8] = ms_out[5];                       // the separate-kernel iteration
     { int r = fused_setup(c); if (r) return r; }
     ms_out[12] = (double)c->fused;
+    ms_out[13] = (double)c->slab_nb; ms_out[14] = c->slab_coupling;
     if (c->fused == 2) {                          // hybrid path: separate direction update, x, y sweeps + k_zfwd + k_zback_update
         FusedArgs fa;
         fill_fused_args(c, fa, g, c->d_tot, jac);

@@ -33,6 +33,7 @@ struct FusedArgs {
     const double *Fy[3], *Fz[3], *iFx[3];
     double *zs;             // [(nz+1)][nt][ny][nx] z-forward intermediates
     const double *s0;       // z-slab ranks: column 0 of the local z-line inverses, face-indexed
+    int s0cut;              // z-slab ranks: s0_f is below 1e-22 |s0_0| on every line for f >= s0cut (it decays like 0.17^f): not loaded there
     double *vG;             // z-slab ranks: [2][nt][nxy] local solutions at the two interface faces
     CgState *st;
     double *red_part;       // z back: block partials
@@ -178,7 +179,7 @@ __global__ void __launch_bounds__(128, NF_ZF2_MINB) k_zfwd2(const FusedArgs a, d
                 }
                 if (f <= nz) {
                     lu[j] = ldg2(um + (size_t)f * sxy); lm[j] = ldg2(mi + (size_t)f * sxy);
-                    if (SLAB) ls[j] = ldg2(sp + (size_t)f * sxy);
+                    if (SLAB && f < a.s0cut) ls[j] = ldg2(sp + (size_t)f * sxy);
                 }
             }
 #pragma unroll
@@ -375,7 +376,7 @@ __global__ void __launch_bounds__(128, NF_ZB2_MINB) k_zback2(const FusedArgs a, 
                 lz[j] = lu[j] = lm[j] = ls[j] = zero2;
                 if (f >= 0) {
                     lz[j] = ldg2(zp + (size_t)f * nt * sxy); lu[j] = ldg2(um + (size_t)f * sxy); lm[j] = ldg2(mi + (size_t)f * sxy);
-                    if (SLAB) ls[j] = ldg2(sp + (size_t)f * sxy);
+                    if (SLAB && f < a.s0cut) ls[j] = ldg2(sp + (size_t)f * sxy);
                     if (f < nz) {
 #pragma unroll
                         for (int p = 0; p < M1; ++p) {
@@ -491,6 +492,67 @@ __global__ void __launch_bounds__(128) k_slab_iface(const SweepArgs a, const Sla
             lamn = (-myG0n * d0 + myG00 * dn) * idet;
         }
         acc += a.w[t] * (myv0 * lam0 + myvn * lamn);
+        u.lam[i] = lam0;
+        u.lam[nl + i] = lamn;
+    }
+    double v[1] = {acc};
+    grid_reduce<1>(v, a.red_part, a.ticket, a.red_out);
+}
+
+// ---- z-slab ranks, neighbour mode -----------------------------------------------------------------------------------------
+// The entries of the inverse of a condensed line matrix decay like 0.27^|i-j| (RT0), 0.17^|i-j| (RT1), 0.13^|i-j| (RT2)
+// ("hard parts"): once every slab is a few dozen planes thick, the coupling G_0n between the two
+// interfaces of a slab is below 1e-20 of the diagonal and the reduced interface system is diagonal TO ROUNDING -- every
+// operation of the full solve that involves G_0n changes its result by less than half an ulp. nf_build measures
+// max |G_0n| / sqrt(G_00 G_nn) over all lines, groups and ranks; below 1e-20 the ranks exchange only with their neighbours
+// (v_n up, v_0 down: 2 x 8.4 MB per rank at the bench size instead of a 134 MB all-gather) and k_slab_iface_nb solves the two
+// 1 x 1 interface equations of the rank. Thin slabs (the N-vs-1 parity mesh of bench.py, the small test meshes) keep the
+// all-gather + k_slab_iface path; both are tested against the single-GPU solve (tests/slab_gpu_worker.py).
+// max over the lines of |s0_f| / |s0_0| for every face plane f (one block per plane): nf_build derives s0cut from it
+__global__ void __launch_bounds__(256) k_slab_s0_decay(const double *__restrict__ s0, long long nxy, unsigned long long *out)
+{
+    const long long f = blockIdx.x;
+    double m = 0.0;
+    for (long long i = threadIdx.x; i < nxy; i += blockDim.x) m = fmax(m, fabs(s0[f * nxy + i]) / fabs(s0[i]));
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_down_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out + f, (unsigned long long)__double_as_longlong(m));
+}
+
+__global__ void __launch_bounds__(256) k_slab_coupling(const double *__restrict__ E, long long nxy, unsigned long long *out)
+{
+    double m = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nxy; i += (long long)gridDim.x * blockDim.x) {
+        const double G00 = E[i], G0n = E[nxy + i], Gnn = E[2 * nxy + i];
+        m = fmax(m, fabs(G0n) / sqrt(fabs(G00 * Gnn)));
+    }
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_down_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, (unsigned long long)__double_as_longlong(m));      // m >= 0: the bit pattern orders like the value
+}
+
+template <int K, int M1>
+__global__ void __launch_bounds__(128) k_slab_iface_nb(const SweepArgs a, const SlabUpd u, const double *__restrict__ vGnb)
+{
+    if (u.st->done) return;
+    const int P = a.nranks, me = a.rank;
+    const long long nl = a.nxy * a.nt;
+    double acc = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nl; i += (long long)gridDim.x * blockDim.x) {
+        const int t = (int)(i / a.nxy);
+        const long long lxy = i - (long long)t * a.nxy;
+        const double G00 = __ldg(a.Eall + ((size_t)me * 3 + 0) * a.nxy + lxy), Gnn = __ldg(a.Eall + ((size_t)me * 3 + 2) * a.nxy + lxy);
+        const double v0 = __ldg(a.vG + i), vn = __ldg(a.vG + nl + i);
+        double lam0 = 0.0, lamn = 0.0;
+        if (me > 0) {               // interface with the rank below: its v_n and G_nn, my v_0 and G_00
+            const double Gb = __ldg(a.Eall + ((size_t)(me - 1) * 3 + 2) * a.nxy + lxy), vb = __ldg(vGnb + i);
+            const double g = (vb / Gb + v0 / G00) / (1.0 / Gb + 1.0 / G00);
+            lam0 = (g - v0) / G00;
+        }
+        if (me < P - 1) {           // interface with the rank above: my v_n and G_nn, its v_0 and G_00
+            const double Ga = __ldg(a.Eall + ((size_t)(me + 1) * 3 + 0) * a.nxy + lxy), va = __ldg(vGnb + nl + i);
+            const double g = (vn / Gnn + va / Ga) / (1.0 / Gnn + 1.0 / Ga);
+            lamn = (g - vn) / Gnn;
+        }
+        acc += a.w[t] * (v0 * lam0 + vn * lamn);
         u.lam[i] = lam0;
         u.lam[nl + i] = lamn;
     }

@@ -33,6 +33,7 @@ struct RowGeom {
     int PWx, LcX, NFx;          // x lines: pairs per pass (1 / 2 / 4; 32 / PWx lanes per pair), faces per chunk, PWx-independent row length 32 / PWx * LcX
     int pitchP, pitchJ;         // shared-memory row pitches (doubles) of the P and J tiles
     int offPO, offJAC, offBAR;  // offsets (doubles) of the p_old / J tile, the M^-1 tile and the mbarrier inside a warp's slice
+    int offJ;                   // offset of the J tile (== offPO unless the p_old / M^-1 rows of the next pass are prefetched)
     int xsmemW;                 // doubles of shared memory per warp
     int bulk;                   // 1: rows are requested with cp.async.bulk (nx % 8 == 0: 16-byte aligned rows of every array)
     int Cy, LcY, colsY, warpsY; // y lines: chunks per line, faces per chunk, columns per item, warps per CTA
@@ -48,6 +49,11 @@ __device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned coun
 __device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, unsigned bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// adds `bytes` to the transaction count of the barrier's current (incomplete) phase without arriving on it
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
 {
@@ -153,6 +159,12 @@ __device__ __forceinline__ void chunk_bwd_final(double (&T)[LCT], const int jn, 
 // NCL = compile-time bound on the cells a lane owns (ceil(nx / 32)): per-cell cross-sections live in registers.
 // DEFER: x += alpha_prev * p_old, the solution update the previous iteration left pending (nf_fused.cuh).
 constexpr int kCB = 8;          // cells per lane in one batch of the output pass
+// NF_XPF = 1: the p_old and M^-1 rows of the NEXT pass are requested as soon as the direction update of this pass has consumed
+// its own (the J tile then needs its own buffer: 32 KB per warp, 7 warps per SM instead of 8); only r and x wait at the top of a pass.
+#ifndef NF_XPF
+#define NF_XPF 0
+#endif
+constexpr int kXPF = NF_XPF;
 
 template <int K, int M1, int PW, int NCL, int LCT, bool DEFER>
 __device__ __forceinline__ void xrow_warp(const FusedArgs &a, const RowGeom &g, const int iz, const int iy, const double beta,
@@ -163,7 +175,7 @@ __device__ __forceinline__ void xrow_warp(const FusedArgs &a, const RowGeom &g, 
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int n = a.nx, PP = g.pitchP, PJ = g.pitchJ;
-    double *UB = sm, *MINV = UB + NF + 2, *P = MINV + NF + 2, *PO = sm + g.offPO, *Jb = PO;
+    double *UB = sm, *MINV = UB + NF + 2, *P = MINV + NF + 2, *PO = sm + g.offPO, *Jb = sm + g.offJ;
     jac_t *JAC = reinterpret_cast<jac_t *>(sm + g.offJAC);
     unsigned long long *bar = reinterpret_cast<unsigned long long *>(sm + g.offBAR);
     const long long line = (long long)iz * a.ny + iy;
@@ -197,16 +209,17 @@ __device__ __forceinline__ void xrow_warp(const FusedArgs &a, const RowGeom &g, 
         const int np = min(PW, a.nt - t0), rows = np * M1;
         // ---- request the rows of this pass: r -> P, p_old -> PO, M^-1 -> JAC
         if (g.bulk) {
+            const bool pre = kXPF && t0 > 0;            // p_old / M^-1 of this pass were requested during the previous pass
             if (lane == 0) {
-                const unsigned bytes = (unsigned)rows * (unsigned)n * (8u * (need_po ? 2u : 1u) + (pcg ? 2u : 0u));
+                const unsigned bytes = (unsigned)rows * (unsigned)n * (8u * ((need_po && !pre) ? 2u : 1u) + ((pcg && !pre) ? 2u : 0u));
                 mbar_arrive_expect_tx(bar, bytes);
             }
             __syncwarp();
             if (lane < rows) {
                 const size_t off = (size_t)a.mode[0][t0 + lane / M1][lane % M1] * a.ne + e0;
                 bulk_g2s(P + lane * PP, a.r + off, (unsigned)n * 8u, bar);
-                if (need_po) bulk_g2s(PO + lane * n, a.p + off, (unsigned)n * 8u, bar);
-                if (pcg) bulk_g2s(JAC + lane * n, a.jac + off, (unsigned)n * 2u, bar);
+                if (need_po && !pre) bulk_g2s(PO + lane * n, a.p + off, (unsigned)n * 8u, bar);
+                if (pcg && !pre) bulk_g2s(JAC + lane * n, a.jac + off, (unsigned)n * 2u, bar);
             }
         } else {
             for (int m = 0; m < rows; ++m) {
@@ -256,6 +269,19 @@ __device__ __forceinline__ void xrow_warp(const FusedArgs &a, const RowGeom &g, 
             }
         }
         __syncwarp();
+        if (kXPF && g.bulk && t0 + PW < a.nt && (need_po || pcg)) {
+            // p_old and M^-1 of this pass are consumed: request those of the next pass now, behind the solve and the output
+            const int t1 = t0 + PW, rows1 = min(PW, a.nt - t1) * M1;
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_expect_tx(bar, (unsigned)rows1 * (unsigned)n * ((need_po ? 8u : 0u) + (pcg ? 2u : 0u)));
+            __syncwarp();
+            if (lane < rows1) {
+                const size_t off = (size_t)a.mode[0][t1 + lane / M1][lane % M1] * a.ne + e0;
+                if (need_po) bulk_g2s(PO + lane * n, a.p + off, (unsigned)n * 8u, bar);
+                if (pcg) bulk_g2s(JAC + lane * n, a.jac + off, (unsigned)n * 2u, bar);
+            }
+        }
         // ---- chunk ownership: lane = (pair slot s, chunk k)
         const bool tv = s < np;
         const int sp = tv ? s : 0;

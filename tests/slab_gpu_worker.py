@@ -22,7 +22,8 @@ def main():
     msgs = []
     for (n, rt, pp) in [((9, 7, 11), 1, 1), ((6, 5, 2 * world), 2, 2), ((33, 4, 3 * world + 1), 0, 0), ((5, 6, 7), 2, 1),
                         ((16, 9, 3 * world + 2), 1, 1), ((264, 6, 2 * world), 1, 0), ((12, 40, 2 * world + 1), 2, 2),    # even nx: x-row / y-column kernels
-                        ((96, 96, 12 * world + 2), 1, 1)]:   # mid-size, UNEVEN slabs: every collective-affecting decision must be rank-invariant
+                        ((96, 96, 12 * world + 2), 1, 1),    # mid-size, UNEVEN slabs: every collective-affecting decision must be rank-invariant
+                        ((16, 10, 32 * world + 1), 1, 1), ((8, 6, 40 * world), 0, 0)]:   # THICK slabs: neighbour-exchange mode of the interface solve
         p = random_problem(17, 3, n, ng=2, bc="mixed")
         p["NSF"] *= 3.0
         nx, ny, nz = n
@@ -40,6 +41,11 @@ def main():
                     Chi=s.local_planes(p["Chi"]), SigS=s.local_planes(p["SigS"], 2))
         c.build()
         nl = c.n_phi_loc
+        if nx % 2 == 0:
+            kt = c.time_kernels(0, 1, True)
+            thick = nz >= 32 * world
+            msgs.append(f"rank{rank} n={n} RT{rt}P{pp} path {int(kt['path'])} neighbour mode {int(kt['slab_neighbour_mode'])} coupling {kt['slab_coupling']:.1e}")
+            ok &= kt["path"] == 5.0 and int(kt["slab_neighbour_mode"]) == (1 if thick else 0)
         x = np.random.default_rng(5).uniform(0.5, 1.5, full.n_Phi)
         lo, hi = s.z0 * nx * ny * nl, s.z1 * nx * ny * nl
         for g in range(2):
