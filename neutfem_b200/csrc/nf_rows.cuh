@@ -165,6 +165,17 @@ constexpr int kCB = 8;          // cells per lane in one batch of the output pas
 #define NF_XPF 0
 #endif
 constexpr int kXPF = NF_XPF;
+// NF_XV2 = 1: the direction-update and output passes of the x rows work on PAIRS of adjacent cells (16-byte shared-memory and
+// global accesses): the kernel is bound by instruction latency at 2 warps per scheduler (ncu r02a: 85 thread-instructions per
+// DOF, issue slots 24 % busy, stalls on fixed-latency dependencies, shared-memory returns and instruction fetch), so halving
+// the memory instructions of those two passes is what shortens it.
+#ifndef NF_XV2
+#define NF_XV2 1
+#endif
+__device__ __forceinline__ double2 jac_pair(const unsigned v)        // two adjacent 16-bit entries -> two doubles
+{
+    return make_double2(__hiloint2double((int)(v << 16), 0), __hiloint2double((int)(v & 0xffff0000u), 0));
+}
 
 template <int K, int M1, int PW, int NCL, int LCT, bool DEFER>
 __device__ __forceinline__ void xrow_warp(const FusedArgs &a, const RowGeom &g, const int iz, const int iy, const double beta,
@@ -194,12 +205,24 @@ __device__ __forceinline__ void xrow_warp(const FusedArgs &a, const RowGeom &g, 
         asm volatile("cp.async.commit_group;\n" ::: "memory");
     }
     // per-cell cross-sections of the lane's cells: requested now, first used in the output pass of the first pair
+#if NF_XV2
+    constexpr int NCP = (NCL + 1) / 2;          // pairs of adjacent cells a lane owns in the coalesced passes
+    const int nq = n >> 1;                      // n is even on the rows paths
+    const double2 zero2 = make_double2(0.0, 0.0), one2 = make_double2(1.0, 1.0);
+    double2 Dv[NCP], Sv[NCP];
+#pragma unroll
+    for (int c = 0; c < NCP; ++c) {
+        const int q = min(lane + 32 * c, nq - 1);
+        Dv[c] = ldg2(a.D + e0 + 2 * q); Sv[c] = ldg2(a.SigR + e0 + 2 * q);
+    }
+#else
     double Dv[NCL], Sv[NCL];
 #pragma unroll
     for (int c = 0; c < NCL; ++c) {
         const int ixl = min(lane + 32 * c, n - 1);
         Dv[c] = __ldg(a.D + e0 + ixl); Sv[c] = __ldg(a.SigR + e0 + ixl);
     }
+#endif
     const double fy0 = __ldg(a.Fy[0] + iy), fy1 = __ldg(a.Fy[1] + iy), fy2 = __ldg(a.Fy[2] + iy);
     const double fz0 = __ldg(a.Fz[0] + iz), fz1 = __ldg(a.Fz[1] + iz), fz2 = __ldg(a.Fz[2] + iz);
     const double ify0 = 1.0 / (fy0 * fz0), ify1 = 1.0 / (fy1 * fz1), ify2 = 1.0 / (fy2 * fz2);
@@ -233,6 +256,17 @@ __device__ __forceinline__ void xrow_warp(const FusedArgs &a, const RowGeom &g, 
             asm volatile("cp.async.commit_group;\n" ::: "memory");
         }
         // ---- x of the lane's cells (deferred update): requested into registers while the rows are in flight
+#if NF_XV2
+        double2 xv[NR][NCP];
+        if (xupd) {
+#pragma unroll
+            for (int m = 0; m < NR; ++m) {
+                const size_t off = (size_t)a.mode[0][min(t0 + m / M1, a.nt - 1)][m % M1] * a.ne + e0;
+#pragma unroll
+                for (int c = 0; c < NCP; ++c) xv[m][c] = *reinterpret_cast<const double2 *>(a.x + off + 2 * min(lane + 32 * c, nq - 1));
+            }
+        }
+#else
         double xv[NR][NCL];
         if (xupd) {
 #pragma unroll
@@ -242,10 +276,36 @@ __device__ __forceinline__ void xrow_warp(const FusedArgs &a, const RowGeom &g, 
                 for (int c = 0; c < NCL; ++c) xv[m][c] = a.x[off + min(lane + 32 * c, n - 1)];
             }
         }
+#endif
         asm volatile("cp.async.wait_group 0;\n" ::: "memory");       // factors (first pass) and the rows of the fallback path
         if (g.bulk) { mbar_wait(bar, phase); phase ^= 1u; }
         __syncwarp();
         // ---- direction update p = M^-1 r + beta p_old (in place in P, and to global memory); x += alpha_prev p_old
+#if NF_XV2
+#pragma unroll
+        for (int m = 0; m < NR; ++m) {
+            if (m < rows) {
+                const size_t off = (size_t)a.mode[0][t0 + m / M1][m % M1] * a.ne + e0;
+                double *Pm = P + m * PP;
+                const double *POm = PO + m * n;
+                const jac_t *Jm = JAC + m * n;
+#pragma unroll
+                for (int c = 0; c < NCP; ++c) {
+                    const int q = lane + 32 * c;
+                    if (q < nq) {
+                        double2 *Pq = reinterpret_cast<double2 *>(Pm + 2 * q);
+                        const double2 rv = *Pq;
+                        const double2 jv = pcg ? jac_pair(*reinterpret_cast<const unsigned *>(Jm + 2 * q)) : one2;
+                        const double2 po = need_po ? *reinterpret_cast<const double2 *>(POm + 2 * q) : zero2;
+                        const double2 pn = make_double2(jv.x * rv.x + beta * po.x, jv.y * rv.y + beta * po.y);
+                        *Pq = pn;
+                        st2(a.p + off + 2 * q, pn);
+                        if (xupd) st2(a.x + off + 2 * q, make_double2(xv[m][c].x + alpha_prev * po.x, xv[m][c].y + alpha_prev * po.y));
+                    }
+                }
+            }
+        }
+#else
 #pragma unroll
         for (int m = 0; m < NR; ++m) {
             if (m < rows) {
@@ -268,6 +328,7 @@ __device__ __forceinline__ void xrow_warp(const FusedArgs &a, const RowGeom &g, 
                 }
             }
         }
+#endif
         __syncwarp();
         if (kXPF && g.bulk && t0 + PW < a.nt && (need_po || pcg)) {
             // p_old and M^-1 of this pass are consumed: request those of the next pass now, behind the solve and the output
@@ -332,6 +393,52 @@ __device__ __forceinline__ void xrow_warp(const FusedArgs &a, const RowGeom &g, 
         __syncwarp();
         // ---- yp = diag * p + w B_x J (coalesced): batches of kCB cells per lane, modes outside, cells inside
         // (3-D only: 1/Fx of the y and z directions are both hx, and the cell volume is hx * hy * hz = hx * ify0)
+#if NF_XV2
+        constexpr int kCBP = 4;                  // pairs of cells per lane in one batch
+#pragma unroll
+        for (int cb = 0; cb < NCP; cb += kCBP) {
+            if (lane + 32 * cb < nq) {
+                double2 G0[kCBP], G1[kCBP], SV[kCBP];
+#pragma unroll
+                for (int c = 0; c < kCBP; ++c) {
+                    const int cc = (cb + c < NCP) ? cb + c : NCP - 1;
+                    const int q = min(lane + 32 * cc, nq - 1);
+                    const double2 hx = ldg2(a.iFx[1] + 2 * q), f0x = ldg2(a.iFx[0] + 2 * q);
+                    G0[c] = make_double2(Dv[cc].x * f0x.x, Dv[cc].y * f0x.y);
+                    G1[c] = make_double2(Dv[cc].x * hx.x, Dv[cc].y * hx.y);
+                    SV[c] = make_double2(Sv[cc].x * (hx.x * ify0), Sv[cc].y * (hx.y * ify0));
+                }
+                for (int s2 = 0; s2 < np; ++s2) {
+                    const double w = a.w[t0 + s2];
+                    const double *Js = Jb + s2 * PJ;
+#pragma unroll
+                    for (int p = 0; p < M1; ++p) {
+                        const int md = a.mode[0][t0 + s2][p];
+                        const double cw = a.wC[md], c0 = a.cb[0][md] * ify0, c12 = a.cb[1][md] * ify1 + a.cb[2][md] * ify2;
+                        const double *Pm = P + (s2 * M1 + p) * PP;
+                        double *yo = a.yp + (size_t)md * a.ne + e0;
+#pragma unroll
+                        for (int c = 0; c < kCBP; ++c) {
+                            const int q = lane + 32 * (cb + c);
+                            if (cb + c < NCP && q < nq) {
+                                const double2 JL = *reinterpret_cast<const double2 *>(Js + 2 * q);
+                                const double2 JR = make_double2(JL.y, Js[2 * q + 2]);
+                                double2 sol;
+                                if (p == 0) sol = make_double2(w * (JR.x - JL.x), w * (JR.y - JL.y));
+                                else if (p == 1) sol = (K >= 1) ? make_double2(w * (5.0 / 6.0) * (JL.x + JR.x), w * (5.0 / 6.0) * (JL.y + JR.y)) : zero2;
+                                else sol = (K >= 2) ? make_double2(w * (7.0 / 10.0) * (JR.x - JL.x), w * (7.0 / 10.0) * (JR.y - JL.y)) : zero2;
+                                const double2 xv2 = *reinterpret_cast<const double2 *>(Pm + 2 * q);
+                                const double2 yv = make_double2((SV[c].x * cw + G0[c].x * c0 + G1[c].x * c12) * xv2.x,
+                                                                (SV[c].y * cw + G0[c].y * c0 + G1[c].y * c12) * xv2.y);
+                                acc += yv.x * xv2.x + yv.y * xv2.y;
+                                st2(yo + 2 * q, make_double2(yv.x + sol.x, yv.y + sol.y));
+                            }
+                        }
+                    }
+                }
+            }
+        }
+#else
 #pragma unroll
         for (int cb = 0; cb < NCL; cb += kCB) {
             if (lane + 32 * cb < n) {
@@ -370,6 +477,7 @@ __device__ __forceinline__ void xrow_warp(const FusedArgs &a, const RowGeom &g, 
                 }
             }
         }
+#endif
         // the next pass (or row) overwrites P / PO / JAC through the async proxy: order this lane's accesses before it
         fence_proxy_async();
         __syncwarp();

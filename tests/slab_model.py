@@ -76,3 +76,26 @@ def rank_finish(r, P, v, E, spikes, JG):
         lam0 = (Gnn * d0 - G0n * dn) / det
         lamn = (-G0n * d0 + G00 * dn) / det
     return v + s0 * lam0 + sn * lamn
+
+
+def coupling(E):
+    """|G_0n| / sqrt(G_00 G_nn) of one rank's local inverse: below 1e-20 the reduced interface system is diagonal to rounding."""
+    G00, G0n, Gnn = E
+    return abs(G0n) / np.sqrt(abs(G00 * Gnn))
+
+
+def neighbour_multipliers(r, P, E_me, v_me, below, above):
+    """Neighbour mode of thick slabs (k_slab_iface_nb): below = (G_nn, v_n) of rank r-1, above = (G_00, v_0) of rank r+1 (None at
+    the ends). Returns (lam0, lamn) of rank r -- the two 1 x 1 interface equations, everything involving G_0n dropped."""
+    G00, _, Gnn = E_me
+    v0, vn = v_me
+    lam0 = lamn = 0.0
+    if r > 0:
+        Gb, vb = below
+        g = (vb / Gb + v0 / G00) / (1.0 / Gb + 1.0 / G00)
+        lam0 = (g - v0) / G00
+    if r < P - 1:
+        Ga, va = above
+        g = (vn / Gnn + va / Ga) / (1.0 / Gnn + 1.0 / Ga)
+        lamn = (g - vn) / Gnn
+    return lam0, lamn

@@ -81,6 +81,30 @@ def test_config4_koeberg_rt2p2_upscatter():
     c.close()
 
 
+def test_config4_koeberg_34x34_golden():
+    """configs[3] at SURVEY's own size (34x34 cells, n_phi = 10 404 per group): the oracle needs ~7 minutes for it, so its answer
+    is a committed golden vector (tests/golden/config4_koeberg34_rt2p2.npz, made by tools/make_golden_config4.py at tolerances
+    1e-7). Parity mode on the GPU reproduces the reference's iteration: same number of outer iterations."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "config4_koeberg34_rt2p2.npz"))
+    from neutfem_b200 import cabi
+    p = bm.problem_2d("koeberg2d", 2)
+    assert [p.x_breaks.size - 1, p.y_breaks.size - 1] == g["mesh"].tolist() == [34, 34]
+    tol = float(g["tol"])
+    c = cabi.Context(2, 2, p.ng, p.x_breaks, p.y_breaks, p.z_breaks)
+    c.set_solver(solver_type=BICGSTAB, tol_keff=tol, tol_flux=tol, max_outer=800, max_inner=8000)
+    for a, t, v in p.bcs:
+        c.set_bc(a, t, v)
+    c.upload_xs(D=p.D, SigR=p.SigR, NSF=p.NSF, Chi=p.Chi, SigS=p.SigS)
+    c.build()
+    k, st = c.solve_keff(False)
+    assert st["converged"] == 1
+    assert abs(k - float(g["keff"])) / float(g["keff"]) < K_TOL
+    assert relerr(c.get_flux(), g["flux"]) < PHI_TOL
+    assert abs(st["outer_iterations"] - int(g["outer_iterations"])) <= 1
+    c.close()
+
+
 def test_warm_restart_and_reset():
     """A second SolveKeff starts from the stored flux and k (NeutFEM.cpp:1662); reset_flux clears it (:347-354)."""
     p = bm.problem_2d("iaea2d", 1)

@@ -15,7 +15,7 @@ timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -s 300 -c
 FULL_MESH=${FULL_MESH:-"512 512 100"}
 PCMD="python tools/perf_probe.py --n $FULL_MESH --fast 1 --reps 2"
 timeout 600 $PCMD > gpurun_out/${tag}_plain_probe.log 2>&1 || exit 1
-for k in k_xrow k_ycol3 k_zfwd2 k_zback2; do
+for k in ${KERNELS:-k_xrow k_ycol k_zfwd2 k_zback2}; do
   out=gpurun_out/${tag}_full_${k}
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:"$k" --launch-skip 3 --launch-count 1 -f -o $out \
       $PCMD > $out.log 2>&1

@@ -87,7 +87,7 @@ elif bench:
 tot_bytes = 0.0
 tot_ms = 0.0
 table = []
-for k in ("k_xrow", "k_ycol3", "k_zfwd2", "k_zback2"):
+for k in ("k_xrow", "k_ycol", "k_zfwd2", "k_zback2"):
     f = os.path.join(G, f"{tag}_full_{k}.raw.csv")
     if not os.path.exists(f):
         continue
