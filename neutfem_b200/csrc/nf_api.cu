@@ -78,7 +78,6 @@ struct nf_ctx {
     int fused = -1;                        // -1: not yet decided, 0: separate kernels, 2: hybrid, 3: rows, 5: rows on a z-slab rank
     double *d_zs = nullptr;                // z-forward intermediates
     RowGeom rg; int xrow_grid = 0, ycol_grid = 0;   // register-resident x-row / y-column kernels (nf_rows.cuh)
-    int ycol3 = 1;                         // 1: three-phase y-column kernel (k_ycol3), 0: k_ycol (NF_YCOL=0, development knob)
     int zf_grid = 0, zb_grid = 0;          // whole waves of resident CTAs of the z marching kernels
     double inner_eta = 0.0;                // fast mode: inexact inner solves (option "inner_reduction"), 0 = off
     int and_m = kAndM;                     // Anderson depth (option "anderson_depth", 1..kAndM)
@@ -341,14 +340,9 @@ static bool rows_geometry(const nf_ctx *c, RowGeom &g)
     g.pitchJ = pj;
     const int rows = g.PWx * c->M1;
     g.offPO = 2 * (g.NFx + 2) + rows * g.pitchP;
-    const int jd = g.PWx * g.pitchJ;
-    if (kXPF) {                                   // p_old / M^-1 of the next pass are prefetched: J needs its own tile
-        g.offJ = g.offPO + ((rows * c->nx + 1) & ~1);
-        g.offJAC = g.offJ + ((jd + 1) & ~1);
-    } else {                                      // J reuses the consumed p_old tile
-        g.offJ = g.offPO;
-        g.offJAC = g.offPO + ((std::max(rows * c->nx, jd) + 1) & ~1);
-    }
+    const int po = std::max(rows * c->nx, g.PWx * g.pitchJ);      // J reuses the consumed p_old tile
+    g.offJ = g.offPO;
+    g.offJAC = g.offPO + ((po + 1) & ~1);
     const int jacd = (rows * c->nx * (int)sizeof(jac_t) + 7) / 8;
     g.offBAR = g.offJAC + ((jacd + 1) & ~1);
     g.xsmemW = g.offBAR + 2;
@@ -390,21 +384,9 @@ static int rows_prepare_t(nf_ctx *c)
     if (xcap > 0) per_sm = std::min(per_sm, xcap);
     const long long nrows = (long long)c->ny * c->nz;
     c->xrow_grid = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(kRedBlocks, (long long)per_sm * c->sm_count), (nrows + kXW - 1) / kXW));
-    c->ycol3 = env_int("NF_YCOL", 0) != 0;        // default: k_ycol (k_ycol3 measured slower at 3 CTAs / SM: its shared-memory columns leave the SM ~7 KB of L1)
-    const size_t ysmem3 = (size_t)(2 * c->rg.LcY + 4) * ynt * sizeof(double2);
-    if (ysmem3 + 2048 > c->smem_optin) c->ycol3 = 0;
     if (ynt != 128) NF_FAIL(c, NF_ERR_STATE, "y-column kernels are built for 128-thread CTAs");
-    if (c->ycol3) {
-        CU(c, cudaFuncSetAttribute(k_ycol3<K, M1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ysmem3));
-        const int carve = env_int("NF_YCOL3_CARVE", 0);      // % of the unified L1 / shared memory given to shared memory
-        if (carve > 0) CU(c, cudaFuncSetAttribute(k_ycol3<K, M1, 128>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-        CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ycol3<K, M1, 128>, 128, ysmem3));
-        const int ycap = env_int("NF_YCOL3_CTAS", 0);
-        if (ycap > 0) per_sm = std::min(per_sm, ycap);
-    } else {
-        CU(c, cudaFuncSetAttribute(k_ycol<K, M1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ysmem));
-        CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ycol<K, M1, 128>, 128, ysmem));
-    }
+    CU(c, cudaFuncSetAttribute(k_ycol<K, M1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ysmem));
+    CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ycol<K, M1, 128>, 128, ysmem));
     const long long nitems = (long long)c->nz * ((c->nx + c->rg.colsY - 1) / c->rg.colsY) * c->nt;
     c->ycol_grid = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(kRedBlocks, (long long)std::max(per_sm, 1) * c->sm_count), nitems));
     // the z marching kernels are persistent grid-stride loops: whole waves of resident CTAs only (no ragged last wave)
@@ -447,10 +429,7 @@ static int rows_launch_t(nf_ctx *c, const FusedArgs &a, int which)
     if (which & 2) {
         const int ynt = 32 * c->rg.warpsY;
         const size_t ysmem = (size_t)(c->rg.LcY + 1 + 5) * ynt * sizeof(double2);
-        const size_t ysmem3 = (size_t)(2 * c->rg.LcY + 4) * ynt * sizeof(double2);
-        double *ypart = c->d_part + (size_t)1 * kRedBlocks;
-        if (c->ycol3) LAUNCH(c, (k_ycol3<K, M1, 128>), c->ycol_grid, 128, ysmem3, a, c->rg, ypart, c->d_ticket + 1, &c->d_cg->pAp[1]);
-        else LAUNCH(c, (k_ycol<K, M1, 128>), c->ycol_grid, 128, ysmem, a, c->rg, ypart, c->d_ticket + 1, &c->d_cg->pAp[1]);
+        LAUNCH(c, (k_ycol<K, M1, 128>), c->ycol_grid, 128, ysmem, a, c->rg, c->d_part + (size_t)1 * kRedBlocks, c->d_ticket + 1, &c->d_cg->pAp[1]);
     }
     CU(c, cudaGetLastError());
     return NF_OK;

@@ -33,7 +33,7 @@ struct RowGeom {
     int PWx, LcX, NFx;          // x lines: pairs per pass (1 / 2 / 4; 32 / PWx lanes per pair), faces per chunk, PWx-independent row length 32 / PWx * LcX
     int pitchP, pitchJ;         // shared-memory row pitches (doubles) of the P and J tiles
     int offPO, offJAC, offBAR;  // offsets (doubles) of the p_old / J tile, the M^-1 tile and the mbarrier inside a warp's slice
-    int offJ;                   // offset of the J tile (== offPO unless the p_old / M^-1 rows of the next pass are prefetched)
+    int offJ;                   // offset of the J tile: it reuses the p_old tile once the direction update has consumed it
     int xsmemW;                 // doubles of shared memory per warp
     int bulk;                   // 1: rows are requested with cp.async.bulk (nx % 8 == 0: 16-byte aligned rows of every array)
     int Cy, LcY, colsY, warpsY; // y lines: chunks per line, faces per chunk, columns per item, warps per CTA
@@ -49,11 +49,6 @@ __device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned coun
 __device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, unsigned bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-// adds `bytes` to the transaction count of the barrier's current (incomplete) phase without arriving on it
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
-{
-    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
 {
@@ -158,20 +153,11 @@ __device__ __forceinline__ void chunk_bwd_final(double (&T)[LCT], const int jn, 
 // without guards (T = 0, u = 0, 1/m = 0 past the end of the line leave every result unchanged).
 // NCL = compile-time bound on the cells a lane owns (ceil(nx / 32)): per-cell cross-sections live in registers.
 // DEFER: x += alpha_prev * p_old, the solution update the previous iteration left pending (nf_fused.cuh).
-constexpr int kCB = 8;          // cells per lane in one batch of the output pass
-// NF_XPF = 1: the p_old and M^-1 rows of the NEXT pass are requested as soon as the direction update of this pass has consumed
-// its own (the J tile then needs its own buffer: 32 KB per warp, 7 warps per SM instead of 8); only r and x wait at the top of a pass.
-#ifndef NF_XPF
-#define NF_XPF 0
-#endif
-constexpr int kXPF = NF_XPF;
-// NF_XV2 = 1: the direction-update and output passes of the x rows work on PAIRS of adjacent cells (16-byte shared-memory and
-// global accesses): the kernel is bound by instruction latency at 2 warps per scheduler (ncu r02a: 85 thread-instructions per
-// DOF, issue slots 24 % busy, stalls on fixed-latency dependencies, shared-memory returns and instruction fetch), so halving
-// the memory instructions of those two passes is what shortens it.
-#ifndef NF_XV2
-#define NF_XV2 1
-#endif
+constexpr int kCBP = 4;         // pairs of adjacent cells per lane in one batch of the output pass
+// The direction-update and output passes of the x rows work on PAIRS of adjacent cells (16-byte shared-memory and global
+// accesses): the kernel is bound by instruction latency at 2 warps per scheduler (ncu r02a: 85 thread-instructions per DOF,
+// issue slots 24 % busy, stalls on fixed-latency dependencies, shared-memory returns and instruction fetch), so halving the
+// memory instructions of those two passes is what shortens it (r02b: 70 thread-instructions per DOF, 2.05 -> 1.85 ms).
 __device__ __forceinline__ double2 jac_pair(const unsigned v)        // two adjacent 16-bit entries -> two doubles
 {
     return make_double2(__hiloint2double((int)(v << 16), 0), __hiloint2double((int)(v & 0xffff0000u), 0));
@@ -205,7 +191,6 @@ __device__ __forceinline__ void xrow_warp(const FusedArgs &a, const RowGeom &g, 
         asm volatile("cp.async.commit_group;\n" ::: "memory");
     }
     // per-cell cross-sections of the lane's cells: requested now, first used in the output pass of the first pair
-#if NF_XV2
     constexpr int NCP = (NCL + 1) / 2;          // pairs of adjacent cells a lane owns in the coalesced passes
     const int nq = n >> 1;                      // n is even on the rows paths
     const double2 zero2 = make_double2(0.0, 0.0), one2 = make_double2(1.0, 1.0);
@@ -215,14 +200,6 @@ __device__ __forceinline__ void xrow_warp(const FusedArgs &a, const RowGeom &g, 
         const int q = min(lane + 32 * c, nq - 1);
         Dv[c] = ldg2(a.D + e0 + 2 * q); Sv[c] = ldg2(a.SigR + e0 + 2 * q);
     }
-#else
-    double Dv[NCL], Sv[NCL];
-#pragma unroll
-    for (int c = 0; c < NCL; ++c) {
-        const int ixl = min(lane + 32 * c, n - 1);
-        Dv[c] = __ldg(a.D + e0 + ixl); Sv[c] = __ldg(a.SigR + e0 + ixl);
-    }
-#endif
     const double fy0 = __ldg(a.Fy[0] + iy), fy1 = __ldg(a.Fy[1] + iy), fy2 = __ldg(a.Fy[2] + iy);
     const double fz0 = __ldg(a.Fz[0] + iz), fz1 = __ldg(a.Fz[1] + iz), fz2 = __ldg(a.Fz[2] + iz);
     const double ify0 = 1.0 / (fy0 * fz0), ify1 = 1.0 / (fy1 * fz1), ify2 = 1.0 / (fy2 * fz2);
@@ -232,17 +209,16 @@ __device__ __forceinline__ void xrow_warp(const FusedArgs &a, const RowGeom &g, 
         const int np = min(PW, a.nt - t0), rows = np * M1;
         // ---- request the rows of this pass: r -> P, p_old -> PO, M^-1 -> JAC
         if (g.bulk) {
-            const bool pre = kXPF && t0 > 0;            // p_old / M^-1 of this pass were requested during the previous pass
             if (lane == 0) {
-                const unsigned bytes = (unsigned)rows * (unsigned)n * (8u * ((need_po && !pre) ? 2u : 1u) + ((pcg && !pre) ? 2u : 0u));
+                const unsigned bytes = (unsigned)rows * (unsigned)n * (8u * (need_po ? 2u : 1u) + (pcg ? 2u : 0u));
                 mbar_arrive_expect_tx(bar, bytes);
             }
             __syncwarp();
             if (lane < rows) {
                 const size_t off = (size_t)a.mode[0][t0 + lane / M1][lane % M1] * a.ne + e0;
                 bulk_g2s(P + lane * PP, a.r + off, (unsigned)n * 8u, bar);
-                if (need_po && !pre) bulk_g2s(PO + lane * n, a.p + off, (unsigned)n * 8u, bar);
-                if (pcg && !pre) bulk_g2s(JAC + lane * n, a.jac + off, (unsigned)n * 2u, bar);
+                if (need_po) bulk_g2s(PO + lane * n, a.p + off, (unsigned)n * 8u, bar);
+                if (pcg) bulk_g2s(JAC + lane * n, a.jac + off, (unsigned)n * 2u, bar);
             }
         } else {
             for (int m = 0; m < rows; ++m) {
@@ -256,7 +232,6 @@ __device__ __forceinline__ void xrow_warp(const FusedArgs &a, const RowGeom &g, 
             asm volatile("cp.async.commit_group;\n" ::: "memory");
         }
         // ---- x of the lane's cells (deferred update): requested into registers while the rows are in flight
-#if NF_XV2
         double2 xv[NR][NCP];
         if (xupd) {
 #pragma unroll
@@ -266,22 +241,10 @@ __device__ __forceinline__ void xrow_warp(const FusedArgs &a, const RowGeom &g, 
                 for (int c = 0; c < NCP; ++c) xv[m][c] = *reinterpret_cast<const double2 *>(a.x + off + 2 * min(lane + 32 * c, nq - 1));
             }
         }
-#else
-        double xv[NR][NCL];
-        if (xupd) {
-#pragma unroll
-            for (int m = 0; m < NR; ++m) {
-                const size_t off = (size_t)a.mode[0][min(t0 + m / M1, a.nt - 1)][m % M1] * a.ne + e0;
-#pragma unroll
-                for (int c = 0; c < NCL; ++c) xv[m][c] = a.x[off + min(lane + 32 * c, n - 1)];
-            }
-        }
-#endif
         asm volatile("cp.async.wait_group 0;\n" ::: "memory");       // factors (first pass) and the rows of the fallback path
         if (g.bulk) { mbar_wait(bar, phase); phase ^= 1u; }
         __syncwarp();
         // ---- direction update p = M^-1 r + beta p_old (in place in P, and to global memory); x += alpha_prev p_old
-#if NF_XV2
 #pragma unroll
         for (int m = 0; m < NR; ++m) {
             if (m < rows) {
@@ -305,44 +268,7 @@ __device__ __forceinline__ void xrow_warp(const FusedArgs &a, const RowGeom &g, 
                 }
             }
         }
-#else
-#pragma unroll
-        for (int m = 0; m < NR; ++m) {
-            if (m < rows) {
-                const size_t off = (size_t)a.mode[0][t0 + m / M1][m % M1] * a.ne + e0;
-                double *Pm = P + m * PP;
-                const double *POm = PO + m * n;
-                const jac_t *Jm = JAC + m * n;
-#pragma unroll
-                for (int c = 0; c < NCL; ++c) {
-                    const int ix = lane + 32 * c;
-                    if (ix < n) {
-                        const double rv = Pm[ix];
-                        const double jv = pcg ? jac_to_double(Jm[ix]) : 1.0;
-                        const double po = need_po ? POm[ix] : 0.0;
-                        const double pn = jv * rv + beta * po;
-                        Pm[ix] = pn;
-                        a.p[off + ix] = pn;
-                        if (xupd) a.x[off + ix] = xv[m][c] + alpha_prev * po;
-                    }
-                }
-            }
-        }
-#endif
         __syncwarp();
-        if (kXPF && g.bulk && t0 + PW < a.nt && (need_po || pcg)) {
-            // p_old and M^-1 of this pass are consumed: request those of the next pass now, behind the solve and the output
-            const int t1 = t0 + PW, rows1 = min(PW, a.nt - t1) * M1;
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_expect_tx(bar, (unsigned)rows1 * (unsigned)n * ((need_po ? 8u : 0u) + (pcg ? 2u : 0u)));
-            __syncwarp();
-            if (lane < rows1) {
-                const size_t off = (size_t)a.mode[0][t1 + lane / M1][lane % M1] * a.ne + e0;
-                if (need_po) bulk_g2s(PO + lane * n, a.p + off, (unsigned)n * 8u, bar);
-                if (pcg) bulk_g2s(JAC + lane * n, a.jac + off, (unsigned)n * 2u, bar);
-            }
-        }
         // ---- chunk ownership: lane = (pair slot s, chunk k)
         const bool tv = s < np;
         const int sp = tv ? s : 0;
@@ -391,10 +317,8 @@ __device__ __forceinline__ void xrow_warp(const FusedArgs &a, const RowGeom &g, 
             for (int j = 0; j < LCT; ++j) Jr[j] = T[j];
         }
         __syncwarp();
-        // ---- yp = diag * p + w B_x J (coalesced): batches of kCB cells per lane, modes outside, cells inside
+        // ---- yp = diag * p + w B_x J (coalesced): batches of kCBP pairs of cells per lane, modes outside, cells inside
         // (3-D only: 1/Fx of the y and z directions are both hx, and the cell volume is hx * hy * hz = hx * ify0)
-#if NF_XV2
-        constexpr int kCBP = 4;                  // pairs of cells per lane in one batch
 #pragma unroll
         for (int cb = 0; cb < NCP; cb += kCBP) {
             if (lane + 32 * cb < nq) {
@@ -438,46 +362,6 @@ __device__ __forceinline__ void xrow_warp(const FusedArgs &a, const RowGeom &g, 
                 }
             }
         }
-#else
-#pragma unroll
-        for (int cb = 0; cb < NCL; cb += kCB) {
-            if (lane + 32 * cb < n) {
-                double G0[kCB], G1[kCB], SV[kCB];
-#pragma unroll
-                for (int c = 0; c < kCB; ++c) {
-                    const int cc = (cb + c < NCL) ? cb + c : NCL - 1;
-                    const int ixl = min(lane + 32 * cc, n - 1);
-                    const double hx = __ldg(a.iFx[1] + ixl), f0x = __ldg(a.iFx[0] + ixl);
-                    G0[c] = Dv[cc] * f0x; G1[c] = Dv[cc] * hx;
-                    SV[c] = Sv[cc] * (hx * ify0);
-                }
-                for (int s2 = 0; s2 < np; ++s2) {
-                    const double w = a.w[t0 + s2];
-                    const double *Js = Jb + s2 * PJ + lane + 32 * cb;
-#pragma unroll
-                    for (int p = 0; p < M1; ++p) {
-                        const int md = a.mode[0][t0 + s2][p];
-                        const double cw = a.wC[md], c0 = a.cb[0][md] * ify0, c12 = a.cb[1][md] * ify1 + a.cb[2][md] * ify2;
-                        const double *Pm = P + (s2 * M1 + p) * PP + lane + 32 * cb;
-                        double *yo = a.yp + (size_t)md * a.ne + e0 + lane + 32 * cb;
-#pragma unroll
-                        for (int c = 0; c < kCB; ++c) {
-                            if (cb + c < NCL && lane + 32 * (cb + c) < n) {
-                                const double JL = Js[32 * c], JR = Js[32 * c + 1];
-                                const double sol = (p == 0) ? w * (JR - JL) : (p == 1 ? ((K >= 1) ? w * (5.0 / 6.0) * (JL + JR) : 0.0)
-                                                                                      : ((K >= 2) ? w * (7.0 / 10.0) * (JR - JL) : 0.0));
-                                const double xv2 = Pm[32 * c];
-                                const double dg = SV[c] * cw + G0[c] * c0 + G1[c] * c12;
-                                const double yv = dg * xv2;
-                                acc += yv * xv2;
-                                yo[32 * c] = yv + sol;
-                            }
-                        }
-                    }
-                }
-            }
-        }
-#endif
         // the next pass (or row) overwrites P / PO / JAC through the async proxy: order this lane's accesses before it
         fence_proxy_async();
         __syncwarp();
@@ -768,192 +652,6 @@ __global__ void __launch_bounds__(NT) k_ycol(const FusedArgs a, const RowGeom g,
         const int t = (int)(item % a.nt);
         const long long r = item / a.nt;
         ycol_block<K, M1, NT>(a, g, (int)(r / nxb), (int)(r % nxb), t, sT, sS, acc);
-    }
-    double v[1] = {acc};
-    grid_reduce<1>(v, red_part, ticket, red_out);
-}
-
-// ---- y columns, three-phase variant --------------------------------------------------------------------------------------
-// Same ownership as ycol_block (thread = pair of adjacent columns x chunk of LcY cells), but every chunk is walked with global
-// loads only THREE times instead of six (k_ycol is bound by the latency of its dependent load rounds: 12 warps per SM, L1 hit
-// rate < 1 %, profiles/r01g):
-//   1. forward: p, u and 1/m of the chunk are requested together; the right-hand side T_f is consumed on the fly by the local
-//      forward substitution from z_in = 0, together with the homogeneous response h_f = prod(-u): the chunk keeps
-//      zm0_f = z0_f / m_f and hm_f = h_f / m_f (so that d_f = z_f / m_f = zm0_f + hm_f z_in needs no further load) and three
-//      scalars that give sum_f z_f^2 / m_f for any z_in;                                   [stitch: z_in of every chunk]
-//   2. backward: only u is requested; J0_f (from J_in = 0) and g_f = prod(-u) replace zm0 / hm;   [stitch: J_in]
-//   3. output: yp is requested and updated with J_f = J0_f + g_f J_in; J of the first face of the next chunk IS J_in.
-// The chunk state lives in two thread-private shared-memory columns of LcY rows; the top face of the line (last chunk only)
-// stays in registers, so that three CTAs of 128 threads fit an SM at LcY = 16.
-#ifndef NF_YB3
-#define NF_YB3 4
-#endif
-constexpr int kYB3 = NF_YB3;    // rows of loads issued ahead of each stretch of work
-
-template <int K, int M1, int NT>
-__device__ __forceinline__ void ycol_block3(const FusedArgs &a, const RowGeom &g, const int iz, const int xb, const int t,
-                                            double2 *sC0, double2 *sC1, double2 *sS, double &acc)
-{
-    const int tid = threadIdx.x;
-    const int CPI = g.colsY >> 1, CY = g.Cy, Lc = g.LcY;           // column pairs per item; NT == CPI * CY
-    const int cp = tid % CPI, kc = tid / CPI;
-    const int n = a.ny, nx = a.nx;
-    const int ix = xb * g.colsY + 2 * cp;
-    const bool cv = ix < nx;
-    const int ixc = cv ? ix : nx - 2;            // column pairs past the mesh redo the last one; nothing of theirs is stored
-    const int f0 = min(kc * Lc, n + 1);
-    const int ncell = max(0, min(Lc, n - f0));   // cells f0 .. f0+ncell-1, faces f0 .. f0+ncell-1 (+ the top face: last chunk)
-    const bool top = (ncell > 0 && f0 + ncell == n);
-    double2 *sA = sS, *sZ = sS + NT, *sB = sS + 2 * NT, *sJ = sS + 3 * NT;
-    double2 *C0 = sC0 + tid, *C1 = sC1 + tid;    // thread-private columns: row j at [j * NT]
-    const double w = a.w[t];
-    const size_t S = (size_t)nx;                 // row stride (doubles)
-    const size_t cell0 = (size_t)iz * n * nx + ixc + (size_t)f0 * nx;
-    const double *gp0 = a.p + (size_t)a.mode[1][t][0] * a.ne + cell0;
-    const double *gp1 = a.p + (size_t)a.mode[1][t][M1 >= 2 ? 1 : 0] * a.ne + cell0;
-    const double *gp2 = a.p + (size_t)a.mode[1][t][M1 >= 3 ? 2 : 0] * a.ne + cell0;
-    double *gy0 = a.yp + (size_t)a.mode[1][t][0] * a.ne + cell0;
-    double *gy1 = a.yp + (size_t)a.mode[1][t][M1 >= 2 ? 1 : 0] * a.ne + cell0;
-    double *gy2 = a.yp + (size_t)a.mode[1][t][M1 >= 3 ? 2 : 0] * a.ne + cell0;
-    const double *gu = a.u[1] + (size_t)iz * (n + 1) * nx + ixc + (size_t)f0 * nx;       // u_f at gu + j*S, u_{f-1} at gu + (j-1)*S
-    const double *gm = a.minv[1] + (size_t)iz * (n + 1) * nx + ixc + (size_t)f0 * nx;
-    const double2 zero2 = make_double2(0.0, 0.0), one2 = make_double2(1.0, 1.0);
-    const int slot = kc * CPI + cp;
-    // ---- phase 1: forward substitution from z_in = 0 and homogeneous response, rhs consumed on the fly
-    double2 z0 = zero2, h = one2, qa = zero2, qb = zero2, qc = zero2, tzm = zero2, thm = zero2;
-    {
-        double2 lop = zero2, dum;
-        if (f0 > 0 && f0 <= n) lohi2<K, M1>(ld2cg(gp0 - S), (K >= 1 && M1 >= 2) ? ld2cg(gp1 - S) : zero2, (K >= 2 && M1 >= 3) ? ld2cg(gp2 - S) : zero2, lop, dum);
-        auto face = [&](const double2 hi, const double2 uu, const double2 mm, double2 &zm, double2 &hm) {
-            z0.x = (lop.x - hi.x) - uu.x * z0.x; z0.y = (lop.y - hi.y) - uu.y * z0.y;
-            h.x *= -uu.x; h.y *= -uu.y;
-            zm = make_double2(mm.x * z0.x, mm.y * z0.y);
-            hm = make_double2(mm.x * h.x, mm.y * h.y);
-            qa.x += z0.x * zm.x; qa.y += z0.y * zm.y;
-            qb.x += z0.x * hm.x; qb.y += z0.y * hm.y;
-            qc.x += h.x * hm.x; qc.y += h.y * hm.y;
-        };
-        int j = 0;
-        for (; j + kYB3 <= ncell; j += kYB3) {
-            double2 x0[kYB3], x1[kYB3], x2[kYB3], uu[kYB3], mm[kYB3];
-            const double *q0 = gp0 + j * S, *q1 = gp1 + j * S, *q2 = gp2 + j * S, *qu = gu + j * S - S, *qm = gm + j * S;
-#pragma unroll
-            for (int i = 0; i < kYB3; ++i) {
-                x0[i] = ld2cg(q0 + i * S);
-                x1[i] = (K >= 1 && M1 >= 2) ? ld2cg(q1 + i * S) : zero2;
-                x2[i] = (K >= 2 && M1 >= 3) ? ld2cg(q2 + i * S) : zero2;
-                uu[i] = ld2g(qu + i * S); mm[i] = ld2g(qm + i * S);
-            }
-#pragma unroll
-            for (int i = 0; i < kYB3; ++i) {
-                double2 lo, hi, zm, hm;
-                lohi2<K, M1>(x0[i], x1[i], x2[i], lo, hi);
-                face(hi, uu[i], mm[i], zm, hm);
-                C0[(j + i) * NT] = zm; C1[(j + i) * NT] = hm;
-                lop = lo;
-            }
-        }
-        for (; j < ncell; ++j) {
-            double2 lo, hi, zm, hm;
-            lohi2<K, M1>(ld2cg(gp0 + j * S), (K >= 1 && M1 >= 2) ? ld2cg(gp1 + j * S) : zero2, (K >= 2 && M1 >= 3) ? ld2cg(gp2 + j * S) : zero2, lo, hi);
-            face(hi, ld2g(gu + j * S - S), ld2g(gm + j * S), zm, hm);
-            C0[j * NT] = zm; C1[j * NT] = hm;
-            lop = lo;
-        }
-        if (top) face(zero2, ld2g(gu + ncell * S - S), ld2g(gm + ncell * S), tzm, thm);      // top face of the line: hi = 0
-    }
-    sA[slot] = h; sZ[slot] = z0;
-    __syncthreads();
-    double2 zin = zero2;
-    for (int kk = 0; kk < kc; ++kk) {
-        const double2 Ak = sA[kk * CPI + cp], zk = sZ[kk * CPI + cp];
-        zin.x = Ak.x * zin.x + zk.x; zin.y = Ak.y * zin.y + zk.y;
-    }
-    if (cv) acc += w * ((qa.x + zin.x * (2.0 * qb.x + zin.x * qc.x)) + (qa.y + zin.y * (2.0 * qb.y + zin.y * qc.y)));
-    // ---- phase 2: backward substitution from J_in = 0 and homogeneous response; J0 / g replace zm0 / hm
-    double2 J0 = zero2, gg = one2;
-    {
-        if (top) {          // u of the top face is 0 by construction: J0 = d, g = 0
-            J0 = make_double2(tzm.x + thm.x * zin.x, tzm.y + thm.y * zin.y);
-            gg = zero2;
-            tzm = J0; thm = gg;
-        }
-        auto face = [&](const int j, const double2 uu) {
-            const double2 zm = C0[j * NT], hm = C1[j * NT];
-            J0.x = (zm.x + hm.x * zin.x) - uu.x * J0.x; J0.y = (zm.y + hm.y * zin.y) - uu.y * J0.y;
-            gg.x *= -uu.x; gg.y *= -uu.y;
-            C0[j * NT] = J0; C1[j * NT] = gg;
-        };
-        int j = ncell - 1;
-        const int nfull = (ncell / kYB3) * kYB3;
-        for (; j >= nfull; --j) face(j, ld2g(gu + j * S));
-        for (j = nfull - kYB3; j >= 0; j -= kYB3) {
-            double2 uu[kYB3];
-            const double *qu = gu + j * S;
-#pragma unroll
-            for (int i = kYB3 - 1; i >= 0; --i) uu[i] = ld2g(qu + i * S);
-#pragma unroll
-            for (int i = kYB3 - 1; i >= 0; --i) face(j + i, uu[i]);
-        }
-    }
-    sB[slot] = gg; sJ[slot] = J0;
-    __syncthreads();
-    double2 Jin = zero2;
-    for (int kk = CY - 1; kk > kc; --kk) {
-        const double2 Bk = sB[kk * CPI + cp], Jk = sJ[kk * CPI + cp];
-        Jin.x = Bk.x * Jin.x + Jk.x; Jin.y = Bk.y * Jin.y + Jk.y;
-    }
-    // ---- phase 3: yp += w B_y J for the cells f0 .. f0+ncell-1 of this column pair, J_f = J0_f + g_f J_in
-    if (cv) {
-        auto Jat = [&](const int j) {            // j in [0, ncell]: face f0 + j
-            if (j < ncell) { const double2 a0 = C0[j * NT], a1 = C1[j * NT]; return make_double2(a0.x + a1.x * Jin.x, a0.y + a1.y * Jin.y); }
-            return top ? make_double2(tzm.x + thm.x * Jin.x, tzm.y + thm.y * Jin.y) : Jin;
-        };
-        auto put = [&](double *y0p, double *y1p, double *y2p, const double2 y0, const double2 y1, const double2 y2, const double2 JL,
-                       const double2 JR) {
-            *reinterpret_cast<double2 *>(y0p) = make_double2(y0.x + w * (JR.x - JL.x), y0.y + w * (JR.y - JL.y));
-            if (M1 >= 2)
-                *reinterpret_cast<double2 *>(y1p) = (K >= 1) ? make_double2(y1.x + w * (5.0 / 6.0) * (JL.x + JR.x), y1.y + w * (5.0 / 6.0) * (JL.y + JR.y)) : y1;
-            if (M1 >= 3)
-                *reinterpret_cast<double2 *>(y2p) = (K >= 2) ? make_double2(y2.x + w * (7.0 / 10.0) * (JR.x - JL.x), y2.y + w * (7.0 / 10.0) * (JR.y - JL.y)) : y2;
-        };
-        int j = 0;
-        for (; j + kYB3 <= ncell; j += kYB3) {
-            double2 y0[kYB3], y1[kYB3], y2[kYB3], jj[kYB3 + 1];
-            double *q0 = gy0 + j * S, *q1 = gy1 + j * S, *q2 = gy2 + j * S;
-#pragma unroll
-            for (int i = 0; i < kYB3; ++i) {
-                y0[i] = ld2cg(q0 + i * S);
-                y1[i] = (M1 >= 2) ? ld2cg(q1 + i * S) : zero2;
-                y2[i] = (M1 >= 3) ? ld2cg(q2 + i * S) : zero2;
-            }
-#pragma unroll
-            for (int i = 0; i <= kYB3; ++i) jj[i] = Jat(j + i);
-#pragma unroll
-            for (int i = 0; i < kYB3; ++i) put(q0 + i * S, q1 + i * S, q2 + i * S, y0[i], y1[i], y2[i], jj[i], jj[i + 1]);
-        }
-        for (; j < ncell; ++j)
-            put(gy0 + j * S, gy1 + j * S, gy2 + j * S, ld2cg(gy0 + j * S), (M1 >= 2) ? ld2cg(gy1 + j * S) : zero2,
-                (M1 >= 3) ? ld2cg(gy2 + j * S) : zero2, Jat(j), Jat(j + 1));
-    }
-    __syncthreads();        // sS is reused by the next item
-}
-
-// yp += (y part of S p) ; red_out = p^T (y part) p.   Dynamic shared memory: (2 LcY + 4) * NT double2.
-template <int K, int M1, int NT>
-__global__ void __launch_bounds__(NT, (NT == 128 ? 3 : 1)) k_ycol3(const FusedArgs a, const RowGeom g, double *red_part, unsigned *ticket,
-                                                                   double *red_out)
-{
-    if (a.st->done) return;
-    extern __shared__ __align__(16) double sm[];
-    double2 *sC0 = reinterpret_cast<double2 *>(sm), *sC1 = sC0 + (size_t)g.LcY * NT, *sS = sC1 + (size_t)g.LcY * NT;
-    const int nxb = (a.nx + g.colsY - 1) / g.colsY;
-    const long long nitems = (long long)a.nz * nxb * a.nt;
-    double acc = 0.0;
-    for (long long item = blockIdx.x; item < nitems; item += gridDim.x) {
-        const int t = (int)(item % a.nt);
-        const long long r = item / a.nt;
-        ycol_block3<K, M1, NT>(a, g, (int)(r / nxb), (int)(r % nxb), t, sC0, sC1, sS, acc);
     }
     double v[1] = {acc};
     grid_reduce<1>(v, red_part, ticket, red_out);
