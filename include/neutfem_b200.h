@@ -42,8 +42,13 @@ enum { NF_MODE_PARITY = 0, NF_MODE_FAST = 1 };
 /* outer-iteration accelerators: CHEBYSHEV = ChebyshevAccel(15, 0.98) exactly as the reference runs it (solvers.cpp:664-756);
  * ANDERSON = type-II Anderson mixing with the parameters of the reference's AndersonAccel (m = 5, beta = 1, Tikhonov 1e-8,
  * step clamp 0.3; solvers.cpp:772-891). The reference never instantiates that class and its formula returns the previous
- * iterate (oracle/neutfem_oracle.py AndersonAccelReference): the standard formulation is implemented instead. Parity unpinned. */
-enum { NF_ACCEL_NONE = 0, NF_ACCEL_CHEBYSHEV = 1, NF_ACCEL_ANDERSON = 2 };
+ * iterate (oracle/neutfem_oracle.py AndersonAccelReference): the standard formulation is implemented instead. Parity unpinned.
+ * CMFD = coarse-mesh finite-difference correction after every group sweep from outer iteration 2 on, Chebyshev off, i.e. where
+ * SolveKeff(use_cmfd=true) calls ApplyCMFDCorrection (NeutFEM.cpp:1748-1761). The reference's version (NeutFEM.cpp:662-1017)
+ * corrects the x faces only and has no scattering source, so its fixed point is not the fine solution in 2-D / 3-D; the
+ * complete method (all directions, multigroup coarse eigenvalue problem, any coarsening) is implemented instead
+ * (neutfem_b200/csrc/nf_cmfd.cuh, CPU restatement oracle/cmfd_oracle.py). Single GPU only. Parity unpinned. */
+enum { NF_ACCEL_NONE = 0, NF_ACCEL_CHEBYSHEV = 1, NF_ACCEL_ANDERSON = 2, NF_ACCEL_CMFD = 3 };
 
 enum { NF_OK = 0, NF_ERR_ARG = -1, NF_ERR_CUDA = -2, NF_ERR_STATE = -3, NF_ERR_NCCL = -4, NF_ERR_NODEVICE = -5 };
 
@@ -88,8 +93,17 @@ NF_API int nf_set_solver(nf_ctx *ctx, int solver_type, double tol_keff, double t
 /* Tuning knobs without a reference counterpart (fast mode only; parity mode ignores them):
  *   "inner_reduction" eta in [0, 1): inexact inner solves -- a group solve also stops once its residual is eta times the
  *                     residual it started from (warm start); 0 = off (stop on tol_flux ||b|| only, like the reference);
- *   "anderson_depth"  history depth of NF_ACCEL_ANDERSON, 1..5 (memory: 2 depth + 2 vectors of ng * n_Phi). */
+ *   "anderson_depth"  history depth of NF_ACCEL_ANDERSON, 1..5 (memory: 2 depth + 2 vectors of ng * n_Phi);
+ *   "cmfd_cx", "cmfd_cy", "cmfd_cz"  fine cells per coarse cell of NF_ACCEL_CMFD (0 = automatic: at most 64 coarse cells per
+ *                     axis; 1 = the fine mesh itself, the reference's choice);
+ *   "cmfd_relaxation" omega of NeutFEM::SetCMFDRelaxation (NeutFEM.hpp: cmfd_data_->relaxation), default 1;
+ *   "cmfd_tol", "cmfd_check", "cmfd_max_sweeps"  coarse eigenvalue solve: stop when the l1 change of one Jacobi sweep is below
+ *                     tol (1e-10) of the l1 norm, tested every `check` (50) sweeps, at most max_sweeps (100000). */
 NF_API int nf_set_option(nf_ctx *ctx, const char *key, double value);
+/* read-back of options and counters: "cmfd_calls", "cmfd_sweeps" (total), "cmfd_last_sweeps", "cmfd_last_k",
+ * "cmfd_last_status" (0 applied, 1 skipped, 2 applied without reaching cmfd_tol), "cmfd_last_change", "cmfd_cx/cy/cz",
+ * "cmfd_coarse_cells", "cg_path" (id of the CG-iteration path, see nf_time_kernels). Unknown key: NF_ERR_ARG. */
+NF_API int nf_query(const nf_ctx *ctx, const char *key, double *value);
 
 /* ---- operators -------------------------------------------------------------------------------------------
  * Host->device snapshot of the cross-sections (the reference's public Vec members, NeutFEM.hpp:373-379, that
@@ -133,6 +147,12 @@ NF_API int nf_schur_solve(nf_ctx *ctx, int g, const double *rhs, double *phi, in
 NF_API int nf_current_from_flux(nf_ctx *ctx, int g, const double *phi, double *J);
 /* 1/S_ee of the diagonal RT0-P0 path for group g, [NE] */
 NF_API int nf_get_diagonal_cache(nf_ctx *ctx, int g, double *s_inv);
+
+/* One CMFD correction of the current flux (nf_set_flux / the last solve), as NF_ACCEL_CMFD applies it inside nf_solve_keff:
+ * keff = the k of the group sweep that produced the flux, prod_old = fission production of the iterate that sweep started
+ * from (NeutFEM.cpp:1703). Returns the coarse-mesh eigenvalue, the Jacobi sweeps used and the status of nf_query
+ * "cmfd_last_status". Test hook for the step-by-step comparison with oracle/cmfd_oracle.py. */
+NF_API int nf_cmfd_step(nf_ctx *ctx, double keff, double prod_old, double *k_coarse, int32_t *sweeps, int32_t *status);
 
 /* Average device time (ms) per launch of the hot-path kernels, CUDA events on the library's stream. ms_out holds 16
  * doubles: [0..2] x/y/z sweep, [3] CG update, [4] CG direction update and [8] one CG iteration of the

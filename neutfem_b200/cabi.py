@@ -20,7 +20,7 @@ LIB_PATH = os.environ.get("NF_LIB", os.path.join(_LIBDIR, "libneutfem_b200.so"))
 BC_DIRICHLET, BC_NEUMANN, BC_MIRROR, BC_ROBIN, BC_PERIODIC = range(5)
 (DIRECT_LU, DIRECT_LDLT, DIRECT_LLT, CG, CG_DIAG, CG_ICHOL, BICGSTAB, BICGSTAB_DIAG, BICGSTAB_ILU, LCG) = range(10)
 MODE_PARITY, MODE_FAST = 0, 1
-ACCEL_NONE, ACCEL_CHEBYSHEV, ACCEL_ANDERSON = 0, 1, 2
+ACCEL_NONE, ACCEL_CHEBYSHEV, ACCEL_ANDERSON, ACCEL_CMFD = 0, 1, 2, 3
 
 EXPORTED = [
     "nf_create", "nf_destroy", "nf_last_error", "nf_get_sizes", "nf_set_bc", "nf_set_solver", "nf_upload_xs",
@@ -28,7 +28,7 @@ EXPORTED = [
     "nf_get_current", "nf_solve_keff", "nf_solve_adjoint", "nf_solve_source", "nf_get_last_keff", "nf_schur_apply",
     "nf_schur_solve", "nf_current_from_flux", "nf_get_diagonal_cache", "nf_comm_unique_id", "nf_comm_init",
     "nf_create_slab",
-    "nf_version", "nf_kernel_launch_count", "nf_time_kernels", "nf_set_option",
+    "nf_version", "nf_kernel_launch_count", "nf_time_kernels", "nf_set_option", "nf_query", "nf_cmfd_step",
 ]
 
 
@@ -72,6 +72,8 @@ def load():
     L.nf_set_solver.argtypes = [vp, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int]
     L.nf_upload_xs.argtypes = [vp, dp, dp, dp, dp, dp, dp]
     L.nf_set_option.argtypes = [vp, ctypes.c_char_p, ctypes.c_double]
+    L.nf_query.argtypes = [vp, ctypes.c_char_p, dp]
+    L.nf_cmfd_step.argtypes = [vp, ctypes.c_double, ctypes.c_double, dp, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]
     L.nf_build.argtypes = [vp]
     L.nf_build_diagonal_cache.argtypes = [vp]
     L.nf_set_flux.argtypes = [vp, dp]
@@ -153,6 +155,18 @@ class Context:
 
     def set_option(self, key, value):
         self._ck(self._L.nf_set_option(self._h, key.encode(), float(value)), "nf_set_option")
+
+    def query(self, key):
+        v = ctypes.c_double()
+        self._ck(self._L.nf_query(self._h, key.encode(), ctypes.byref(v)), f"nf_query({key})")
+        return v.value
+
+    def cmfd_step(self, keff, prod_old):
+        """One CMFD correction of the current flux (test hook). Returns (k_coarse, sweeps, status)."""
+        k, sw, st = ctypes.c_double(), ctypes.c_int32(), ctypes.c_int32()
+        self._ck(self._L.nf_cmfd_step(self._h, float(keff), float(prod_old), ctypes.byref(k), ctypes.byref(sw), ctypes.byref(st)),
+                 "nf_cmfd_step")
+        return k.value, sw.value, st.value
 
     def upload_xs(self, D=None, SigR=None, NSF=None, Chi=None, SigS=None, SRC=None):
         arrs = [_f64(a) for a in (D, SigR, NSF, Chi, SigS, SRC)]

@@ -155,7 +155,11 @@ public:
         check(nf_set_bc(ctx_, attr, (int)t, v), "nf_set_bc");
     }
     void SetRobin(int attr, double a, double b) { robin_[attr] = {a, b}; }
-    void SetCMFDRelaxation(double w) { cmfd_relax_ = w; }
+    void SetCMFDRelaxation(double w)          // cmfd_data_->relaxation of the reference (NeutFEM.hpp, src/wrapper.cpp set_cmfd_relaxation)
+    {
+        cmfd_relax_ = w;
+        check(nf_set_option(ctx_, "cmfd_relaxation", w), "nf_set_option");
+    }
     void ApplyQuarter(int, int)
     {
         SetBC((int)BoundaryID::LEFT_2D, BCType::MIRROR, 0.0);
@@ -174,9 +178,16 @@ public:
         if (a == "none") accel_ = NF_ACCEL_NONE;
         else if (a == "chebyshev") accel_ = NF_ACCEL_CHEBYSHEV;
         else if (a == "anderson") accel_ = NF_ACCEL_ANDERSON;
-        else throw std::runtime_error("set_accelerator: expected 'none', 'chebyshev' or 'anderson'");
+        else if (a == "cmfd") accel_ = NF_ACCEL_CMFD;
+        else throw std::runtime_error("set_accelerator: expected 'none', 'chebyshev', 'anderson' or 'cmfd'");
     }
     void SetOption(const std::string &key, double value) { check(nf_set_option(ctx_, key.c_str(), value), "nf_set_option"); }
+    double Query(const std::string &key)
+    {
+        double v = 0.0;
+        if (nf_query(ctx_, key.c_str(), &v) != NF_OK) throw std::runtime_error("query: unknown key '" + key + "'");
+        return v;
+    }
     void ResetFlux()
     {
         std::fill(Phi_.begin(), Phi_.end(), 1.0);
@@ -204,7 +215,9 @@ public:
     {
         Log(VerbosityLevel::NORMAL, "\n=== CALCUL DE K-EFFECTIF (DIRECT) ===");
         require_built("SolveKeff");
-        if (use_cmfd) Log(VerbosityLevel::NORMAL, "  Note: CMFD non porte (SURVEY 8(f).3); acceleration externe = ", accel_ == NF_ACCEL_ANDERSON ? "Anderson" : "Chebyshev");
+        // use_cmfd replaces the Chebyshev acceleration by the CMFD correction, like the reference (src/NeutFEM.cpp:1651-1654, 1748-1786)
+        const int accel = use_cmfd ? NF_ACCEL_CMFD : accel_;
+        if (accel == NF_ACCEL_CMFD) Log(VerbosityLevel::NORMAL, "  Acceleration: CMFD active");
         double k0 = -1.0;
         if (use_coarse && !factors.empty()) {
             auto r = SolveCoarse(factors);
@@ -214,7 +227,7 @@ public:
         }
         check(nf_set_flux(ctx_, Phi_.data()), "nf_set_flux");
         double k = 0.0;
-        check(nf_solve_keff(ctx_, use_diag ? 1 : 0, accel_, k0, &k, &stats_), "nf_solve_keff");
+        check(nf_solve_keff(ctx_, use_diag ? 1 : 0, accel, k0, &k, &stats_), "nf_solve_keff");
         check(nf_get_flux(ctx_, Phi_.data()), "nf_get_flux");
         has_valid_ = true; last_k_ = k; J_valid_ = false;
         if (stats_.converged) Log(VerbosityLevel::NORMAL, "  Convergence en ", stats_.outer_iterations, " iterations");
@@ -678,7 +691,9 @@ PYBIND11_MODULE(_neutfem_eigen, m)
                  return py::make_tuple(res.first, a);
              }, py::arg("refine"))
         .def("build_diagonal_cache", &NeutFEM::BuildDiagonalCache)
-        .def("initialize_cmfd", [](NeutFEM &) {})
+        .def("initialize_cmfd", [](NeutFEM &) {}, "The coarse mesh and its work arrays are set up by the first SolveKeff(use_cmfd=True)")
+        .def("query", [](NeutFEM &s, const std::string &key) { return s.Query(key); }, py::arg("key"),
+             "Counters / options of the CUDA library (nf_query): cmfd_calls, cmfd_sweeps, cmfd_last_k, cg_path ... (extension)")
         .def("ExportVTK", &NeutFEM::ExportVTK, py::arg("filename"), py::arg("export_flux") = true, py::arg("export_current") = true,
              py::arg("export_xs") = false, py::arg("export_adjoint") = false)
         .def("ExportFluxVTK", [](NeutFEM &s, const std::string &f, bool adj) { s.ExportVTK(f, true, false, false, adj); },

@@ -20,6 +20,7 @@
 #include "nf_current.cuh"
 #include "nf_fused.cuh"
 #include "nf_rows.cuh"
+#include "nf_cmfd.cuh"
 
 using namespace nf;
 
@@ -84,6 +85,14 @@ struct nf_ctx {
     double *d_and[2 * kAndM + 2] = {nullptr};   // Anderson history: dF[0..m), dG[0..m), f_prev, g_prev (allocated on first use)
     cudaStream_t stream2 = nullptr;        // z-slab ranks: side stream (z forward substitution + all-gather beside the y columns)
     cudaEvent_t evx = nullptr, evz = nullptr;
+    // ---- CMFD acceleration (nf_cmfd.cuh), allocated on first use
+    bool cmfd_ready = false;
+    CmfdData cm;                           // device pointers into d_cmfd / d_cmfd_Jf
+    double *d_cmfd = nullptr, *d_cmfd_Jf = nullptr;
+    int cmfd_c[3] = {0, 0, 0};             // fine cells per coarse cell (options "cmfd_cx/cy/cz"), 0 = automatic
+    CmfdParams cmfd_prm;
+    CmfdResult cmfd_last;
+    long long cmfd_calls = 0, cmfd_sweeps = 0;
 };
 
 #define NC(ctx, call)                                                                                      \
@@ -613,6 +622,90 @@ static int slab_iteration(nf_ctx *c, const FusedArgs &fa, int g, double tol, int
 #undef CALL
 }
 
+// ---- CMFD acceleration (nf_cmfd.cuh) ----------------------------------------------------------------------------------
+// CUDA launch backend of cmfd_correct: functor kernels on the context stream, deterministic 4-value grid reduction.
+struct CudaCmfdBackend {
+    nf_ctx *c;
+    bool good = true;
+    template <class Op>
+    void for_each(const Op &op, long long n)
+    {
+        if (n <= 0 || !good) return;
+        const int grid = (int)std::max<long long>(1, std::min<long long>(16LL * c->sm_count, (n + 127) / 128));
+        k_cmfd_for<Op><<<grid, 128, 0, c->stream>>>(op, n);
+        ++g_launches; ++c->launches_call;
+    }
+    template <class Op>
+    void reduce(const Op &op, long long n, double out[kCmfdNV])
+    {
+        static_assert(kCmfdNV <= 5, "partials: d_part rows 27..31, scalars: d_scal / h_scal 52..56");
+        for (int i = 0; i < kCmfdNV; ++i) out[i] = 0.0;
+        if (n <= 0 || !good) return;
+        const int grid = (int)std::max<long long>(1, std::min<long long>(kRedBlocks, (n + 255) / 256));
+        k_cmfd_reduce<Op><<<grid, 256, 0, c->stream>>>(op, n, c->d_part + (size_t)27 * kRedBlocks, c->d_ticket + 7, c->d_scal + 52);
+        ++g_launches; ++c->launches_call;
+        if (cudaMemcpyAsync(c->h_scal + 52, c->d_scal + 52, kCmfdNV * sizeof(double), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+            cudaStreamSynchronize(c->stream) != cudaSuccess) { good = false; return; }
+        for (int i = 0; i < kCmfdNV; ++i) out[i] = c->h_scal[52 + i];
+    }
+    bool ok()
+    {
+        if (cudaGetLastError() != cudaSuccess) good = false;
+        return good;
+    }
+};
+
+// coarse mesh, coarse widths and the work arrays (one allocation + the fine-face scratch)
+static int cmfd_setup(nf_ctx *c)
+{
+    if (c->cmfd_ready) return NF_OK;
+    if (c->slab) NF_FAIL(c, NF_ERR_STATE, "the CMFD acceleration is not sharded over z-slabs (replicas only, DESIGN.md)");
+    for (double **p : {&c->d_cmfd, &c->d_cmfd_Jf}) if (*p) { cudaFree(*p); *p = nullptr; }
+    CmfdData &m = c->cm;
+    memset(&m, 0, sizeof(m));
+    cmfd_make_grid(m.g, m.ncf, c->nx, c->ny, c->nz, c->dim, c->cmfd_c, c->ng, c->nloc, c->M1, c->K);
+    const size_t total = cmfd_work_doubles(m.g, m.ncf);
+    { int r = dalloc(c, &c->d_cmfd, total); if (r) return r; }
+    const size_t nJf = (size_t)std::max(c->nfaces[0], std::max(c->nfaces[1], c->nfaces[2]));
+    { int r = dalloc(c, &c->d_cmfd_Jf, nJf); if (r) return r; }
+    CU(c, cudaMemsetAsync(c->d_cmfd, 0, total * sizeof(double), c->stream));
+    const size_t hoff = cmfd_partition(m, c->d_cmfd);
+    std::vector<double> hC((size_t)m.g.NCx + m.g.NCy + m.g.NCz);
+    cmfd_coarse_widths(m.g, c->hx.data(), c->hy.data(), c->hz.data(), hC.data());
+    CU(c, cudaMemcpyAsync(c->d_cmfd + hoff, hC.data(), hC.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));          // hC is a stack-lifetime host buffer
+    m.Jf = c->d_cmfd_Jf;
+    m.vol = c->d_vol; m.D = c->d_D; m.SigR = c->d_SigR; m.NSF = c->d_NSF; m.Chi = c->d_Chi; m.SigS = c->d_SigS;
+    static_assert(sizeof(m.wM) == sizeof(c->wM), "mode weight tables");
+    memcpy(m.wM, c->wM, sizeof(m.wM));
+    c->cmfd_ready = true;
+    return NF_OK;
+}
+
+// one CMFD correction of the flux `phi` (SoA, all groups) after a group sweep run with `keff`; prod_old = fission production
+// of the iterate the sweep started from (reference variable of that name, src/NeutFEM.cpp:1703)
+static int cmfd_apply(nf_ctx *c, double *phi, double keff, double prod_old, double damp = 1.0)
+{
+    { int r = cmfd_setup(c); if (r) return r; }
+    c->cm.phi = phi;
+    std::vector<CmfdLine> lines((size_t)c->ng * 3);
+    for (int g = 0; g < c->ng; ++g)
+        for (int d = 0; d < c->dim; ++d) {
+            CmfdLine &l = lines[(size_t)g * 3 + d];
+            l.minv = c->d_minv[g * 3 + d]; l.u = c->d_u[g * 3 + d]; l.w = c->tw[d][0];
+            for (int p = 0; p < 3; ++p) l.mode[p] = (p < c->M1) ? c->tmode[d][0][p] : 0;
+        }
+    CudaCmfdBackend be{c};
+    CmfdResult res;
+    CmfdParams prm = c->cmfd_prm;
+    prm.relaxation *= damp;
+    const int rc = cmfd_correct(be, c->cm, lines.data(), keff, prod_old, prm, &res);
+    if (rc != 0 || !be.ok()) NF_FAIL(c, NF_ERR_CUDA, "CMFD: kernel launch or reduction failed: %s", cudaGetErrorString(cudaGetLastError()));
+    c->cmfd_last = res;
+    c->cmfd_calls += 1; c->cmfd_sweeps += res.sweeps;
+    return NF_OK;
+}
+
 static int dirichlet_flags(const nf_ctx *c, int *fl)
 {
     // side -> attribute map of the reference (NeutFEM::GetBoundaryAttribute, src/NeutFEM.cpp:2338-2347)
@@ -831,6 +924,7 @@ int nf_destroy(nf_ctx *c)
     for (double *p : c->d_s0) if (p) cudaFree(p);
     for (double *p : {c->d_E, c->d_Eall, c->d_vG, c->d_vGall, c->d_lam, c->d_vGnb, c->d_zs}) if (p) cudaFree(p);
     for (double *p : c->d_and) if (p) cudaFree(p);
+    for (double *p : {c->d_cmfd, c->d_cmfd_Jf}) if (p) cudaFree(p);
     if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
     for (cudaEvent_t e : {c->evx, c->evz}) if (e) cudaEventDestroy(e);
     if (c->comm) ncclCommDestroy(c->comm);
@@ -884,7 +978,35 @@ int nf_set_option(nf_ctx *c, const char *key, double value)
     const std::string k(key);
     if (k == "inner_reduction") { if (value < 0.0 || value >= 1.0) NF_FAIL(c, NF_ERR_ARG, "inner_reduction must be in [0, 1)"); c->inner_eta = value; return NF_OK; }
     if (k == "anderson_depth") { if (value < 1 || value > kAndM) NF_FAIL(c, NF_ERR_ARG, "anderson_depth must be in 1..%d", kAndM); c->and_m = (int)value; return NF_OK; }
+    if (k == "cmfd_cx" || k == "cmfd_cy" || k == "cmfd_cz") {
+        if (value < 0 || value > 1e6) NF_FAIL(c, NF_ERR_ARG, "%s must be >= 0 (0 = automatic)", key);
+        c->cmfd_c[k == "cmfd_cx" ? 0 : (k == "cmfd_cy" ? 1 : 2)] = (int)value;
+        c->cmfd_ready = false;
+        return NF_OK;
+    }
+    if (k == "cmfd_relaxation") { if (!(value > 0.0) || value > 2.0) NF_FAIL(c, NF_ERR_ARG, "cmfd_relaxation must be in (0, 2]"); c->cmfd_prm.relaxation = value; return NF_OK; }
+    if (k == "cmfd_tol") { if (!(value > 0.0)) NF_FAIL(c, NF_ERR_ARG, "cmfd_tol must be > 0"); c->cmfd_prm.tol = value; return NF_OK; }
+    if (k == "cmfd_check") { if (value < 1) NF_FAIL(c, NF_ERR_ARG, "cmfd_check must be >= 1"); c->cmfd_prm.check = (int)value; return NF_OK; }
+    if (k == "cmfd_max_sweeps") { if (value < 1) NF_FAIL(c, NF_ERR_ARG, "cmfd_max_sweeps must be >= 1"); c->cmfd_prm.max_sweeps = (int)value; return NF_OK; }
     NF_FAIL(c, NF_ERR_ARG, "nf_set_option: unknown option '%s'", key);
+}
+
+int nf_query(const nf_ctx *c, const char *key, double *value)
+{
+    if (!c || !key || !value) return NF_ERR_ARG;
+    const std::string k(key);
+    if (k == "cmfd_calls") { *value = (double)c->cmfd_calls; return NF_OK; }
+    if (k == "cmfd_sweeps") { *value = (double)c->cmfd_sweeps; return NF_OK; }
+    if (k == "cmfd_last_sweeps") { *value = (double)c->cmfd_last.sweeps; return NF_OK; }
+    if (k == "cmfd_last_k") { *value = c->cmfd_last.k; return NF_OK; }
+    if (k == "cmfd_last_status") { *value = (double)c->cmfd_last.status; return NF_OK; }
+    if (k == "cmfd_last_change") { *value = c->cmfd_last.change; return NF_OK; }
+    if (k == "cmfd_cx") { *value = c->cmfd_ready ? c->cm.g.cx : c->cmfd_c[0]; return NF_OK; }
+    if (k == "cmfd_cy") { *value = c->cmfd_ready ? c->cm.g.cy : c->cmfd_c[1]; return NF_OK; }
+    if (k == "cmfd_cz") { *value = c->cmfd_ready ? c->cm.g.cz : c->cmfd_c[2]; return NF_OK; }
+    if (k == "cmfd_coarse_cells") { *value = c->cmfd_ready ? (double)c->cm.g.NC : 0.0; return NF_OK; }
+    if (k == "cg_path") { *value = (double)c->fused; return NF_OK; }
+    return NF_ERR_ARG;
 }
 
 int nf_upload_xs(nf_ctx *c, const double *D, const double *SigR, const double *NSF, const double *Chi, const double *SigS,
@@ -1230,6 +1352,7 @@ static int power_iteration(nf_ctx *c, bool adjoint, int use_diag, int accel, dou
         for (int j = 0; j < kAndM; ++j) { aa.dF[j] = c->d_and[j]; aa.dG[j] = c->d_and[kAndM + j]; }
         aa.fprev = c->d_and[2 * kAndM]; aa.gprev = c->d_and[2 * kAndM + 1];
     }
+    double cmfd_damp = 1.0, cmfd_dk_prev = 0.0;
     for (int it = 0; it < c->max_outer; ++it) {
         // one sweep: Phi_old = Phi, total fission source (+ prod_old), right-hand side of the first group
         LAUNCH(c, k_total_fission, blocks, 256, 0, oa, c->d_tot, adjoint ? 1 : 0, c->d_part + 5 * kRedBlocks, c->d_ticket + 5, c->d_scal + 0,
@@ -1243,6 +1366,13 @@ static int power_iteration(nf_ctx *c, bool adjoint, int use_diag, int accel, dou
             int r = solve_group(c, g, c->d_rhs, phi + (size_t)g * np, nullptr, nullptr, st);
             if (r) return r;
         }
+        if (accel == NF_ACCEL_CMFD && !adjoint && it >= cheb_from) {
+            // ApplyCMFDCorrection of the reference sits here (src/NeutFEM.cpp:1748-1761): after the sweep, before the k update
+            CU(c, cudaMemcpyAsync(c->h_scal + 60, c->d_scal + 0, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            CU(c, cudaStreamSynchronize(c->stream));
+            int r = cmfd_apply(c, phi, keff, c->h_scal[60], cmfd_damp);
+            if (r) return r;
+        }
         LAUNCH(c, k_outer_post, blocks, 256, 0, oa, c->d_old, adjoint ? 1 : 0, c->d_part + 5 * kRedBlocks, c->d_ticket + 5, c->d_scal + 1);
         { int r = allreduce_sum(c, c->d_scal, 4); if (r) return r; }
         CU(c, cudaMemcpyAsync(c->h_scal, c->d_scal, 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -1252,6 +1382,14 @@ static int power_iteration(nf_ctx *c, bool adjoint, int use_diag, int accel, dou
         if (!adjoint) {
             const double keff_new = keff * (prod_new / prod_old);
             diff_k = std::fabs(keff_new - keff);
+            if (accel == NF_ACCEL_CMFD && it >= cheb_from) {
+                // Oscillation guard: on optically thick cells the CMFD correction overshoots and k alternates around its limit.
+                // Two successive k updates of opposite sign, the second not at least twice smaller: relaxation times 0.7
+                // (floor 0.3 of the configured omega). Same rule in oracle/neutfem_oracle.py SolveKeff.
+                const double dk = keff_new - keff;
+                if (dk * cmfd_dk_prev < 0.0 && std::fabs(dk) > 0.5 * std::fabs(cmfd_dk_prev)) cmfd_damp = std::max(0.3, 0.7 * cmfd_damp);
+                cmfd_dk_prev = dk;
+            }
             if (it >= 1) keff = keff_new;                          // NeutFEM.cpp:1774
         } else if (!fixed_k) {
             double keff_new = keff;
@@ -1330,6 +1468,7 @@ int nf_solve_keff(nf_ctx *c, int use_diag, int accel, double keff_init, double *
     c->launches_call = 0;
     if (use_diag && !(c->K == 0 && c->M == 0)) use_diag = 0;      // NeutFEM.cpp:1640-1644
     if (use_diag) { int r = nf_build_diagonal_cache(c); if (r) return r; }
+    if (accel == NF_ACCEL_CMFD) { int r = cmfd_setup(c); if (r) return r; }
     CU(c, cudaEventRecord(c->ev0, c->stream));
     double k0 = (keff_init > 0) ? keff_init : (c->has_valid ? c->last_keff : 1.0);
     double k = k0;
@@ -1535,6 +1674,20 @@ int nf_get_diagonal_cache(nf_ctx *c, int g, double *s_inv)
     if (!c->diag_valid) NF_FAIL(c, NF_ERR_STATE, "nf_get_diagonal_cache: cache not built");
     CU(c, cudaSetDevice(c->dev));
     CU(c, cudaMemcpy(s_inv, c->d_sinv + (size_t)g * c->ne, (size_t)c->ne * sizeof(double), cudaMemcpyDeviceToHost));
+    return NF_OK;
+}
+
+int nf_cmfd_step(nf_ctx *c, double keff, double prod_old, double *k_coarse, int32_t *sweeps, int32_t *status)
+{
+    if (!c || !(keff > 0.0)) return NF_ERR_ARG;
+    if (!c->built) NF_FAIL(c, NF_ERR_STATE, "nf_cmfd_step: call nf_build first");
+    CU(c, cudaSetDevice(c->dev));
+    c->launches_call = 0;
+    { int r = cmfd_apply(c, c->d_phi, keff, prod_old); if (r) return r; }
+    CU(c, cudaStreamSynchronize(c->stream));
+    if (k_coarse) *k_coarse = c->cmfd_last.k;
+    if (sweeps) *sweeps = c->cmfd_last.sweeps;
+    if (status) *status = c->cmfd_last.status;
     return NF_OK;
 }
 

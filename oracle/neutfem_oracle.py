@@ -639,8 +639,22 @@ class OracleNeutFEM:
 
     # ---- SolveKeff (NeutFEM.cpp:1627-1815)
     def SolveKeff(self, use_coarse_init=False, coarse_factors=(), use_diagonal_solver=False, use_cmfd=False,
-                  max_outer_override=None, accel_kind="chebyshev"):
-        assert not use_cmfd, "CMFD is out of scope (SURVEY section 2)"
+                  max_outer_override=None, accel_kind="chebyshev", cmfd_factors=None, cmfd_relaxation=1.0,
+                  cmfd_solver="lu", cmfd_impl=None):
+        """use_cmfd: the coarse-mesh finite-difference acceleration of oracle/cmfd_oracle.py takes the place of the
+        reference's ApplyCMFDCorrection (NeutFEM.cpp:1748-1761: after the group sweep, before the k update, from it >= 2,
+        Chebyshev off) -- see that module for what the reference's own version does and why it is not restated literally."""
+        cmfd = None
+        if use_cmfd:
+            from oracle.cmfd_oracle import CMFDOracle
+            cmfd = CMFDOracle(self, cmfd_factors, cmfd_relaxation)
+            self.cmfd = cmfd
+        if cmfd_impl is not None:            # tests: another implementation of the same correction (tests/cmfd_shim.py)
+            cmfd = cmfd_impl
+        # Oscillation guard of the CMFD iteration (same rule as nf_api.cu power_iteration): on optically thick cells the
+        # correction overshoots and k alternates around its limit; when two successive k updates have opposite signs and the
+        # second is not at least twice smaller, the relaxation is multiplied by 0.7 (floor 0.3 of the user's omega).
+        cmfd_damp, dk_prev = 1.0, 0.0
         f, ng, nP, nJ = self.fes, self.ng, self.fes.n_Phi, self.fes.n_J
         st = self.stats = SolveStats()
         t_start = time.perf_counter()
@@ -677,11 +691,22 @@ class OracleNeutFEM:
                     self.Sol_J[g * nJ:(g + 1) * nJ] = J
                 else:
                     self._solve_group(g, rhs)
+            if cmfd is not None and it >= 2:
+                if cmfd_impl is not None:
+                    self.Sol_Phi = cmfd.correct(self.Sol_Phi, keff, prod_old, relaxation=cmfd_relaxation * cmfd_damp)
+                else:
+                    cmfd.relaxation = cmfd_relaxation * cmfd_damp
+                    self.Sol_Phi = cmfd.correct(self.Sol_Phi, keff, prod_old, solver=cmfd_solver)
             prod_new = 0.0
             for g in range(ng):
                 prod_new += float((self.M_fiss[g] @ self.Sol_Phi[g * nP:(g + 1) * nP]).sum())
             keff_new = keff * (prod_new / prod_old)
             diff_k = abs(keff_new - keff)
+            if cmfd is not None and it >= 2:
+                dk = keff_new - keff
+                if dk * dk_prev < 0.0 and abs(dk) > 0.5 * abs(dk_prev):
+                    cmfd_damp = max(0.3, 0.7 * cmfd_damp)
+                dk_prev = dk
             if it >= 1:
                 keff = keff_new
             sol_sq = float(self.Sol_Phi @ self.Sol_Phi)
@@ -690,12 +715,14 @@ class OracleNeutFEM:
             norm = math.sqrt(sol_sq)
             if norm > 1e-14:
                 self.Sol_Phi /= norm
-            if it >= 2:
+            if it >= 2 and cmfd is None:
                 if accel_kind == "chebyshev":
                     self.Sol_Phi = accel(self.Sol_Phi)
                 elif anderson is not None:
                     self.Sol_Phi = anderson.step(old, self.Sol_Phi)
             st.outer_iterations = it + 1
+            if getattr(self, "trace", None) is not None:
+                self.trace.append((it, keff, diff_k, diff_flux))
             if diff_k < self.tol_keff and diff_flux < self.tol_flux:
                 st.converged = True
                 break

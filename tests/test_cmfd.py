@@ -1,0 +1,217 @@
+"""CMFD acceleration on the CPU: the oracle restatement (oracle/cmfd_oracle.py) against the unaccelerated
+oracle, and the CUDA library's own CMFD source (neutfem_b200/csrc/nf_cmfd.cuh, compiled with g++ by tests/cmfd_shim.py and run
+in loops) against that oracle -- so the source the GPU executes is checked line by line without a GPU. The GPU tests
+(tests/test_zz_gpu_cmfd.py) then only have to show that the CUDA backend runs the same functors."""
+import numpy as np
+import pytest
+
+from helpers import make_oracle, random_problem
+from oracle.cmfd_oracle import CMFDOracle, default_factors
+
+from cmfd_shim import ShimCMFD
+
+CASES = [   # dim, (nx, ny, nz), rt, p, coarsening, bc
+    (1, (12, 1, 1), 0, 0, (3, 1, 1), "all"),
+    (1, (11, 1, 1), 2, 2, (1, 1, 1), "mixed"),
+    (2, (9, 7, 1), 1, 1, (2, 3, 1), "mixed"),          # ragged last coarse cells in x and y
+    (2, (8, 9, 1), 2, 2, (0, 0, 0), "all"),            # automatic coarsening (= the fine mesh below 64 cells per axis)
+    (3, (5, 4, 6), 1, 1, (2, 2, 4), "mixed"),
+    (3, (6, 4, 5), 0, 0, (4, 3, 2), "all"),
+    (3, (4, 5, 3), 2, 1, (1, 1, 1), "all"),            # mixed orders
+    (3, (4, 4, 4), 2, 2, (2, 2, 2), "mixed"),
+]
+
+
+def _unconverged_iterate(p, rt, pp, noise):
+    o = make_oracle(p, rt, pp)
+    o.set_tol(1e-9, 1e-8, 1e-5, 3, 2000)
+    k = o.SolveKeff()                                   # three outer iterations: far from the fixed point
+    nP = o.fes.n_Phi
+    prod_old = float(sum((o.M_fiss[g] @ o.Sol_Phi[g * nP:(g + 1) * nP]).sum() for g in range(o.ng)))
+    rng = np.random.default_rng(1)
+    phi = o.Sol_Phi * (1.0 + noise * rng.uniform(-1, 1, o.Sol_Phi.size))
+    return o, k, prod_old, phi
+
+
+@pytest.mark.parametrize("dim,n,rt,pp,fac,bc", CASES)
+def test_library_source_matches_oracle_step(dim, n, rt, pp, fac, bc):
+    """Every intermediate of one correction (restriction, coarse-face currents, coarse operator) and the corrected flux."""
+    p = random_problem(5, dim, n, ng=2, bc=bc)
+    o, k, prod_old, phi = _unconverged_iterate(p, rt, pp, 0.3)
+    c = CMFDOracle(o, None if fac == (0, 0, 0) else fac)
+    r = c.restrict(phi)
+    co = c.coefficients(r)
+    s = ShimCMFD(o, fac)
+    out = s.correct(phi, k, prod_old, tol=1e-12, check=20)
+    assert s.c == c.c and s.NC == c.NC[::-1]
+
+    def close(name, a, b, tol=1e-12):
+        a, b = np.asarray(a).ravel(), np.asarray(b).ravel()
+        assert a.shape == b.shape, name
+        assert np.abs(a - b).max() <= tol * max(np.abs(b).max(), 1e-300), name
+
+    for name in ("Phi", "Rem", "Nsf", "ChiP", "Dv", "Sca", "Prf"):
+        close(name, s.array(name), r[name])
+    for d in range(dim):
+        close(f"Jc{d}", s.array(f"Jc{d}"), r["Jc"][d])
+    close("diag", np.where(s.array("diag") > 0, s.array("diag"), 1.0), co["diag"])
+    close("off", s.array("off").reshape((o.ng, 6) + c.NC), np.moveaxis(co["off"], -1, 1))
+    for name in ("nsf", "chi", "sca"):
+        close(name, s.array(name), co[name])
+    assert s.status == 0
+    ref = c.correct(phi, k, prod_old, solver="jacobi", tol=1e-12, check=20)
+    assert abs(s.k - c.last["k_coarse"]) < 1e-10 * s.k
+    assert np.linalg.norm(out - ref) < 1e-9 * np.linalg.norm(ref)
+    ref_lu = c.correct(phi, k, prod_old, solver="lu")           # independent coarse solver (sparse LU power iteration)
+    assert abs(s.k - c.last["k_coarse"]) < 1e-9 * s.k
+    assert np.linalg.norm(out - ref_lu) < 1e-8 * np.linalg.norm(ref_lu)
+    # the correction is what makes the outer iteration's k update land on the coarse eigenvalue
+    nP = o.fes.n_Phi
+    prod_new = float(sum((o.M_fiss[g] @ out[g * nP:(g + 1) * nP]).sum() for g in range(o.ng)))
+    assert abs(k * prod_new / prod_old - s.k) < 1e-10 * s.k
+
+
+def test_mode0_balance_rows_have_two_entries_per_direction():
+    """The net currents are built on this: row (e, 0) of B holds -w / +w on the lowest DOF of the two faces of each direction."""
+    for dim, n, rt, pp in ((1, (5, 1, 1), 2, 1), (2, (4, 3, 1), 1, 1), (3, (3, 2, 2), 2, 2)):
+        o = make_oracle(random_problem(2, dim, n, ng=1, bc="all"), rt, pp)
+        B = o.B.tocsr()
+        nl = o.fes.nphi_loc
+        for e in range(o.fes.ne):
+            row = B[e * nl]
+            assert row.nnz == 2 * dim
+            assert np.allclose(np.abs(row.data), 2.0 ** (dim - 1))
+
+
+@pytest.mark.parametrize("dim,n,rt,pp,fac,bc", [(2, (12, 10, 1), 1, 1, (2, 2, 1), "mixed"), (2, (12, 10, 1), 1, 1, (1, 1, 1), "none"),
+                                                 (3, (6, 5, 4), 1, 0, (2, 2, 2), "all"), (1, (40, 1, 1), 2, 2, (4, 1, 1), "all")])
+def test_cmfd_converges_to_the_unaccelerated_solution(dim, n, rt, pp, fac, bc):
+    """Same (k, flux) as the Chebyshev-accelerated reference iteration, in fewer outer iterations; the library source (shim) and
+    the oracle walk the same iterates."""
+    p = random_problem(5, dim, n, ng=2, bc=bc)
+    res = {}
+    for mode in ("cheb", "oracle", "shim"):
+        o = make_oracle(p, rt, pp)
+        o.set_tol(1e-9, 1e-8, 1e-5, 300, 4000)
+        if mode == "cheb":
+            k = o.SolveKeff()
+        elif mode == "oracle":
+            k = o.SolveKeff(use_cmfd=True, cmfd_factors=fac)
+        else:
+            k = o.SolveKeff(use_cmfd=True, cmfd_factors=fac, cmfd_impl=ShimCMFD(o, fac))
+        assert o.stats.converged
+        res[mode] = (k, o.stats.outer_iterations, o.Sol_Phi.copy())
+    for mode in ("oracle", "shim"):
+        assert abs(res[mode][0] - res["cheb"][0]) < 2e-8
+        assert np.linalg.norm(res[mode][2] - res["cheb"][2]) < 2e-6 * np.linalg.norm(res["cheb"][2])
+        assert res[mode][1] < 0.6 * res["cheb"][1]
+    assert res["shim"][1] == res["oracle"][1]
+    assert abs(res["shim"][0] - res["oracle"][0]) < 1e-9
+
+
+def test_fixed_point_is_left_alone():
+    p = random_problem(7, 2, (10, 8, 1), ng=2, bc="all")
+    o = make_oracle(p, 1, 1)
+    o.set_tol(1e-11, 1e-10, 1e-5, 500, 4000)
+    k = o.SolveKeff()
+    nP = o.fes.n_Phi
+    prod = float(sum((o.M_fiss[g] @ o.Sol_Phi[g * nP:(g + 1) * nP]).sum() for g in range(o.ng)))
+    # a sweep from the converged iterate reproduces it scaled by 1: prod_old == prod_new, k unchanged
+    s = ShimCMFD(o, (2, 2, 1))
+    out = s.correct(o.Sol_Phi, k, prod)
+    assert abs(s.k - k) < 1e-8
+    assert np.linalg.norm(out - o.Sol_Phi) < 1e-6 * np.linalg.norm(o.Sol_Phi)
+
+
+def test_relaxation():
+    p = random_problem(5, 2, (9, 7, 1), ng=2, bc="mixed")
+    o, k, prod_old, phi = _unconverged_iterate(p, 1, 1, 0.2)
+    full = ShimCMFD(o, (2, 2, 1)).correct(phi, k, prod_old)
+    s = ShimCMFD(o, (2, 2, 1))
+    half = s.correct(phi, k, prod_old, relaxation=0.5)
+    c = CMFDOracle(o, (2, 2, 1), relaxation=0.5)
+    ref = c.correct(phi, k, prod_old, solver="lu")
+    assert np.linalg.norm(half - ref) < 1e-8 * np.linalg.norm(ref)
+    assert np.linalg.norm(half - full) > 1e-3 * np.linalg.norm(full)
+    nP = o.fes.n_Phi
+    prod_new = float(sum((o.M_fiss[g] @ half[g * nP:(g + 1) * nP]).sum() for g in range(o.ng)))
+    assert abs(k * prod_new / prod_old - s.k) < 1e-10 * s.k          # the k update still lands on the coarse eigenvalue
+
+
+def test_iterate_without_a_positive_balance_is_skipped():
+    """A flux iterate whose coarse balance has no positive production / loss (here: 30 % noise on every Legendre moment of a
+    problem without Dirichlet sides) is left alone, by the library source and by the oracle alike."""
+    p = random_problem(5, 3, (4, 5, 3), ng=2, bc="none")
+    o, k, prod_old, phi = _unconverged_iterate(p, 2, 1, 0.3)
+    s = ShimCMFD(o, (1, 1, 1))
+    out = s.correct(phi, k, prod_old)
+    assert s.status == 1
+    assert np.array_equal(out, phi)
+    ref = CMFDOracle(o, (1, 1, 1)).correct(phi, k, prod_old, solver="jacobi")
+    assert np.array_equal(ref, phi)
+
+
+def _cheb_vs_cmfd(p, rt, pp, fac, tol=(1e-8, 1e-7)):
+    from oracle.neutfem_oracle import OracleNeutFEM
+    res = {}
+    for mode in ("cheb", "cmfd"):
+        o = OracleNeutFEM(rt, pp, p.ng, p.x_breaks, p.y_breaks, p.z_breaks, fast_assembly=True)
+        p.apply(o)
+        o.set_linear_solver(6)
+        o.set_tol(tol[0], tol[1], 1e-5, 400, 4000)
+        o.BuildMatrices()
+        sh = ShimCMFD(o, fac)
+        k = o.SolveKeff() if mode == "cheb" else o.SolveKeff(use_cmfd=True, cmfd_factors=fac, cmfd_impl=sh)
+        assert o.stats.converged
+        res[mode] = (k, o.stats.outer_iterations, sh.status if mode == "cmfd" else 0)
+    return res
+
+
+def test_koeberg_four_groups_upscatter_blank_cells():
+    """KOEBERG-2D (SURVEY config 4 material set): 4 groups with up-scattering, 'blank' cells with Sigma_r = 1e8 whose flux is
+    rounding noise -- left alone by the floor -- and a third of the outer iterations of the Chebyshev run."""
+    from neutfem_b200 import benchmarks as bm
+    res = _cheb_vs_cmfd(bm.problem_2d("koeberg2d", 4), 0, 0, (2, 2, 1))
+    assert res["cmfd"][2] == 0
+    assert abs(res["cmfd"][0] - res["cheb"][0]) < 5e-8
+    assert res["cmfd"][1] <= 0.4 * res["cheb"][1]
+
+
+def test_iaea3d_void_cells_thick_mesh():
+    """IAEA-3D with its 1e15 'void' cells on 19 cm cells: far too thick for CMFD to pay (the oscillation guard ends at the lowest
+    relaxation), but the coarse solve must converge (the void cells would otherwise put +-1e15 into the coarse operator and the
+    two-group bipartite structure an eigenvalue -1 into the Jacobi sweeps) and the answer must be the unaccelerated one."""
+    from neutfem_b200 import benchmarks as bm
+    res = _cheb_vs_cmfd(bm.problem_iaea3d_synthetic(20, 20, 10), 0, 0, (2, 2, 2))
+    assert res["cmfd"][2] == 0
+    assert abs(res["cmfd"][0] - res["cheb"][0]) < 5e-6
+
+
+def test_default_coarsening():
+    assert default_factors(34, 34, 1) == (1, 1, 1)
+    assert default_factors(512, 512, 400) == (8, 8, 7)
+    assert default_factors(65, 64, 129) == (2, 1, 3)
+    p = random_problem(1, 2, (70, 3, 1), ng=1, bc="all")
+    o = make_oracle(p, 0, 0)
+    s = ShimCMFD(o, (0, 0, 0))
+    assert s.c == default_factors(70, 3, 1) and s.NC == (35, 3, 1)
+
+
+def test_rtk_p0_diffuses_four_times_faster():
+    """Why the finite-difference coupling of the coarse operator carries a factor 4 for RT_k-P0, k >= 1: in a homogeneous slab
+    k_eff = nuSf / (Sr + D_eff B^2) gives D_eff(RT1-P0) ~ 4 D_eff(RT0-P0) (the bubble DOFs have no flux moment to couple to)."""
+    from oracle.neutfem_oracle import OracleNeutFEM
+    L, n = 100.0, 100
+    deff = {}
+    for K, M in ((0, 0), (1, 0), (1, 1)):
+        o = OracleNeutFEM(K, M, 1, np.linspace(0, L, n + 1), np.array([0.0]), np.array([0.0]))
+        o.set_linear_solver(6)
+        o.set_bc(1, 0, 0.0)
+        o.set_bc(2, 0, 0.0)
+        o.D[:], o.SigR[:], o.NSF[:], o.Chi[:] = 1.0, 0.02, 0.03, 1.0
+        o.set_tol(1e-9, 1e-8, 1e-5, 2000, 5000)
+        o.BuildMatrices()
+        k = o.SolveKeff()
+        deff[(K, M)] = (0.03 / k - 0.02) / (np.pi / L) ** 2
+    assert abs(deff[(1, 1)] / deff[(0, 0)] - 1.0) < 0.01
+    assert 3.8 < deff[(1, 0)] / deff[(0, 0)] < 4.5
