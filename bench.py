@@ -463,37 +463,56 @@ def run_ours(args):
     s_per_outer = ms * 1e-3 / max(K, 1)
     ttk = {"mesh": list(mesh), "tolerances": {"keff": 1e-5, "flux": 1e-4}, "what": "nf_solve_keff to convergence + nf_get_flux, wall clock, XS resident"}
     conv = dict(solver_type=cabi.BICGSTAB, tol_keff=1e-5, tol_flux=1e-4, max_inner=2000, mode=mode)
-    for tag in ("coarse_start", "flat_start"):          # the cheaper one first: it is the one that must fit the budget
+    # Chebyshev (the reference's accelerator) from the coarse-mesh start and from the flat flux, and the CMFD acceleration
+    # (SolveKeff(use_cmfd=True); single GPU) from the coarse-mesh start (NEUTFEM_BENCH_CMFD_FLAT=1: also from the flat flux). The
+    # Chebyshev runs come first, the CMFD runs are capped at 40 outer iterations and an error there is reported in their section.
+    tags = ["coarse_start", "flat_start", "cmfd_coarse_start"] + (["cmfd_flat_start"] if os.environ.get("NEUTFEM_BENCH_CMFD_FLAT") == "1" else [])
+    for tag in tags:
+        cmfd = tag.startswith("cmfd")
         if args.no_converged:
             ttk[tag] = {"skipped": "--no-converged"}
+            continue
+        if cmfd and world > 1:
+            ttk[tag] = {"skipped": "the CMFD acceleration is not sharded over z-slabs (single GPU only)"}
             continue
         left = gmax(-budget_left()) * -1.0                      # min over ranks
         # safety cap on the outer iterations, not a target: later outer iterations are cheaper than the average of the first K
         # (warm-started inner solves), so 0.9 x that average is a fair price per iteration
         cap = int((left - 30.0) / (0.9 * s_per_outer))
+        if cmfd:
+            cap = min(cap, 40)
         if cap < 12:
             ttk[tag] = {"skipped": f"wall-clock budget: {left:.0f} s left, {s_per_outer:.1f} s per outer iteration"}
             continue
-        ctx.reset_flux()
-        barrier()
-        t0 = time.perf_counter()
-        extra = {}
-        k0 = -1.0
-        if tag == "coarse_start":
-            kc, f0, tc = coarse_initial_flux(args, cabi, bm, mesh, (z0, z1), local_rank)
-            ctx.set_flux(f0)
-            del f0
-            k0 = kc
-            extra = {"coarse": {"mesh": [m // 2 for m in mesh], "order": "RT0-P0", "keff": kc, "seconds": tc}}
-        ctx.set_solver(max_outer=min(cap, 400), **conv)
-        kc2, st2 = ctx.solve_keff(False, cabi.ACCEL_CHEBYSHEV, k0)
-        fl = ctx.get_flux()
-        barrier()
-        dtc = gmax(time.perf_counter() - t0)
-        ttk[tag] = dict(seconds=dtc, keff=kc2, converged=bool(st2["converged"]), outer_iterations=st2["outer_iterations"],
-                        cg_iterations=st2["cg_iterations"], outer_cap=min(cap, 400),
-                        schur_cg_gdof_per_s=gsum(st2["cg_dof_iterations"]) / max(gmax(st2["ms_schur_cg"]), 1e-9) / 1e6, **extra)
-        del fl
+        try:
+            ctx.reset_flux()
+            barrier()
+            t0 = time.perf_counter()
+            extra = {}
+            k0 = -1.0
+            if tag.endswith("coarse_start"):
+                kc, f0, tc = coarse_initial_flux(args, cabi, bm, mesh, (z0, z1), local_rank)
+                ctx.set_flux(f0)
+                del f0
+                k0 = kc
+                extra = {"coarse": {"mesh": [m // 2 for m in mesh], "order": "RT0-P0", "keff": kc, "seconds": tc}}
+            ctx.set_solver(max_outer=min(cap, 400), **conv)
+            kc2, st2 = ctx.solve_keff(False, cabi.ACCEL_CMFD if cmfd else cabi.ACCEL_CHEBYSHEV, k0)
+            fl = ctx.get_flux()
+            barrier()
+            dtc = gmax(time.perf_counter() - t0)
+            if cmfd:
+                extra["cmfd"] = {"coarsening": [int(ctx.query(k)) for k in ("cmfd_cx", "cmfd_cy", "cmfd_cz")],
+                                 "coarse_cells": int(ctx.query("cmfd_coarse_cells")), "corrections": int(ctx.query("cmfd_calls")),
+                                 "jacobi_sweeps": int(ctx.query("cmfd_sweeps")), "last_status": int(ctx.query("cmfd_last_status"))}
+            ttk[tag] = dict(seconds=dtc, keff=kc2, converged=bool(st2["converged"]), outer_iterations=st2["outer_iterations"],
+                            cg_iterations=st2["cg_iterations"], outer_cap=min(cap, 400), accelerator="cmfd" if cmfd else "chebyshev",
+                            schur_cg_gdof_per_s=gsum(st2["cg_dof_iterations"]) / max(gmax(st2["ms_schur_cg"]), 1e-9) / 1e6, **extra)
+            del fl
+        except RuntimeError as e:
+            if not cmfd:
+                raise
+            ttk[tag] = {"error": str(e)[:300]}
     line["time_to_keff"] = ttk
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args)

@@ -1353,6 +1353,7 @@ static int power_iteration(nf_ctx *c, bool adjoint, int use_diag, int accel, dou
         aa.fprev = c->d_and[2 * kAndM]; aa.gprev = c->d_and[2 * kAndM + 1];
     }
     double cmfd_damp = 1.0, cmfd_dk_prev = 0.0;
+    bool cmfd_osc_prev = false;
     for (int it = 0; it < c->max_outer; ++it) {
         // one sweep: Phi_old = Phi, total fission source (+ prod_old), right-hand side of the first group
         LAUNCH(c, k_total_fission, blocks, 256, 0, oa, c->d_tot, adjoint ? 1 : 0, c->d_part + 5 * kRedBlocks, c->d_ticket + 5, c->d_scal + 0,
@@ -1384,11 +1385,12 @@ static int power_iteration(nf_ctx *c, bool adjoint, int use_diag, int accel, dou
             diff_k = std::fabs(keff_new - keff);
             if (accel == NF_ACCEL_CMFD && it >= cheb_from) {
                 // Oscillation guard: on optically thick cells the CMFD correction overshoots and k alternates around its limit.
-                // Two successive k updates of opposite sign, the second not at least twice smaller: relaxation times 0.7
-                // (floor 0.3 of the configured omega). Same rule in oracle/neutfem_oracle.py SolveKeff.
+                // A k update of the opposite sign of the one before and not at least twice smaller, two outer iterations in a
+                // row: relaxation times 0.7 (floor 0.3 of the configured omega). Same rule in oracle/neutfem_oracle.py SolveKeff.
                 const double dk = keff_new - keff;
-                if (dk * cmfd_dk_prev < 0.0 && std::fabs(dk) > 0.5 * std::fabs(cmfd_dk_prev)) cmfd_damp = std::max(0.3, 0.7 * cmfd_damp);
-                cmfd_dk_prev = dk;
+                const bool osc = dk * cmfd_dk_prev < 0.0 && std::fabs(dk) > 0.5 * std::fabs(cmfd_dk_prev);
+                if (osc && cmfd_osc_prev) cmfd_damp = std::max(0.3, 0.7 * cmfd_damp);
+                cmfd_dk_prev = dk; cmfd_osc_prev = osc;
             }
             if (it >= 1) keff = keff_new;                          // NeutFEM.cpp:1774
         } else if (!fixed_k) {

@@ -652,9 +652,10 @@ class OracleNeutFEM:
         if cmfd_impl is not None:            # tests: another implementation of the same correction (tests/cmfd_shim.py)
             cmfd = cmfd_impl
         # Oscillation guard of the CMFD iteration (same rule as nf_api.cu power_iteration): on optically thick cells the
-        # correction overshoots and k alternates around its limit; when two successive k updates have opposite signs and the
-        # second is not at least twice smaller, the relaxation is multiplied by 0.7 (floor 0.3 of the user's omega).
-        cmfd_damp, dk_prev = 1.0, 0.0
+        # correction overshoots and k alternates around its limit; when a k update has the opposite sign of the one before and
+        # is not at least twice smaller, two outer iterations in a row, the relaxation is multiplied by 0.7 (floor 0.3 of the
+        # user's omega).
+        cmfd_damp, dk_prev, osc_prev = 1.0, 0.0, False
         f, ng, nP, nJ = self.fes, self.ng, self.fes.n_Phi, self.fes.n_J
         st = self.stats = SolveStats()
         t_start = time.perf_counter()
@@ -704,9 +705,10 @@ class OracleNeutFEM:
             diff_k = abs(keff_new - keff)
             if cmfd is not None and it >= 2:
                 dk = keff_new - keff
-                if dk * dk_prev < 0.0 and abs(dk) > 0.5 * abs(dk_prev):
+                osc = dk * dk_prev < 0.0 and abs(dk) > 0.5 * abs(dk_prev)
+                if osc and osc_prev:
                     cmfd_damp = max(0.3, 0.7 * cmfd_damp)
-                dk_prev = dk
+                dk_prev, osc_prev = dk, osc
             if it >= 1:
                 keff = keff_new
             sol_sq = float(self.Sol_Phi @ self.Sol_Phi)
