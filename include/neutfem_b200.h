@@ -47,7 +47,8 @@ enum { NF_MODE_PARITY = 0, NF_MODE_FAST = 1 };
  * SolveKeff(use_cmfd=true) calls ApplyCMFDCorrection (NeutFEM.cpp:1748-1761). The reference's version (NeutFEM.cpp:662-1017)
  * corrects the x faces only and has no scattering source, so its fixed point is not the fine solution in 2-D / 3-D; the
  * complete method (all directions, multigroup coarse eigenvalue problem, any coarsening) is implemented instead
- * (neutfem_b200/csrc/nf_cmfd.cuh, CPU restatement oracle/cmfd_oracle.py). Single GPU only. Parity unpinned. */
+ * (neutfem_b200/csrc/nf_cmfd.cuh, CPU restatement oracle/cmfd_oracle.py). Single GPU only; with use_diagonal_solver the
+ * Chebyshev acceleration is kept (the diagonal path's fixed point is not that of the exact balance). Parity unpinned. */
 enum { NF_ACCEL_NONE = 0, NF_ACCEL_CHEBYSHEV = 1, NF_ACCEL_ANDERSON = 2, NF_ACCEL_CMFD = 3 };
 
 enum { NF_OK = 0, NF_ERR_ARG = -1, NF_ERR_CUDA = -2, NF_ERR_STATE = -3, NF_ERR_NCCL = -4, NF_ERR_NODEVICE = -5 };

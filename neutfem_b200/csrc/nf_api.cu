@@ -1470,6 +1470,9 @@ int nf_solve_keff(nf_ctx *c, int use_diag, int accel, double keff_init, double *
     c->launches_call = 0;
     if (use_diag && !(c->K == 0 && c->M == 0)) use_diag = 0;      // NeutFEM.cpp:1640-1644
     if (use_diag) { int r = nf_build_diagonal_cache(c); if (r) return r; }
+    // The diagonal RT0-P0 path replaces S by its diagonal: its fixed point is not that of the exact balance the CMFD correction
+    // is built on (the two fight each other, oracle experiment in DESIGN.md 4.3), so that path keeps the Chebyshev acceleration.
+    if (use_diag && accel == NF_ACCEL_CMFD) accel = NF_ACCEL_CHEBYSHEV;
     if (accel == NF_ACCEL_CMFD) { int r = cmfd_setup(c); if (r) return r; }
     CU(c, cudaEventRecord(c->ev0, c->stream));
     double k0 = (keff_init > 0) ? keff_init : (c->has_valid ? c->last_keff : 1.0);

@@ -645,6 +645,10 @@ class OracleNeutFEM:
         reference's ApplyCMFDCorrection (NeutFEM.cpp:1748-1761: after the group sweep, before the k update, from it >= 2,
         Chebyshev off) -- see that module for what the reference's own version does and why it is not restated literally."""
         cmfd = None
+        if use_diagonal_solver and not (self.rt_order == 0 and self.p_order == 0):
+            use_diagonal_solver = False
+        if use_cmfd and use_diagonal_solver:      # the diagonal path keeps Chebyshev (its fixed point is not the exact balance's)
+            use_cmfd, cmfd_impl = False, None
         if use_cmfd:
             from oracle.cmfd_oracle import CMFDOracle
             cmfd = CMFDOracle(self, cmfd_factors, cmfd_relaxation)

@@ -185,6 +185,23 @@ def test_module_use_cmfd_flag(tmp_path):
     assert its[True] < 0.6 * its[False]
 
 
+def test_diagonal_path_keeps_chebyshev():
+    from neutfem_b200 import cabi
+    p = bm.problem_2d("iaea2d", 1)
+    res = []
+    for accel in (cabi.ACCEL_CHEBYSHEV, cabi.ACCEL_CMFD):
+        c = cabi.Context(0, 0, p.ng, p.x_breaks, p.y_breaks, p.z_breaks)
+        for a, t, v in p.bcs:
+            c.set_bc(a, t, v)
+        c.upload_xs(D=p.D, SigR=p.SigR, NSF=p.NSF, Chi=p.Chi, SigS=p.SigS)
+        c.build()
+        c.set_solver(solver_type=cabi.BICGSTAB, tol_keff=1e-6, tol_flux=1e-5, max_outer=300)
+        k, st = c.solve_keff(True, accel)
+        res.append((k, st["outer_iterations"], c.query("cmfd_calls")))
+        c.close()
+    assert res[0] == res[1] and res[1][2] == 0
+
+
 def test_cmfd_options_and_relaxation():
     from neutfem_b200 import cabi
     p = random_problem(3, 2, (6, 5, 1), ng=1, bc="all")
