@@ -18,7 +18,10 @@
 //      a_F = D~_F / V_L (+ delta / X_L if delta > 0), b_F = D~_F / V_R (+ -delta / X_R if delta < 0), delta = the part of the
 //      fine current the finite-difference coupling D~_F does not explain. The correction sits on the upstream side, so
 //      a_F, b_F > 0 for ANY fine iterate: the coarse matrix is a column-diagonally-dominant M-matrix and plain Jacobi sweeps
-//      converge. Boundary faces: J_F = alpha_F X_I.
+//      converge. Boundary faces: J_F = alpha_F X_I. Entries whose flux integral is not positive ("void" cells with Sigma_r = 1e15,
+//      negative cell fluxes of RT0 on very thick cells) cannot be rows of an M-matrix: they are frozen at their flux integral,
+//      keep feeding the fission / scattering sources of the rows that are solved, the faces towards them are closed like
+//      boundary faces, and they follow the mean flux ratio -- so the fixed point stays the fine eigenpair.
 //   4. CmfdSweepOp  Jacobi sweeps of the coarse multigroup eigenvalue problem, all groups in one launch, no reduction; every
 //      `check` sweeps CmfdCheckOp (one deterministic grid reduction) gives k = production / net loss and the l1 change of the
 //      last sweep. The coarse problem is tiny (<= 64^3 cells by default): the solve is launch-bound by design and costs tens
@@ -223,6 +226,17 @@ struct CmfdNormOp {
     NF_HD void operator()(long long t, double v[5]) const { v[0] = fabs(d.Phi[t]); v[1] = v[2] = v[3] = v[4] = 0.0; }
 };
 
+// production of the frozen entries (v[0]) and of all entries (v[1]) at the start of the coarse iteration
+struct CmfdFrozenOp {
+    CmfdData d;
+    NF_HD void operator()(long long t, double v[5]) const
+    {
+        const double p = d.nsf[t] * d.X[t];
+        v[0] = (d.diag[t] > 0.0) ? 0.0 : p;
+        v[1] = p; v[2] = v[3] = v[4] = 0.0;
+    }
+};
+
 // ---- 3. coarse operator, one thread per (group, coarse cell) -------------------------------------------------------------------
 struct CmfdCoefOp {
     CmfdData d;
@@ -252,7 +266,12 @@ struct CmfdCoefOp {
             else flo = ((long long)ic[2] * g.NCy + ic[1]) * g.NCx + ic[0];
             const long long fhi = flo + ((dir == 0) ? 1 : (dir == 1 ? (long long)g.NCx : (long long)g.NCx * g.NCy));
             const double *Jc = d.Jc[dir] + (size_t)gr * d.ncf[dir];
-            if (ic[dir] < nc[dir] - 1) {                 // + face: this cell is the low side (L)
+            // A neighbour without a positive flux integral (void cells; negative cell fluxes of RT0 on very thick cells) is not
+            // part of the coarse system: the face towards it is treated like a boundary face (outflow = alpha X), which
+            // reproduces the fine current whatever that neighbour holds -- the fixed point stays the fine solution.
+            const bool hasR = ic[dir] < nc[dir] - 1 && d.Phi[t + stride[dir]] > fl;
+            const bool hasL = ic[dir] > 0 && d.Phi[t - stride[dir]] > fl;
+            if (hasR) {                                  // + face: this cell is the low side (L)
                 const long long R = t + stride[dir];
                 const double PR = d.Phi[R], HR = d.hC[dir][ic[dir] + 1], VR = area * HR;
                 const double Dt = dts * 2.0 * area / (HI / DI + HR / d.Dv[R]);
@@ -261,7 +280,7 @@ struct CmfdCoefOp {
                 const double b = Dt / VR + ((delta < 0.0 && PR > fl) ? -delta / PR : 0.0);
                 diag += a; off[2 * dir + 1] = b;
             } else diag += pos ? Jc[fhi] / PI : 0.0;     // boundary: outflow = alpha X
-            if (ic[dir] > 0) {                           // - face: this cell is the high side (R)
+            if (hasL) {                                  // - face: this cell is the high side (R)
                 const long long Lc = t - stride[dir];
                 const double PL = d.Phi[Lc], HL = d.hC[dir][ic[dir] - 1], VL = area * HL;
                 const double Dt = dts * 2.0 * area / (HL / d.Dv[Lc] + HI / DI);
@@ -274,15 +293,19 @@ struct CmfdCoefOp {
         const bool active = pos && diag > 0.0;
         d.diag[t] = active ? diag : 0.0;
         for (int s = 0; s < 6; ++s) d.off[((size_t)gr * 6 + s) * g.NC + I] = active ? off[s] : 0.0;
-        d.nsf[t] = active ? d.Nsf[t] / PI : 0.0;
+        // Entries that are not rows of the coarse system keep their flux integral (frozen) and still feed
+        // the fission and scattering sources of the rows that are: dropping them would move the fixed point (a negative fast
+        // flux in a thick reflector cell scatters a negative source into the thermal group of that cell).
+        const bool fed = fabs(PI) > fl;
+        d.nsf[t] = fed ? d.Nsf[t] / PI : 0.0;
         double Ptot = 0.0;
         for (int g2 = 0; g2 < g.ng; ++g2) Ptot += d.Nsf[(size_t)g2 * g.NC + I];
         d.chi[t] = (Ptot > 0.0) ? d.ChiP[t] / Ptot : 0.0;
         for (int gt = 0; gt < g.ng; ++gt) {
             const size_t q = ((size_t)gt * g.ng + gr) * g.NC + I;
-            d.sca[q] = (active && gt != gr) ? d.Sca[q] / PI : 0.0;
+            d.sca[q] = (fed && gt != gr) ? d.Sca[q] / PI : 0.0;
         }
-        d.X[t] = active ? PI : 0.0;
+        d.X[t] = PI;
     }
 };
 
@@ -309,7 +332,7 @@ struct CmfdSweepOp {
     {
         const CmfdGrid &g = d.g;
         const double dg = d.diag[t];
-        if (!(dg > 0.0)) { Xout[t] = 0.0; return; }
+        if (!(dg > 0.0)) { Xout[t] = Xin[t]; return; }              // not a row of the coarse system: frozen
         const int gr = (int)(t / g.NC);
         const long long I = t - (long long)gr * g.NC;
         double P = 0.0;
@@ -352,7 +375,8 @@ struct CmfdCheckOp {
 
 // ---- 5. flux ratio per (group, coarse cell) and its application to the fine flux ---------------------------------------------
 // what the outer iteration's production count becomes under the correction: v[0] sum of (X / X0) Prf over the corrected cells,
-// v[1] sum of Prf over the cells left alone, v[2] sum of Prf over all cells
+// v[1] sum of Prf over the cells that are not part of the coarse system, v[2] sum of Prf over all cells; v[3], v[4]: sums of X and
+// X0 over the corrected cells (their mean ratio is what the other cells get)
 struct CmfdScaleOp {
     CmfdData d; const double *X;
     NF_HD void operator()(long long t, double v[kCmfdNV]) const
@@ -361,16 +385,20 @@ struct CmfdScaleOp {
         const bool ok = x0 > d.phi_floor && x1 > 0.0;
         v[0] = ok ? (x1 / x0) * pr : 0.0;
         v[1] = ok ? 0.0 : pr;
-        v[2] = pr; v[3] = 0.0; v[4] = 0.0;
+        v[2] = pr;
+        v[3] = ok ? x1 : 0.0;
+        v[4] = ok ? x0 : 0.0;
     }
 };
 
+// Cells outside the coarse system (void cells, negative cell fluxes) follow the mean ratio of the corrected cells: leaving them
+// alone would let their amplitude drift against the rest and give the accelerated iteration a fixed point of its own.
 struct CmfdRatioOp {
-    CmfdData d; const double *X; double s, omega;
+    CmfdData d; const double *X; double s, rbar, omega;
     NF_HD void operator()(long long t) const
     {
         const double x0 = d.Phi[t], x1 = X[t];
-        const double r = (x0 > d.phi_floor && x1 > 0.0) ? s * x1 / x0 : 1.0;
+        const double r = (x0 > d.phi_floor && x1 > 0.0) ? s * x1 / x0 : s * rbar;
         d.ratio[t] = omega * r + (1.0 - omega);
     }
 };
@@ -416,11 +444,21 @@ int cmfd_correct(Backend &be, CmfdData &d, const CmfdLine *lines, double keff, d
         d.phi_floor = prm.floor_rel * v[0] / (double)ncell;
     }
     be.for_each(CmfdCoefOp{d}, ncell);
-    double k = keff, scale = 1.0, P = 0.0, P0 = -1.0;
+    // The frozen entries make the coarse problem inhomogeneous: find (X, k) on the rows of the system with the frozen entries
+    // held and the TOTAL production held at its initial value P0 (only the rows of the system are renormalised).
+    double Pf = 0.0, P0 = 0.0;
+    {
+        double v[kCmfdNV] = {0.0, 0.0, 0.0, 0.0, 0.0};
+        be.reduce(CmfdFrozenOp{d}, ncell, v);
+        if (!be.ok()) return -1;
+        Pf = v[0]; P0 = v[1];
+    }
+    double k = keff, scale = 1.0, P = 0.0, rbar = 1.0;
+    if (!(P0 - Pf > 0.0)) r.status = 1;
     double *cur = d.X, *nxt = d.Y;
     const int check = prm.check > 0 ? prm.check : 1;
     bool converged = false;
-    while (r.sweeps < prm.max_sweeps && !converged) {
+    while (r.status != 1 && r.sweeps < prm.max_sweeps && !converged) {
         for (int j = 0; j < check; ++j) {
             be.for_each(CmfdSweepOp{d, cur, nxt, 1.0 / k, scale, prm.theta}, ncell);
             scale = 1.0;
@@ -431,10 +469,9 @@ int cmfd_correct(Backend &be, CmfdData &d, const CmfdLine *lines, double keff, d
         be.reduce(CmfdCheckOp{d, cur, nxt}, ncell, v);
         if (!be.ok()) return -1;
         P = v[0];
-        if (!(P > 0.0) || !(v[1] > 0.0) || !(v[3] > 0.0) || !(v[4] > 0.0)) { r.status = 1; break; }
+        if (!(P - Pf > 0.0) || !(v[1] > 0.0) || !(v[3] > 0.0) || !(v[4] > 0.0)) { r.status = 1; break; }
         k = v[4] / v[1];
-        if (P0 < 0.0) P0 = P;
-        scale = P0 / P;
+        scale = (P0 - Pf) / (P - Pf);
         r.change = v[2] / v[3];
         converged = r.change < prm.tol;
     }
@@ -442,16 +479,18 @@ int cmfd_correct(Backend &be, CmfdData &d, const CmfdLine *lines, double keff, d
     if (r.status != 1) {
         if (!converged) r.status = 2;
         // scale s of the coarse eigenvector such that the production count of the corrected flux is (k_coarse / keff) prod_old,
-        // i.e. the k update of the outer iteration lands on k_coarse:  omega (s A + B_alone) + (1 - omega) B_all = target
+        // i.e. the k update of the outer iteration lands on k_coarse:  omega s (A + rbar B_other) + (1 - omega) B_all = target
         double v[kCmfdNV] = {0.0, 0.0, 0.0, 0.0, 0.0};
         be.reduce(CmfdScaleOp{d, cur}, ncell, v);
         if (!be.ok()) return -1;
         const double om = prm.relaxation, target = (k / keff) * prod_old;
-        r.ratio_scale = (target - (1.0 - om) * v[2] - om * v[1]) / (om * v[0]);
-        if (!(r.ratio_scale > 0.0) || !(prod_old > 0.0) || !(v[0] > 0.0)) r.status = 1;
+        rbar = (v[4] > 0.0) ? v[3] / v[4] : 1.0;
+        const double den = om * (v[0] + rbar * v[1]);
+        r.ratio_scale = (target - (1.0 - om) * v[2]) / den;
+        if (!(r.ratio_scale > 0.0) || !(prod_old > 0.0) || !(den > 0.0) || !(rbar > 0.0)) r.status = 1;
     }
     if (r.status != 1) {
-        be.for_each(CmfdRatioOp{d, cur, r.ratio_scale, prm.relaxation}, ncell);
+        be.for_each(CmfdRatioOp{d, cur, r.ratio_scale, rbar, prm.relaxation}, ncell);
         be.for_each(CmfdProlongOp{d}, (long long)g.ng * g.ne);
     }
     if (!be.ok()) return -1;

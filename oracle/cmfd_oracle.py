@@ -19,9 +19,15 @@ library implements (neutfem_b200/csrc/nf_cmfd.cuh), so that the two can be compa
      finite-difference coupling D~_F (harmonic mean of the volume-averaged D) plus the correction that reproduces the fine
      current, put on the upstream side (a_F, b_F >= D~ > 0: the coarse matrix is a column-diagonally-dominant M-matrix for any
      fine iterate, which is what lets the GPU solve it with plain Jacobi sweeps); boundary faces: J_F = alpha_F X_I;
-  3. the coarse multigroup eigenvalue problem  M X = (1/k) chi (nsf . X) + S X  with flux-weighted coefficients;
-  4. fine flux <- fine flux * (X_new / X_old) per coarse cell and group (all Legendre modes), relaxed by omega, the coarse
-     eigenvector scaled so that the reference's own update k <- k * prod_new / prod_old yields the coarse eigenvalue.
+  3. the coarse multigroup eigenvalue problem  M X = (1/k) chi (nsf . X) + S X  with flux-weighted coefficients. Entries (group,
+     coarse cell) whose flux integral is not positive -- "void" cells (Sigma_r = 1e15: rounding noise of either sign) and the
+     negative cell fluxes RT0 produces on very thick cells -- cannot be rows of an M-matrix: they are FROZEN at their flux
+     integral, keep feeding the fission / scattering sources of the rows that are solved, and the faces towards them are closed
+     like boundary faces (outflow = alpha X, reproducing the fine current); the total production is held while the rows are
+     renormalised, which makes (X, k) well defined;
+  4. fine flux <- fine flux * (X_new / X_old) per coarse cell and group (all Legendre modes; frozen entries: the mean ratio of
+     the others), relaxed by omega, the coarse eigenvector scaled so that the reference's own update k <- k * prod_new /
+     prod_old yields the coarse eigenvalue.
 
 At the fixed point of the fine iteration the coarse problem is satisfied by the restricted fine solution with the fine k, so
 the ratio is one: the accelerated iteration converges to the same (k, flux) as the unaccelerated one.
@@ -167,19 +173,25 @@ class CMFDOracle:
                 # the correction goes on the upstream side: a, b >= Dt / V > 0 whatever the fine iterate is
                 a = Dt / VL + np.where((delta > 0) & (PL > fl), delta / np.where(PL > fl, PL, 1.0), 0.0)
                 b = Dt / VR + np.where((delta < 0) & (PR > fl), -delta / np.where(PR > fl, PR, 1.0), 0.0)
-                diag[sl(0, n - 1)] += a
-                off[sl(0, n - 1) + (2 * d + 1,)] = b
-                diag[sl(1, n)] += b
-                off[sl(1, n) + (2 * d,)] = a
+                # a neighbour without a positive flux integral is not part of the coarse system: the face towards it is treated
+                # like a boundary face (outflow = alpha X), which reproduces the fine current whatever that neighbour holds
+                both = (PL > fl) & (PR > fl)
+                diag[sl(0, n - 1)] += np.where(both, a, np.where(PL > fl, J / np.where(PL > fl, PL, 1.0), 0.0))
+                off[sl(0, n - 1) + (2 * d + 1,)] = np.where(both, b, 0.0)
+                diag[sl(1, n)] += np.where(both, b, np.where(PR > fl, -J / np.where(PR > fl, PR, 1.0), 0.0))
+                off[sl(1, n) + (2 * d,)] = np.where(both, a, 0.0)
             # boundary faces: outflow = alpha * X
             P0, P1 = Phi[sl(0, 1)], Phi[sl(n - 1, n)]
             diag[sl(0, 1)] += np.where(P0 > fl, -Jc[sl(0, 1)] / np.where(P0 > fl, P0, 1.0), 0.0)
             diag[sl(n - 1, n)] += np.where(P1 > fl, Jc[sl(n, n + 1)] / np.where(P1 > fl, P1, 1.0), 0.0)
         # cells without a positive flux integral (or whose boundary inflow makes the diagonal non-positive) are left alone
         active = pos & (diag > 0)
-        safe = np.where(active, Phi, 1.0)
-        nsf = np.where(active, r["Nsf"] / safe, 0.0)
-        sca = np.where(active[None], r["Sca"] / safe[None], 0.0)            # [gt, gf] normalised by Phi[gf]
+        # entries that are not rows of the coarse system keep their flux integral (frozen) and still feed the fission and
+        # scattering sources of the rows that are -- dropping them would move the fixed point
+        fed = np.abs(Phi) > fl
+        safe = np.where(fed, Phi, 1.0)
+        nsf = np.where(fed, r["Nsf"] / safe, 0.0)
+        sca = np.where(fed[None], r["Sca"] / safe[None], 0.0)               # [gt, gf] normalised by Phi[gf]
         for g in range(ng):
             sca[g, g] = 0.0
         Ptot = r["Nsf"].sum(axis=0)
@@ -222,25 +234,38 @@ class CMFDOracle:
         return M, F
 
     def solve_coarse(self, co, X0, k0, tol=1e-12, max_it=5000):
-        """Fundamental mode of M X = (1/k) F X by power iteration with a sparse LU of M (tight: this is the checker)."""
+        """The coarse problem by fixed-point iteration with a sparse LU of M (tight: this is the independent checker).
+        Entries that are not rows of the system are frozen at their flux integral and feed the sources of the rows that are, which
+        makes the problem inhomogeneous: find (X, k) with the frozen entries held and the TOTAL production held at its initial
+        value (only the rows of the system are renormalised); k = fission source entering the rows / their net loss."""
         M, F = self.matrices(co)
         active = co["active"].ravel()
-        # cells without a positive flux integral are taken out of the system: identity row, zero source, X = 0
         keep = sp.diags(active.astype(float)).tocsc()
-        M = (keep @ M @ keep + sp.diags((~active).astype(float))).tocsc()
-        F = (keep @ F @ keep).tocsc()
-        lu = spla.splu(M)
-        X = np.where(active, X0.ravel().copy(), 0.0)
+        frozen = (~active).astype(float)
+        Ma = (keep @ M).tocsc()                     # rows of the system, all columns (frozen columns = sources)
+        Fa = (keep @ F).tocsc()
+        lu = spla.splu((Ma + sp.diags(frozen)).tocsc())
+        X = X0.ravel().copy()
+        Xf = frozen * X
         k = float(k0)
         nsf = co["nsf"].ravel()
-        P = float(nsf @ X)
+        P0 = float(nsf @ X)
+        Pf = float(nsf @ Xf)
+        if not (P0 - Pf > 0):
+            return None, k
         for it in range(max_it):
-            Xn = lu.solve(F @ X / k)
-            Pn = float(nsf @ Xn)
-            kn = k * Pn / P
-            Xn *= P / Pn
+            Xn = lu.solve(Fa @ X / k + Xf)
+            Pa = float(nsf @ Xn) - Pf
+            if not (Pa > 0):
+                return None, k
+            Xn = np.where(active, Xn * ((P0 - Pf) / Pa), Xn)
+            loss = float((Ma @ Xn).sum())
+            srcn = float((Fa @ Xn).sum())
+            if not (loss > 0 and srcn > 0):
+                return None, k
+            k = srcn / loss
             err = np.abs(Xn - X).sum() / np.abs(Xn).sum()
-            X, k = Xn, kn
+            X = Xn
             if err < tol:
                 break
         self.last["coarse_iterations"] = it + 1
@@ -276,12 +301,19 @@ class CMFDOracle:
                         q[g] += sca[g, gp] * X[gp]
             return q
 
-        X = np.where(active, X0, 0.0)
+        X = X0.copy()
         k = float(k0)
         sweeps = 0
-        P0 = None
+        # frozen entries (not rows of the system) are held; the TOTAL production is held at its initial value P0
+        Pf = float(np.where(active, 0.0, nsf * X).sum())
+        P0 = float((nsf * X).sum())
+        if not (P0 - Pf > 0):
+            self.last["coarse_sweeps"] = 0
+            return None, k
+        scale = 1.0
         while sweeps < max_sweeps:
-            Xn = np.where(active, (1.0 - self.theta) * X + self.theta * (src(X, k) + nb(X)) / dsafe, 0.0)
+            Xn = np.where(active, scale * ((1.0 - self.theta) * X + self.theta * (src(X, k) + nb(X)) / dsafe), X)
+            scale = 1.0
             sweeps += 1
             if sweeps % check == 0:
                 ch = np.abs(Xn - X).sum() / np.abs(Xn).sum()
@@ -291,14 +323,12 @@ class CMFDOracle:
                     for gp in range(ng):
                         if gp != g:
                             loss -= float(np.where(active[g], sca[g, gp] * Xn[gp], 0.0).sum())
-                if not (P > 0 and loss > 0):
+                srcn = float(np.where(active, chi * (nsf * Xn).sum(axis=0)[None], 0.0).sum())
+                if not (P - Pf > 0 and loss > 0 and srcn > 0):
                     self.last["coarse_sweeps"] = sweeps
                     return None, k
-                # fission source entering the rows that are solved (= P when sum_g chi = 1 and every row is active)
-                k = float(np.where(active, chi * (nsf * Xn).sum(axis=0)[None], 0.0).sum()) / loss
-                if P0 is None:
-                    P0 = P
-                Xn = Xn * (P0 / P)
+                k = srcn / loss                    # fission source entering the rows that are solved / their net loss
+                scale = (P0 - Pf) / (P - Pf)       # applied by the next sweep, to the rows of the system only
                 if ch < tol:
                     X = Xn
                     break
@@ -327,13 +357,18 @@ class CMFDOracle:
         ok = (X0 > self.phi_floor) & (X > 0)
         om = self.relaxation
         A = float(np.where(ok, X / np.where(ok, X0, 1.0) * r["Prf"], 0.0).sum())
-        B_alone = float(np.where(ok, 0.0, r["Prf"]).sum())
+        B_other = float(np.where(ok, 0.0, r["Prf"]).sum())
         B_all = float(r["Prf"].sum())
-        s = ((kc / keff) * prod_old - (1.0 - om) * B_all - om * B_alone) / (om * A) if A > 0 else -1.0
-        if not (s > 0):
+        # cells outside the coarse system (void cells, negative cell fluxes) follow the mean ratio of the corrected cells:
+        # left alone, their amplitude would drift against the rest and the accelerated iteration would get a fixed point of its own
+        sx0 = float(np.where(ok, X0, 0.0).sum())
+        rbar = float(np.where(ok, X, 0.0).sum()) / sx0 if sx0 > 0 else 1.0
+        den = om * (A + rbar * B_other)
+        s = ((kc / keff) * prod_old - (1.0 - om) * B_all) / den if den > 0 else -1.0
+        if not (s > 0 and rbar > 0):
             self.last.update(k_coarse=kc, skipped=True)
             return Phi_all.copy()
-        ratio = np.where(ok, s * X / np.where(ok, X0, 1.0), 1.0)
+        ratio = np.where(ok, s * X / np.where(ok, X0, 1.0), s * rbar)
         ratio = om * ratio + (1.0 - om)
         self.last.update(k_coarse=kc, ratio_min=float(ratio.min()), ratio_max=float(ratio.max()))
         out = Phi_all.copy()
