@@ -142,7 +142,7 @@ def test_cmfd_on_the_3d_product_path():
     assert ch[2] and cm[2]
     assert cm[4] == 3 and cm[5] == 32 ** 3 and cm[3] == 0
     assert abs(cm[0] - ch[0]) < 5e-6
-    assert cm[1] < 0.6 * ch[1] and cm[6] < ch[6]
+    assert cm[1] < 0.75 * ch[1] and cm[6] < ch[6]
 
 
 def test_automatic_coarsening_above_64_cells_per_axis():
