@@ -17,15 +17,16 @@
 //   3. CmfdCoefOp   per (group, coarse cell): the coarse operator. Face F between L and R: J_F = a_F X_L - b_F X_R with
 //      a_F = D~_F / V_L (+ delta / X_L if delta > 0), b_F = D~_F / V_R (+ -delta / X_R if delta < 0), delta = the part of the
 //      fine current the finite-difference coupling D~_F does not explain. The correction sits on the upstream side, so
-//      a_F, b_F > 0 for ANY fine iterate: the coarse matrix is a column-diagonally-dominant M-matrix and plain Jacobi sweeps
+//      a_F, b_F > 0 for ANY fine iterate: the coarse matrix is a column-diagonally-dominant M-matrix and Jacobi sweeps
 //      converge. Boundary faces: J_F = alpha_F X_I. Entries whose flux integral is not positive ("void" cells with Sigma_r = 1e15,
 //      negative cell fluxes of RT0 on very thick cells) cannot be rows of an M-matrix: they are frozen at their flux integral,
 //      keep feeding the fission / scattering sources of the rows that are solved, the faces towards them are closed like
 //      boundary faces, and they follow the mean flux ratio -- so the fixed point stays the fine eigenpair.
-//   4. CmfdSweepOp  Jacobi sweeps of the coarse multigroup eigenvalue problem, all groups in one launch, no reduction; every
-//      `check` sweeps CmfdCheckOp (one deterministic grid reduction) gives k = production / net loss and the l1 change of the
-//      last sweep. The coarse problem is tiny (<= 64^3 cells by default): the solve is launch-bound by design and costs tens
-//      of milliseconds against seconds for the fine group sweep.
+//   4. CmfdSweepOp  weighted Jacobi sweeps (CmfdParams::theta) of the coarse multigroup eigenvalue problem, all groups in one
+//      launch, no reduction; every `check` sweeps CmfdCheckOp (one deterministic grid reduction) gives k = fission source entering
+//      the rows / their net loss, the l1 change of the last sweep, and the factor that holds the total production (rows of the
+//      system only; the frozen entries are held). The coarse problem is tiny (<= 64^3 cells by default): the solve is
+//      launch-bound by design -- measured 0.13 s per correction against seconds for the fine group sweep.
 //   5. CmfdRatioOp / CmfdProlongOp: phi <- phi * (omega * X_new / X_old + 1 - omega) per coarse cell and group, all Legendre
 //      modes, the coarse eigenvector scaled so that the reference's own update k <- k * prod_new / prod_old yields the coarse k.
 //
