@@ -15,7 +15,8 @@ bracketed by barrier + synchronize -- by CUDA events on the library's stream, ma
 `roofline` follows SURVEY 8(d): (88 + 16/n_loc) algorithmic bytes per DOF per CG iteration over the measured time of one
 CG iteration (nf_time_kernels, CUDA events, operands >> L2). `time_to_keff` is BASELINE.json's other half of the metric:
 wall time of a converged solve (script tolerances 1e-5 / 1e-4) on the SAME mesh at this N, from the flat flux and from a
-coarse-mesh initial guess; `parity_vs_n1` (N > 1) compares a converged z-slab solve of a reduced mesh with uneven slabs
+coarse-mesh initial guess (Chebyshev, the reference's accelerator) and, on one GPU, from the coarse-mesh guess with the CMFD
+acceleration (SolveKeff(use_cmfd=True)); `parity_vs_n1` (N > 1) compares a converged z-slab solve of a reduced mesh with uneven slabs
 against the single-GPU solve of the same mesh. Optional sections are skipped (and say so) when the wall-clock budget
 (NEUTFEM_BENCH_BUDGET_S, default 760 s) would be exceeded.
 
