@@ -307,3 +307,31 @@ def test_rtk_p0_diffuses_four_times_faster():
         deff[(K, M)] = (0.03 / k - 0.02) / (np.pi / L) ** 2
     assert abs(deff[(1, 1)] / deff[(0, 0)] - 1.0) < 0.01
     assert 3.8 < deff[(1, 0)] / deff[(0, 0)] < 4.5
+
+
+GOLDEN_CASES = [   # must match tools/make_golden_cmfd.py
+    ("c2d_rt1p1", 211, 2, (10, 7, 1), 1, 1, (2, 3, 1), "mixed"),
+    ("c3d_rt0p0", 212, 3, (6, 5, 4), 0, 0, (2, 2, 2), "all"),
+    ("c3d_rt1p1", 213, 3, (8, 5, 4), 1, 1, (3, 2, 2), "all"),
+    ("c3d_rt2p1", 214, 3, (4, 4, 3), 2, 1, (1, 1, 1), "all"),
+]
+
+
+@pytest.mark.parametrize("name,seed,dim,n,rt,pp,fac,bc", GOLDEN_CASES)
+def test_golden_cmfd_vectors(name, seed, dim, n, rt, pp, fac, bc):
+    """tests/golden/cmfd_v1.npz (tools/make_golden_cmfd.py): the oracle still reproduces it (guards the checker against drift) and
+    so does the library's CMFD source; the GPU test compares the CUDA path with the same file without a CPU solve."""
+    import os
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cmfd_v1.npz"))
+    p = random_problem(seed, dim, n, ng=2, bc=bc)
+    o = make_oracle(p, rt, pp)
+    phi, k, prod_old = G[name + "_phi"], float(G[name + "_k"]), float(G[name + "_prod_old"])
+    c = CMFDOracle(o, fac)
+    ref = c.correct(phi, k, prod_old, solver="lu")
+    assert "skipped" not in c.last
+    assert abs(c.last["k_coarse"] - float(G[name + "_k_coarse"])) < 1e-11 * abs(c.last["k_coarse"])
+    assert np.linalg.norm(ref - G[name + "_corrected"]) < 1e-11 * np.linalg.norm(ref)
+    s = ShimCMFD(o, fac)
+    out = s.correct(phi, k, prod_old, tol=1e-12)
+    assert s.status == 0 and abs(s.k - float(G[name + "_k_coarse"])) < 1e-9 * abs(s.k)
+    assert np.linalg.norm(out - G[name + "_corrected"]) < 1e-8 * np.linalg.norm(out)

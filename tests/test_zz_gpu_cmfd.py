@@ -59,6 +59,41 @@ def test_one_correction_matches_oracle(dim, n, rt, pp, fac, bc):
     assert abs(k * prod_new / prod_old - kc) < 1e-9 * kc
 
 
+GOLDEN_CASES = [   # must match tools/make_golden_cmfd.py
+    ("c2d_rt1p1", 211, 2, (10, 7, 1), 1, 1, (2, 3, 1), "mixed"),
+    ("c3d_rt0p0", 212, 3, (6, 5, 4), 0, 0, (2, 2, 2), "all"),
+    ("c3d_rt1p1", 213, 3, (8, 5, 4), 1, 1, (3, 2, 2), "all"),
+    ("c3d_rt2p1", 214, 3, (4, 4, 3), 2, 1, (1, 1, 1), "all"),
+]
+
+
+@pytest.mark.parametrize("name,seed,dim,n,rt,pp,fac,bc", GOLDEN_CASES)
+def test_golden_cmfd_vectors(name, seed, dim, n, rt, pp, fac, bc):
+    """tests/golden/cmfd_v1.npz (made by tools/make_golden_cmfd.py from the CPU oracle): one correction and a converged CMFD solve
+    of the CUDA path against the committed vectors -- no CPU solve at run time."""
+    import os
+    from neutfem_b200 import cabi
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cmfd_v1.npz"))
+    p = random_problem(seed, dim, n, ng=2, bc=bc)
+    c = make_gpu(p, rt, pp)
+    _set_factors(c, fac)
+    c.set_option("cmfd_tol", 1e-12)
+    c.set_flux(G[name + "_phi"])
+    kc, sweeps, status = c.cmfd_step(float(G[name + "_k"]), float(G[name + "_prod_old"]))
+    out = c.get_flux()
+    assert status == 0 and abs(kc - float(G[name + "_k_coarse"])) < 1e-9 * abs(kc)
+    assert relerr(out, G[name + "_corrected"]) < 1e-8
+    c.set_option("cmfd_tol", 1e-10)
+    c.set_solver(tol_keff=1e-9, tol_flux=1e-8, max_outer=300, max_inner=4000, mode=cabi.MODE_PARITY)
+    c.reset_flux()
+    k, st = c.solve_keff(False, cabi.ACCEL_CMFD)
+    phi = c.get_flux()
+    c.close()
+    assert st["converged"] and abs(k - float(G[name + "_keff"])) < 2e-8
+    assert abs(st["outer_iterations"] - int(G[name + "_outer"])) <= 1
+    assert relerr(phi, G[name + "_flux"]) < 1e-6
+
+
 @pytest.mark.parametrize("dim,n,rt,pp,fac,bc", [(2, (12, 10, 1), 1, 1, (2, 2, 1), "mixed"), (3, (6, 5, 4), 1, 0, (2, 2, 2), "all"),
                                                  (3, (8, 6, 5), 1, 1, (2, 2, 1), "all")])
 def test_solve_keff_with_cmfd_matches_oracle(dim, n, rt, pp, fac, bc):
