@@ -315,7 +315,7 @@ def measured_traffic(n_phi, path):
     return float(d["dram_bytes_per_dof_per_cg_iteration"]) * n_phi, src
 
 
-def coarse_initial_flux(args, cabi, bm, mesh, z_range, local_rank):
+def coarse_initial_flux(args, cabi, bm, mesh, z_range, local_rank, accel=None):
     """Coarse-mesh initial guess in the spirit of NeutFEM::SolveCoarse (src/NeutFEM.cpp:2380-2611): RT0-P0 on the mesh coarsened
     by (2,2,2), tolerances x10, solved redundantly on every rank's GPU (13 M cells: negligible), piecewise-constant prolongation
     into DOF 0 of this rank's planes. Returns (k_coarse, flux [ng * n_phi_local] in reference numbering, seconds)."""
@@ -329,7 +329,7 @@ def coarse_initial_flux(args, cabi, bm, mesh, z_range, local_rank):
                  mode=cabi.MODE_FAST if args.mode == "fast" else cabi.MODE_PARITY)
     c.upload_xs(D=pc.D, SigR=pc.SigR, NSF=pc.NSF, Chi=pc.Chi, SigS=pc.SigS)
     c.build()
-    kc, _ = c.solve_keff(False)
+    kc, _ = c.solve_keff(False) if accel is None else c.solve_keff(False, accel)
     fc = c.get_flux().reshape(pc.ng, cm[2], cm[1], cm[0])
     c.close()
     z0, z1 = z_range
@@ -492,11 +492,13 @@ def run_ours(args):
             extra = {}
             k0 = -1.0
             if tag.endswith("coarse_start"):
-                kc, f0, tc = coarse_initial_flux(args, cabi, bm, mesh, (z0, z1), local_rank)
+                # the CMFD run also accelerates its coarse-mesh solve with CMFD
+                kc, f0, tc = coarse_initial_flux(args, cabi, bm, mesh, (z0, z1), local_rank, cabi.ACCEL_CMFD if cmfd else None)
                 ctx.set_flux(f0)
                 del f0
                 k0 = kc
-                extra = {"coarse": {"mesh": [m // 2 for m in mesh], "order": "RT0-P0", "keff": kc, "seconds": tc}}
+                extra = {"coarse": {"mesh": [m // 2 for m in mesh], "order": "RT0-P0", "keff": kc, "seconds": tc,
+                                    "accelerator": "cmfd" if cmfd else "chebyshev"}}
             ctx.set_solver(max_outer=min(cap, 400), **conv)
             kc2, st2 = ctx.solve_keff(False, cabi.ACCEL_CMFD if cmfd else cabi.ACCEL_CHEBYSHEV, k0)
             fl = ctx.get_flux()
