@@ -87,7 +87,8 @@ struct CmfdParams {
 };
 
 struct CmfdResult {
-    int status = 0;              // 0 applied, 1 skipped (no positive production / loss), 2 applied without reaching tol
+    int status = 0;              // 0 applied, 1 skipped (no positive production / loss, or sweeps exhausted with a change above
+                                 // 1e-4), 2 applied without reaching tol (change below 1e-4)
     int sweeps = 0;
     double k = 0.0, change = 0.0, ratio_scale = 0.0;   // coarse eigenvalue, last l1 change, scale of the flux ratio
 };
@@ -477,6 +478,8 @@ int cmfd_correct(Backend &be, CmfdData &d, const CmfdLine *lines, double keff, d
         converged = r.change < prm.tol;
     }
     r.k = k;
+    // sweeps exhausted far from convergence (a coarse operator on which the Jacobi sweeps do not contract): leave the flux alone
+    if (r.status != 1 && !converged && !(r.change < 1e-4)) r.status = 1;
     if (r.status != 1) {
         if (!converged) r.status = 2;
         // scale s of the coarse eigenvector such that the production count of the corrected flux is (k_coarse / keff) prod_old,

@@ -310,7 +310,7 @@ class CMFDOracle:
         if not (P0 - Pf > 0):
             self.last["coarse_sweeps"] = 0
             return None, k
-        scale = 1.0
+        scale, ch = 1.0, 1.0
         while sweeps < max_sweeps:
             Xn = np.where(active, scale * ((1.0 - self.theta) * X + self.theta * (src(X, k) + nb(X)) / dsafe), X)
             scale = 1.0
@@ -334,6 +334,8 @@ class CMFDOracle:
                     break
             X = Xn
         self.last["coarse_sweeps"] = sweeps
+        if sweeps >= max_sweeps and not (ch < 1e-4):      # sweeps exhausted far from convergence: leave the flux alone
+            return None, k
         return X, k
 
     # ---- one CMFD step ---------------------------------------------------------------------------------------------------
