@@ -300,9 +300,11 @@ struct CmfdCoefOp {
         // flux in a thick reflector cell scatters a negative source into the thermal group of that cell).
         const bool fed = fabs(PI) > fl;
         d.nsf[t] = fed ? d.Nsf[t] / PI : 0.0;
-        double Ptot = 0.0;
-        for (int g2 = 0; g2 < g.ng; ++g2) Ptot += d.Nsf[(size_t)g2 * g.NC + I];
-        d.chi[t] = (Ptot > 0.0) ? d.ChiP[t] / Ptot : 0.0;
+        // fission spectrum of the cell = chi-weighted production / production; the production of a cell holding negative fluxes
+        // may be negative -- the ratio still reproduces the fine source -- only a (near-)cancelled total is left out
+        double Ptot = 0.0, Pabs = 0.0;
+        for (int g2 = 0; g2 < g.ng; ++g2) { const double v = d.Nsf[(size_t)g2 * g.NC + I]; Ptot += v; Pabs += fabs(v); }
+        d.chi[t] = (fabs(Ptot) > 1e-12 * Pabs && Pabs > 0.0) ? d.ChiP[t] / Ptot : 0.0;
         for (int gt = 0; gt < g.ng; ++gt) {
             const size_t q = ((size_t)gt * g.ng + gr) * g.NC + I;
             d.sca[q] = (fed && gt != gr) ? d.Sca[q] / PI : 0.0;

@@ -194,8 +194,12 @@ class CMFDOracle:
         sca = np.where(fed[None], r["Sca"] / safe[None], 0.0)               # [gt, gf] normalised by Phi[gf]
         for g in range(ng):
             sca[g, g] = 0.0
+        # fission spectrum of the cell = chi-weighted production / production; the production of a cell holding negative fluxes
+        # may be negative -- the ratio still reproduces the fine source -- only a (near-)cancelled total is left out
         Ptot = r["Nsf"].sum(axis=0)
-        chi = np.where(Ptot[None] > 0, r["ChiP"] / np.where(Ptot > 0, Ptot, 1.0)[None], 0.0)
+        Pabs = np.abs(r["Nsf"]).sum(axis=0)
+        okp = (np.abs(Ptot) > 1e-12 * Pabs) & (Pabs > 0)
+        chi = np.where(okp[None], r["ChiP"] / np.where(okp, Ptot, 1.0)[None], 0.0)
         diag = np.where(active, diag, 1.0)
         off = np.where(active[..., None], off, 0.0)
         return dict(diag=diag, off=off, nsf=nsf, sca=sca, chi=chi, active=active)
@@ -344,6 +348,7 @@ class CMFDOracle:
         production of the iterate the sweep started from (reference variable of the same name, NeutFEM.cpp:1703)."""
         o, f = self.o, self.f
         ng, nl = o.ng, f.nphi_loc
+        self.last = {}
         r = self.restrict(Phi_all)
         co = self.coefficients(r)
         X0 = r["Phi"]
