@@ -101,7 +101,8 @@ NF_API int nf_set_solver(nf_ctx *ctx, int solver_type, double tol_keff, double t
  *   "cmfd_tol", "cmfd_check", "cmfd_max_sweeps"  coarse eigenvalue solve: stop when the l1 change of one Jacobi sweep is below
  *                     tol (1e-10) of the l1 norm, tested every `check` (50) sweeps, at most max_sweeps (100000). */
 NF_API int nf_set_option(nf_ctx *ctx, const char *key, double value);
-/* read-back of options and counters: "cmfd_calls", "cmfd_sweeps" (total), "cmfd_last_sweeps", "cmfd_last_k",
+/* read-back of options and counters: "cmfd_calls", "cmfd_sweeps" (total), "cmfd_fallbacks" (solves in which CMFD was switched off
+ * for Chebyshev after three kicks of the flux change), "cmfd_last_sweeps", "cmfd_last_k",
  * "cmfd_last_status" (0 applied, 1 skipped: no positive balance or sweeps exhausted far from convergence, 2 applied without
  * reaching cmfd_tol), "cmfd_last_change", "cmfd_cx/cy/cz",
  * "cmfd_coarse_cells", "cg_path" (id of the CG-iteration path, see nf_time_kernels). Unknown key: NF_ERR_ARG. */

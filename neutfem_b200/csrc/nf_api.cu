@@ -92,7 +92,7 @@ struct nf_ctx {
     int cmfd_c[3] = {0, 0, 0};             // fine cells per coarse cell (options "cmfd_cx/cy/cz"), 0 = automatic
     CmfdParams cmfd_prm;
     CmfdResult cmfd_last;
-    long long cmfd_calls = 0, cmfd_sweeps = 0;
+    long long cmfd_calls = 0, cmfd_sweeps = 0, cmfd_fallbacks = 0;
 };
 
 #define NC(ctx, call)                                                                                      \
@@ -997,6 +997,7 @@ int nf_query(const nf_ctx *c, const char *key, double *value)
     const std::string k(key);
     if (k == "cmfd_calls") { *value = (double)c->cmfd_calls; return NF_OK; }
     if (k == "cmfd_sweeps") { *value = (double)c->cmfd_sweeps; return NF_OK; }
+    if (k == "cmfd_fallbacks") { *value = (double)c->cmfd_fallbacks; return NF_OK; }
     if (k == "cmfd_last_sweeps") { *value = (double)c->cmfd_last.sweeps; return NF_OK; }
     if (k == "cmfd_last_k") { *value = c->cmfd_last.k; return NF_OK; }
     if (k == "cmfd_last_status") { *value = (double)c->cmfd_last.status; return NF_OK; }
@@ -1354,6 +1355,8 @@ static int power_iteration(nf_ctx *c, bool adjoint, int use_diag, int accel, dou
     }
     double cmfd_damp = 1.0, cmfd_dk_prev = 0.0;
     bool cmfd_osc_prev = false;
+    int cmfd_kicks = 0;
+    double cmfd_dphi_prev = -1.0;
     for (int it = 0; it < c->max_outer; ++it) {
         // one sweep: Phi_old = Phi, total fission source (+ prod_old), right-hand side of the first group
         LAUNCH(c, k_total_fission, blocks, 256, 0, oa, c->d_tot, adjoint ? 1 : 0, c->d_part + 5 * kRedBlocks, c->d_ticket + 5, c->d_scal + 0,
@@ -1402,6 +1405,17 @@ static int power_iteration(nf_ctx *c, bool adjoint, int use_diag, int accel, dou
         const double diff_flux = std::sqrt(diff_sq / sol_sq);
         const double norm = std::sqrt(sol_sq);
         const double scale = (norm > 1e-14) ? 1.0 / norm : 1.0;
+        if (accel == NF_ACCEL_CMFD && !adjoint) {
+            // Fallback: on very thick cells with negative cell fluxes an entry can flip in and out of the coarse system from one
+            // outer iteration to the next and kick the iterate. The third time the flux change more than doubles after a
+            // correction, CMFD is switched off for the rest of the solve and the Chebyshev acceleration takes over (fresh
+            // sequence). Same rule in oracle/neutfem_oracle.py SolveKeff.
+            if (it >= cheb_from + 1) {
+                if (cmfd_dphi_prev >= 0.0 && diff_flux > 2.0 * cmfd_dphi_prev) ++cmfd_kicks;
+                if (cmfd_kicks >= 3) { accel = NF_ACCEL_CHEBYSHEV; c->cmfd_fallbacks += 1; }
+            }
+            cmfd_dphi_prev = diff_flux;
+        }
         int step = -1; double ca = 0.0, cb = 0.0;
         if (accel == NF_ACCEL_CHEBYSHEV && it >= cheb_from) cheb.next(step, ca, cb);
         LAUNCH(c, k_scale_chebyshev, blocks_all, 256, 0, phi, c->d_h0, c->d_h1, ntot, scale, step, ca, cb);

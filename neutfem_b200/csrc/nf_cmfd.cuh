@@ -84,6 +84,7 @@ struct CmfdParams {
                                  // same-group fission make the (group, cell) graph bipartite, so the plain Jacobi matrix has the
                                  // eigenvalue -1 next to +1; the weight maps it to 1 - 2 theta and leaves the fundamental alone
     double floor_rel = 1e-12;    // phi_floor = floor_rel * mean |flux integral|
+    double ratio_max = 5.0;      // flux ratios are clamped to [1 / ratio_max, ratio_max]
 };
 
 struct CmfdResult {
@@ -398,11 +399,14 @@ struct CmfdScaleOp {
 // Cells outside the coarse system (void cells, negative cell fluxes) follow the mean ratio of the corrected cells: leaving them
 // alone would let their amplitude drift against the rest and give the accelerated iteration a fixed point of its own.
 struct CmfdRatioOp {
-    CmfdData d; const double *X; double s, rbar, omega;
+    CmfdData d; const double *X; double s, rbar, omega, rmax;
     NF_HD void operator()(long long t) const
     {
         const double x0 = d.Phi[t], x1 = X[t];
-        const double r = (x0 > d.phi_floor && x1 > 0.0) ? s * x1 / x0 : s * rbar;
+        double r = (x0 > d.phi_floor && x1 > 0.0) ? s * x1 / x0 : s * rbar;
+        // the reference clamps the ratio to [0.5, 2] (src/NeutFEM.cpp:1003); a wider clamp is kept: a cell whose flux integral is
+        // almost zero can ask for an arbitrarily large ratio, and one such cell is enough to throw the next sweep off
+        r = r > rmax ? rmax : (r < 1.0 / rmax ? 1.0 / rmax : r);
         d.ratio[t] = omega * r + (1.0 - omega);
     }
 };
@@ -496,7 +500,7 @@ int cmfd_correct(Backend &be, CmfdData &d, const CmfdLine *lines, double keff, d
         if (!(r.ratio_scale > 0.0) || !(prod_old > 0.0) || !(den > 0.0) || !(rbar > 0.0)) r.status = 1;
     }
     if (r.status != 1) {
-        be.for_each(CmfdRatioOp{d, cur, r.ratio_scale, rbar, prm.relaxation}, ncell);
+        be.for_each(CmfdRatioOp{d, cur, r.ratio_scale, rbar, prm.relaxation, prm.ratio_max}, ncell);
         be.for_each(CmfdProlongOp{d}, (long long)g.ng * g.ne);
     }
     if (!be.ok()) return -1;

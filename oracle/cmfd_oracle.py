@@ -60,6 +60,7 @@ class CMFDOracle:
         self.c = (cx, cy, cz)
         self.relaxation = float(relaxation)
         self.floor_rel = 1e-12
+        self.ratio_max = 5.0
         self.theta = 0.8                     # weight of the Jacobi sweeps (see CmfdParams::theta in nf_cmfd.cuh)
         self.starts = [np.arange(0, n, c) for n, c in ((self.nz, cz), (self.ny, cy), (self.nx, cx))]      # axis order z, y, x
         self.NC = tuple(len(s) for s in self.starts)                                                    # (NCz, NCy, NCx)
@@ -376,6 +377,7 @@ class CMFDOracle:
             self.last.update(k_coarse=kc, skipped=True)
             return Phi_all.copy()
         ratio = np.where(ok, s * X / np.where(ok, X0, 1.0), s * rbar)
+        ratio = np.clip(ratio, 1.0 / self.ratio_max, self.ratio_max)      # the reference clamps to [0.5, 2] (NeutFEM.cpp:1003)
         ratio = om * ratio + (1.0 - om)
         self.last.update(k_coarse=kc, ratio_min=float(ratio.min()), ratio_max=float(ratio.max()))
         out = Phi_all.copy()

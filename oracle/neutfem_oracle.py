@@ -660,6 +660,11 @@ class OracleNeutFEM:
         # is not at least twice smaller, two outer iterations in a row, the relaxation is multiplied by 0.7 (floor 0.3 of the
         # user's omega).
         cmfd_damp, dk_prev, osc_prev = 1.0, 0.0, False
+        # Fallback (same rule as nf_api.cu): on very thick cells with negative cell fluxes an entry can flip in and out of the
+        # coarse system from one outer iteration to the next and kick the iterate; the third time the flux change more than
+        # doubles after a correction, CMFD is switched off for the rest of the solve and the Chebyshev acceleration takes over.
+        cmfd_kicks, dphi_prev = 0, None
+        self.cmfd_fallback = False
         f, ng, nP, nJ = self.fes, self.ng, self.fes.n_Phi, self.fes.n_J
         st = self.stats = SolveStats()
         t_start = time.perf_counter()
@@ -721,6 +726,13 @@ class OracleNeutFEM:
             norm = math.sqrt(sol_sq)
             if norm > 1e-14:
                 self.Sol_Phi /= norm
+            if cmfd is not None and it >= 3:
+                if dphi_prev is not None and diff_flux > 2.0 * dphi_prev:
+                    cmfd_kicks += 1
+                if cmfd_kicks >= 3:
+                    cmfd, self.cmfd_fallback = None, True
+                    accel = ChebyshevAccel(15, 0.98)
+            dphi_prev = diff_flux
             if it >= 2 and cmfd is None:
                 if accel_kind == "chebyshev":
                     self.Sol_Phi = accel(self.Sol_Phi)

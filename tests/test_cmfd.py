@@ -68,7 +68,9 @@ def test_library_source_matches_oracle_step(dim, n, rt, pp, fac, bc):
     # the correction is what makes the outer iteration's k update land on the coarse eigenvalue
     nP = o.fes.n_Phi
     prod_new = float(sum((o.M_fiss[g] @ out[g * nP:(g + 1) * nP]).sum() for g in range(o.ng)))
-    assert abs(k * prod_new / prod_old - s.k) < 1e-10 * s.k
+    ratio = s.array("ratio")
+    if ratio.max() < 5.0 and ratio.min() > 0.2:          # (exactly so unless the clamp of the ratio was active)
+        assert abs(k * prod_new / prod_old - s.k) < 1e-10 * s.k
 
 
 def test_mode0_balance_rows_have_two_entries_per_direction():
@@ -261,6 +263,25 @@ def test_negative_cell_fluxes_do_not_move_the_fixed_point():
         assert o2.stats.converged and o2.stats.outer_iterations < 0.5 * o.stats.outer_iterations
         assert abs(k - k_ref) < 1e-9
         assert np.linalg.norm(o2.Sol_Phi - phi_ref) < 1e-6 * np.linalg.norm(phi_ref)
+
+
+def test_fallback_to_chebyshev_on_a_mesh_where_cmfd_keeps_kicking():
+    """3-D RT0-P0 on 5 - 14 cm cells with random cross sections (found by a randomized sweep): negative cell fluxes flip entries
+    in and out of the coarse system and every flip kicks the iterate; without the fallback the accelerated iteration never
+    converges (400 outer iterations), with it the third kick hands over to Chebyshev and the solve ends at the unaccelerated k."""
+    p = random_problem(692, 3, (10, 5, 4), ng=1, bc="mixed")
+    for key in ("xb", "yb", "zb"):
+        p[key] = p[key] * 8.0
+    res = {}
+    for mode in ("cheb", "cmfd"):
+        o = make_oracle(p, 0, 0)
+        o.set_tol(1e-8, 1e-7, 1e-5, 400, 4000)
+        k = o.SolveKeff() if mode == "cheb" else o.SolveKeff(use_cmfd=True, cmfd_factors=(1, 2, 2), cmfd_impl=ShimCMFD(o, (1, 2, 2)))
+        assert o.stats.converged
+        res[mode] = (k, o.stats.outer_iterations, getattr(o, "cmfd_fallback", False))
+    assert res["cmfd"][2] is True
+    assert abs(res["cmfd"][0] - res["cheb"][0]) < 1e-6
+    assert res["cmfd"][1] < 1.5 * res["cheb"][1]
 
 
 def test_diagonal_path_keeps_chebyshev():
