@@ -1355,7 +1355,7 @@ static int power_iteration(nf_ctx *c, bool adjoint, int use_diag, int accel, dou
     }
     double cmfd_damp = 1.0, cmfd_dk_prev = 0.0;
     bool cmfd_osc_prev = false;
-    int cmfd_kicks = 0;
+    int cmfd_kicks = 0, cmfd_skips = 0;
     double cmfd_dphi_prev = -1.0;
     for (int it = 0; it < c->max_outer; ++it) {
         // one sweep: Phi_old = Phi, total fission source (+ prod_old), right-hand side of the first group
@@ -1376,6 +1376,7 @@ static int power_iteration(nf_ctx *c, bool adjoint, int use_diag, int accel, dou
             CU(c, cudaStreamSynchronize(c->stream));
             int r = cmfd_apply(c, phi, keff, c->h_scal[60], cmfd_damp);
             if (r) return r;
+            cmfd_skips = (c->cmfd_last.status == 1) ? cmfd_skips + 1 : 0;
         }
         LAUNCH(c, k_outer_post, blocks, 256, 0, oa, c->d_old, adjoint ? 1 : 0, c->d_part + 5 * kRedBlocks, c->d_ticket + 5, c->d_scal + 1);
         { int r = allreduce_sum(c, c->d_scal, 4); if (r) return r; }
@@ -1412,7 +1413,8 @@ static int power_iteration(nf_ctx *c, bool adjoint, int use_diag, int accel, dou
             // sequence). Same rule in oracle/neutfem_oracle.py SolveKeff.
             if (it >= cheb_from + 1) {
                 if (cmfd_dphi_prev >= 0.0 && diff_flux > 2.0 * cmfd_dphi_prev) ++cmfd_kicks;
-                if (cmfd_kicks >= 3) { accel = NF_ACCEL_CHEBYSHEV; c->cmfd_fallbacks += 1; }
+                // ... or three corrections in a row had to be skipped (no positive coarse balance)
+                if (cmfd_kicks >= 3 || cmfd_skips >= 3) { accel = NF_ACCEL_CHEBYSHEV; c->cmfd_fallbacks += 1; }
             }
             cmfd_dphi_prev = diff_flux;
         }

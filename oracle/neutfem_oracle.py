@@ -663,7 +663,7 @@ class OracleNeutFEM:
         # Fallback (same rule as nf_api.cu): on very thick cells with negative cell fluxes an entry can flip in and out of the
         # coarse system from one outer iteration to the next and kick the iterate; the third time the flux change more than
         # doubles after a correction, CMFD is switched off for the rest of the solve and the Chebyshev acceleration takes over.
-        cmfd_kicks, dphi_prev = 0, None
+        cmfd_kicks, cmfd_skips, dphi_prev = 0, 0, None
         self.cmfd_fallback = False
         f, ng, nP, nJ = self.fes, self.ng, self.fes.n_Phi, self.fes.n_J
         st = self.stats = SolveStats()
@@ -704,9 +704,12 @@ class OracleNeutFEM:
             if cmfd is not None and it >= 2:
                 if cmfd_impl is not None:
                     self.Sol_Phi = cmfd.correct(self.Sol_Phi, keff, prod_old, relaxation=cmfd_relaxation * cmfd_damp)
+                    skipped = getattr(cmfd, "status", 0) == 1
                 else:
                     cmfd.relaxation = cmfd_relaxation * cmfd_damp
                     self.Sol_Phi = cmfd.correct(self.Sol_Phi, keff, prod_old, solver=cmfd_solver)
+                    skipped = bool(cmfd.last.get("skipped"))
+                cmfd_skips = cmfd_skips + 1 if skipped else 0
             prod_new = 0.0
             for g in range(ng):
                 prod_new += float((self.M_fiss[g] @ self.Sol_Phi[g * nP:(g + 1) * nP]).sum())
@@ -729,7 +732,7 @@ class OracleNeutFEM:
             if cmfd is not None and it >= 3:
                 if dphi_prev is not None and diff_flux > 2.0 * dphi_prev:
                     cmfd_kicks += 1
-                if cmfd_kicks >= 3:
+                if cmfd_kicks >= 3 or cmfd_skips >= 3:          # ... or three corrections in a row had to be skipped
                     cmfd, self.cmfd_fallback = None, True
                     accel = ChebyshevAccel(15, 0.98)
             dphi_prev = diff_flux
