@@ -1,7 +1,12 @@
 """
-Pins the CPU oracle against the REAL reference module when oracle/_ref exists (oracle/ref_build/build_ref.py builds it on
-any box that has Eigen headers and the reference sources). In this container Eigen is absent, so the pinning
-cases skip and only the probe logic is exercised; DESIGN.md 5 records the parity status this leaves ("parity unpinned").
+Pins the CPU oracle against the REAL reference code (oracle/ref_build/build_ref.py):
+  * on a box with Eigen headers: the reference's four sources + pybind wrapper, unmodified (`_neutfem_eigen`);
+  * here (no Eigen): the reference's src/FEM.cpp, src/solvers.cpp, src/NeutFEM.cpp, unmodified, over the Eigen stand-in of
+    oracle/ref_build/eigen_shim (`_neutfem_refshim`) -- all FEM / assembly / iteration code that runs is the reference's own,
+    the linear-algebra kernels underneath are the stand-in's.  That build also exposes the assembled matrices, the local
+    matrices, the Schur product, one group solve and the accelerators, so the pin is layer by layer, not only on k.
+Cases skip only when neither build exists (no reference sources on the box, e.g. the GPU box -- where the vectors these
+builds produced are checked instead: tests/golden/ref_v1.npz, tools/make_golden_ref.py).
 
 When the module is present: same XS, same mesh, same tolerances on both sides ->
   k-eff within 1e-8 relative, cell-average flux within 1e-7 relative (both sides iterate to 1e-10; -ffast-math on the
@@ -45,33 +50,216 @@ def test_probe_honours_env(tmp_path, monkeypatch):
 
 def _ref():
     build_ref.build()
-    return build_ref.load()
+    return build_ref.load_any()
 
 
-@pytest.mark.parametrize("dim,n,rt", [(2, (7, 6, 1), 0), (2, (7, 6, 1), 1), (2, (6, 5, 1), 2), (3, (5, 4, 3), 1)])
-def test_oracle_equals_real_reference(dim, n, rt):
+def _need_ref():
     ref = _ref()
     if ref is None:
-        pytest.skip("oracle/_ref not built: no Eigen headers / reference sources on this box (parity unpinned)")
+        pytest.skip("oracle/_ref not built: no reference sources on this box")
+    return ref
+
+
+def make_ref(ref, p, rt, pp, solver="BICGSTAB", tol=(1e-10, 1e-10, 1e-10, 2000, 5000)):
+    s = ref.NeutFEM(rt, pp, p["ng"], p["xb"], p["yb"], p["zb"]) if rt != pp else ref.NeutFEM(rt, p["ng"], p["xb"], p["yb"], p["zb"])
+    s.set_verbosity(ref.VerbosityLevel.SILENT)
+    s.set_linear_solver(getattr(ref.LinearSolverType, solver))
+    s.set_tol(*tol)
+    for a, t, v in p["bcs"]:
+        s.set_bc(int(a), ref.BCType(int(t)), float(v))
+    for name, getter in (("D", s.get_D), ("SigR", s.get_SigR), ("NSF", s.get_NSF), ("Chi", s.get_Chi)):
+        getter().reshape(-1)[:] = p[name]
+    s.get_SigS().reshape(-1)[:] = p["SigS"]
+    s.BuildMatrices()
+    return s
+
+
+@pytest.mark.parametrize("dim,n,rt", [(2, (7, 6, 1), 0), (2, (7, 6, 1), 1), (2, (6, 5, 1), 2), (3, (5, 4, 3), 1), (1, (9, 1, 1), 1)])
+def test_oracle_equals_real_reference(dim, n, rt, capfd):
+    ref = _need_ref()
     p = random_problem(5, dim, n, ng=2, bc="all")
     p["NSF"] *= 3.0
     o = make_oracle(p, rt, rt)
     o.set_tol(1e-10, 1e-10, 1e-10, 2000, 5000)
     k_o = o.SolveKeff()
-    s = ref.NeutFEM(rt, 2, p["xb"], p["yb"], p["zb"])
-    s.set_verbosity(ref.VerbosityLevel.SILENT)
-    s.set_linear_solver(ref.LinearSolverType.BICGSTAB)
-    s.set_tol(1e-10, 1e-10, 1e-10, 2000, 5000)
-    for a, t, v in p["bcs"]:
-        s.set_bc(int(a), ref.BCType(int(t)), float(v))
-    ne = p["ne"]
-    for name, getter in (("D", s.get_D), ("SigR", s.get_SigR), ("NSF", s.get_NSF), ("Chi", s.get_Chi)):
-        getter().reshape(-1)[:] = p[name]
-    s.get_SigS().reshape(-1)[:] = p["SigS"]
-    s.BuildMatrices()
+    s = make_ref(ref, p, rt, rt)
     k_r = s.SolveKeff()
-    assert abs(k_o - k_r) / abs(k_r) < 1e-8
+    assert abs(k_o - k_r) / abs(k_r) < 1e-9
     f_o = np.asarray(o.get_flux()).reshape(-1)
     f_r = np.asarray(s.get_flux()).reshape(-1)
-    assert f_o.shape == f_r.shape == (2 * ne,)
+    assert f_o.shape == f_r.shape == (2 * p["ne"],)
     assert relerr(f_o, f_r) < 1e-7
+    if hasattr(s, "sol_phi"):                      # every DOF, reference numbering
+        assert relerr(o.Sol_Phi, s.sol_phi()) < 1e-7
+        assert relerr(o.Sol_J, s.sol_J()) < 1e-6
+
+
+def _dense(coo):
+    r, c, v, shape = coo
+    import scipy.sparse as sp
+    return sp.coo_matrix((v, (r, c)), shape=shape).toarray()
+
+
+LAYER_CASES = [(1, (9, 1, 1), 0, 0, "mixed"), (1, (7, 1, 1), 2, 2, "all"), (2, (5, 4, 1), 0, 0, "all"), (2, (5, 4, 1), 1, 1, "mixed"),
+               (2, (4, 3, 1), 2, 2, "none"), (2, (4, 5, 1), 2, 1, "all"), (2, (4, 3, 1), 1, 0, "mixed"), (3, (3, 4, 2), 0, 0, "mixed"),
+               (3, (3, 2, 3), 1, 1, "all"), (3, (2, 3, 2), 2, 2, "mixed"), (3, (3, 2, 2), 2, 1, "all")]
+
+
+@pytest.mark.parametrize("dim,n,rt,pp,bc", LAYER_CASES)
+def test_assembled_matrices_equal_reference(dim, n, rt, pp, bc):
+    """A_g (with the Dirichlet terms), B, C_g, fission / scatter / chi mass matrices: entry by entry, reference numbering."""
+    ref = _need_ref()
+    if not hasattr(ref, "ChebyshevAccel"):
+        pytest.skip("the wrapper build does not expose the matrices")
+    p = random_problem(11, dim, n, ng=2, bc=bc)
+    o = make_oracle(p, rt, pp)
+    s = make_ref(ref, p, rt, pp)
+    assert (s.n_J, s.n_Phi) == (o.fes.n_J, o.fes.n_Phi)
+    ng = 2
+    pairs = [("B", 0, 0, o.B)]
+    for g in range(ng):
+        pairs += [("A", g, 0, o.A[g]), ("C", g, 0, o.C[g]), ("M_fiss", g, 0, o.M_fiss[g]), ("M_chi", g, 0, o.M_chi[g])]
+    for i in range(ng * ng):
+        if o.M_scatter[i] is not None:
+            pairs.append(("M_scatter", i // ng, i % ng, o.M_scatter[i]))
+    for name, g, g2, mo in pairs:
+        mr = _dense(s.matrix(name, g, g2))
+        mo = mo.toarray()
+        assert mr.shape == mo.shape, name
+        scale = max(np.abs(mr).max(), 1e-300)
+        assert np.abs(mr - mo).max() <= 1e-12 * scale, (name, g, g2, np.abs(mr - mo).max() / scale)
+
+
+@pytest.mark.parametrize("dim,n,rt,pp,bc", LAYER_CASES)
+def test_local_matrices_and_schur_product_equal_reference(dim, n, rt, pp, bc):
+    ref = _need_ref()
+    if not hasattr(ref, "ChebyshevAccel"):
+        pytest.skip("the wrapper build does not expose the local matrices")
+    p = random_problem(12, dim, n, ng=2, bc=bc)
+    o = make_oracle(p, rt, pp)
+    s = make_ref(ref, p, rt, pp)
+    rng = np.random.default_rng(3)
+    for e in rng.integers(0, p["ne"], 3):
+        D, Sig = float(rng.uniform(0.3, 2.0)), float(rng.uniform(0.01, 0.4))
+        for mr, mo in zip(s.local_matrices(int(e), D, Sig), o.fes.local(int(e), D, Sig)):
+            assert np.abs(mr - np.asarray(mo).reshape(mr.shape)).max() <= 1e-13 * max(np.abs(mr).max(), 1e-300)
+    for g in range(2):
+        x = rng.uniform(-1.0, 1.0, o.fes.n_Phi)
+        assert relerr(o.schur_product(g, x), s.schur_product(g, x)) < 1e-12
+
+
+@pytest.mark.parametrize("dim,n,rt", [(2, (12, 11, 1), 1), (3, (6, 5, 4), 1), (2, (16, 15, 1), 0), (3, (4, 4, 4), 2)])
+def test_implicit_schur_cg_equals_reference(dim, n, rt):
+    """The hot path itself (src/solvers.cpp:577-636, n_Phi >= 200): same iterate count, same flux, same current."""
+    ref = _need_ref()
+    if not hasattr(ref, "ChebyshevAccel"):
+        pytest.skip("the wrapper build does not expose one group solve")
+    from oracle.neutfem_oracle import SchurSolverOracle, CG
+    p = random_problem(13, dim, n, ng=2, bc="mixed")
+    o = make_oracle(p, rt, rt)
+    assert o.fes.n_Phi >= 200
+    s = make_ref(ref, p, rt, rt, solver="CG", tol=(1e-8, 1e-9, 1e-9, 100, 3000))      # inner tolerance = tol_flux (src/NeutFEM.cpp:334)
+    rng = np.random.default_rng(4)
+    for g in range(2):
+        rhs = rng.uniform(0.0, 1.0, o.fes.n_Phi)
+        so = SchurSolverOracle()
+        so.solver_type, so.tol, so.max_iter = CG, 1e-9, 3000
+        so.set_matrices(o.A[g], o.B, o.C[g])
+        J_o, phi_o = so.solve(rhs)
+        J_r, phi_r, its_r = s.schur_solve(g, rhs)
+        assert abs(so.last_iterations - its_r) <= 1, (so.last_iterations, its_r)
+        assert relerr(phi_o, phi_r) < 1e-7 and relerr(J_o, J_r) < 1e-7
+
+
+def test_accelerators_equal_reference():
+    ref = _need_ref()
+    if not hasattr(ref, "ChebyshevAccel"):
+        pytest.skip("the wrapper build does not expose the accelerators")
+    from oracle.neutfem_oracle import AndersonAccelReference, ChebyshevAccel
+    rng = np.random.default_rng(5)
+    a_o, a_r = ChebyshevAccel(15, 0.98), ref.ChebyshevAccel(15, 0.98)
+    base = rng.uniform(0.5, 1.5, 40)
+    for it in range(40):                                     # crosses two restarts of the 15-step cycle
+        phi = base + 0.9 ** it * rng.uniform(-0.2, 0.2, 40)
+        assert relerr(a_o(phi.copy()), a_r(phi)) < 1e-13, it
+    b_o, b_r = AndersonAccelReference(5, 1.0), ref.AndersonAccel(5, 1.0)
+    for it in range(12):
+        phi = base + 0.7 ** it * rng.uniform(-0.2, 0.2, 40)
+        out_r, _ = b_r(phi)
+        assert relerr(b_o(phi.copy()), out_r) < 1e-9, it
+
+
+def test_diagonal_path_equals_reference():
+    """RT0-P0 diagonal cache (src/NeutFEM.cpp:483-597) and SolveKeff(use_diagonal_solver=True), incl. 1e15 'void' cells."""
+    ref = _need_ref()
+    p = random_problem(14, 3, (6, 5, 4), ng=2, bc="mixed")
+    p["NSF"] *= 3.0
+    p["SigR"][3] = p["SigR"][17] = 1e15
+    o = make_oracle(p, 0, 0)
+    o.set_tol(1e-10, 1e-10, 1e-10, 2000, 5000)
+    s = make_ref(ref, p, 0, 0)
+    k_o = o.SolveKeff(False, (), True, False)
+    k_r = s.SolveKeff(False, [], True, False)
+    assert abs(k_o - k_r) / abs(k_r) < 1e-9
+    assert relerr(np.asarray(o.get_flux()).reshape(-1), np.asarray(s.get_flux()).reshape(-1)) < 1e-7
+    if hasattr(s, "diag_cache"):
+        for g in range(2):
+            assert relerr(o.diag_cache[g], s.diag_cache(g)) < 1e-13
+
+
+@pytest.mark.parametrize("dim,n,rt", [(2, (7, 6, 1), 1), (3, (4, 3, 3), 0)])
+def test_adjoint_equals_reference(dim, n, rt):
+    ref = _need_ref()
+    p = random_problem(15, dim, n, ng=2, bc="all")
+    p["NSF"] *= 3.0
+    o = make_oracle(p, rt, rt)
+    o.set_tol(1e-10, 1e-10, 1e-10, 2000, 5000)
+    s = make_ref(ref, p, rt, rt)
+    k_o, k_r = o.SolveKeff(), s.SolveKeff()
+    # use_direct_keff=False is left out on purpose: with its own eigenvalue update (src/NeutFEM.cpp:1968-1976) plus the
+    # Chebyshev step on the normalised vector, the reference's adjoint iteration does not converge on this problem -- it
+    # runs into max_outer on both sides and its k (1.096 / 0.785 / 0.256 for D, D(1+1e-13), D(1+1e-12) in the oracle;
+    # 0.821 in the reference build) is decided by rounding.  Not a pinnable quantity.
+    for flags in ((True, True), (False, True)):
+        ka_o, ka_r = o.SolveAdjoint(*flags), s.SolveAdjoint(*flags)
+        assert abs(ka_o - ka_r) / abs(ka_r) < 1e-8 and abs(k_o - k_r) / k_r < 1e-9
+        assert relerr(np.asarray(o.get_flux_adj()).reshape(-1), np.asarray(s.get_flux_adj()).reshape(-1)) < 1e-6
+
+
+def test_solve_coarse_and_coarse_init_equal_reference():
+    ref = _need_ref()
+    p = random_problem(16, 2, (8, 6, 1), ng=2, bc="all")
+    p["NSF"] *= 3.0
+    o = make_oracle(p, 1, 1)
+    o.set_tol(1e-9, 1e-9, 1e-9, 2000, 5000)
+    s = make_ref(ref, p, 1, 1, tol=(1e-9, 1e-9, 1e-9, 2000, 5000))
+    kc_o, proj_o = o.SolveCoarse([2, 2])
+    kc_r, proj_r = s.SolveCoarse([2, 2])
+    assert abs(kc_o - kc_r) / kc_r < 1e-7 and relerr(proj_o, np.asarray(proj_r).reshape(-1)) < 1e-6
+    k_o, k_r = o.SolveKeff(True, (2, 2)), s.SolveKeff(True, [2, 2])
+    assert abs(k_o - k_r) / k_r < 1e-8
+
+
+def test_reference_benchmark_iaea2d_equals_reference():
+    """The reference's own 2-D IAEA script configuration (RT1-P1, 2 groups, its material map and BCs) at its base mesh."""
+    ref = _need_ref()
+    from neutfem_b200 import benchmarks as bm
+    from oracle.neutfem_oracle import OracleNeutFEM, BICGSTAB
+    p = bm.problem_2d("iaea2d", 1)
+    o = OracleNeutFEM(1, 1, p.ng, p.x_breaks, p.y_breaks, p.z_breaks)
+    o.set_linear_solver(BICGSTAB)
+    o.set_tol(1e-9, 1e-8, 1e-8, 500, 3000)
+    p.apply(o)
+    o.BuildMatrices()
+    s = ref.NeutFEM(1, p.ng, p.x_breaks, p.y_breaks, p.z_breaks)
+    s.set_verbosity(ref.VerbosityLevel.SILENT)
+    s.set_linear_solver(ref.LinearSolverType.BICGSTAB)
+    s.set_tol(1e-9, 1e-8, 1e-8, 500, 3000)
+    for a, t, v in p.bcs:
+        s.set_bc(int(a), ref.BCType(int(t)), float(v))
+    for name, getter in (("D", s.get_D), ("SigR", s.get_SigR), ("NSF", s.get_NSF), ("Chi", s.get_Chi), ("SigS", s.get_SigS)):
+        getter().reshape(-1)[:] = np.asarray(getattr(p, name)).reshape(-1)
+    s.BuildMatrices()
+    k_o, k_r = o.SolveKeff(), s.SolveKeff()
+    assert abs(k_o - k_r) / k_r < 1e-8
+    assert relerr(np.asarray(o.get_flux()).reshape(-1), np.asarray(s.get_flux()).reshape(-1)) < 1e-6
