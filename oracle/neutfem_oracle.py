@@ -21,10 +21,14 @@ ported from; COLAMD ordering in both); `setFromTriplets` with scipy COO->CSC (bo
 reference hands a *formed* Schur matrix to an Eigen Krylov class (n_phi < 200 or DIRECT_*; solvers.cpp:328-509)
 the oracle solves it directly with splu -- the Krylov classes only approximate that solution to `tol`.
 
-PARITY UNPINNED at operator level: the reference has no assertions, golden vectors or CI and cannot
-be built here (no Eigen, undefined symbols). What pins this oracle: (i) internal identities checked in
-tests/test_oracle.py (implicit SchurProduct == explicitly formed S; A, S symmetric positive definite; closed
-forms of SURVEY Appendix A); (ii) the reference's published k-eff table README.md:289-292 (tests/golden/).
+PARITY: pinned against the reference's own compiled code -- oracle/ref_build/build_ref.py compiles its src/FEM.cpp,
+src/solvers.cpp, src/NeutFEM.cpp unmodified (over real Eigen where a box has it; in this image over the Eigen stand-in of
+oracle/ref_build/eigen_shim) and tests/test_ref_pin.py compares layer by layer: assembled matrices entry by entry (1e-12),
+local matrices (1e-13), SchurProduct (1e-12), the implicit CG's iterate count and solution, k (1e-9) and every DOF (1e-7) of
+converged SolveKeff runs, diagonal path, Chebyshev, Anderson, adjoint, coarse solve. Limit: with the stand-in, Eigen's own
+kernels (SparseLU ordering, Krylov classes) are not the ones that run. Also held by internal identities in
+tests/test_oracle.py (implicit SchurProduct == explicitly formed S; A, S symmetric positive definite; closed forms of
+SURVEY Appendix A).
 """
 from __future__ import annotations
 

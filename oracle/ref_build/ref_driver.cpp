@@ -199,6 +199,12 @@ PYBIND11_MODULE(_neutfem_refshim, m)
                  s.schur_solver_->Solve(to_vec(rhs), J, Phi);
                  return py::make_tuple(to_np(J), to_np(Phi), s.schur_solver_->GetLastIterations());
              })
+        .def("current_from_flux",       // J = -A^-1 B^T phi with the solver's own factorisation (src/solvers.cpp:227-228)
+             [](NeutFEM &s, int g, const arr_t &x) {
+                 s.schur_solver_->SetMatrices(s.A_mats_[size_t(g)], s.B_mat_, s.C_mats_[size_t(g)]);
+                 Vec tmp = s.schur_solver_->BT_ * to_vec(x);
+                 return to_np(-s.schur_solver_->A_lu_solver_.solve(tmp));
+             })
         .def("diag_cache",
              [](NeutFEM &s, int g) {
                  if (!s.diag_schur_cache_ || !s.diag_schur_cache_->is_valid) throw std::runtime_error("no diagonal cache");

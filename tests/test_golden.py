@@ -1,7 +1,11 @@
 """
-Frozen vectors (tests/golden/golden_v1.npz, made by tools/make_golden.py from the CPU oracle in the build container).
-CPU: the oracle still reproduces them (guards the checker against drift). GPU: the CUDA path reproduces them through
-the C ABI without any CPU solve at run time. Tolerances: operators 1e-12 relative; k 1e-6, flux 1e-5 (north_star).
+Frozen vectors.
+  * tests/golden/golden_v1.npz -- made by tools/make_golden.py from the CPU oracle in the build container.
+  * tests/golden/ref_v1.npz    -- the SAME cases and keys, made by tools/make_golden_ref.py from the REFERENCE'S OWN CODE
+    (its src/FEM.cpp, src/solvers.cpp, src/NeutFEM.cpp compiled unmodified by oracle/ref_build/build_ref.py; the npz records
+    which linear algebra lay underneath, "eigen" or "eigen_shim").
+CPU: the oracle reproduces both (drift guard + pin against reference-made vectors). GPU: the CUDA path reproduces both
+through the C ABI without any CPU solve at run time. Tolerances: operators 1e-12 relative; k 1e-6, flux 1e-5 (north_star).
 """
 import os
 
@@ -12,6 +16,7 @@ from helpers import make_gpu, make_oracle, random_problem, relerr
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 G = np.load(os.path.join(HERE, "golden", "golden_v1.npz"))
+R = np.load(os.path.join(HERE, "golden", "ref_v1.npz"))          # vectors produced by the reference's own code
 
 OPERATOR_CASES = [   # must match tools/make_golden.py
     ("op1d_rt2p2", 101, 1, (17, 1, 1), 2, 2, "mixed"),
@@ -100,4 +105,96 @@ def test_gpu_reproduces_golden_keff(name):
     phi = c.get_flux()
     assert abs(np.linalg.norm(phi) - G[name + "_phi_norm"][0]) / G[name + "_phi_norm"][0] < 1e-5
     assert relerr(phi[::37], G[name + "_phi_sample"]) < 1e-5
+    c.close()
+
+
+# ---- the same cases against the vectors the REFERENCE'S OWN CODE produced (tests/golden/ref_v1.npz) ----
+
+@pytest.mark.parametrize("name,seed,dim,n,rt,pp,bc", OPERATOR_CASES)
+def test_oracle_reproduces_reference_operators(name, seed, dim, n, rt, pp, bc):
+    p = random_problem(seed, dim, n, ng=2, bc=bc)
+    o = make_oracle(p, rt, pp)
+    x = R[name + "_x"]
+    assert tuple(R[name + "_sizes"]) == (o.fes.n_Phi, o.fes.n_J)          # DOF counts of the reference's FESpace
+    assert np.array_equal(x, np.random.default_rng(seed).uniform(0.5, 1.5, o.fes.n_Phi))
+    assert relerr(o.schur_product(0, x), R[name + "_Sx_g0"]) < 1e-13
+    assert relerr(o.schur_product(1, x), R[name + "_Sx_g1"]) < 1e-13
+    assert relerr(o.current_from_flux(0, x), R[name + "_J_g0"]) < 1e-13
+
+
+def test_oracle_and_reference_vectors_agree_on_every_key():
+    """golden_v1 (oracle) against ref_v1 (reference code): operators to rounding, converged k to 1e-10, flux to 1e-6."""
+    for key in R.files:
+        if key == "linear_algebra" or key.startswith("rows_"):      # rows_*: checked against a fresh oracle solve below
+            continue
+        assert key in G.files, key
+        if key.endswith("_sizes") or key.endswith("_x"):
+            assert np.array_equal(G[key], R[key]), key
+        elif key.startswith("op"):
+            assert relerr(G[key], R[key]) < 1e-13, key
+        elif key.endswith("_k"):
+            assert abs(G[key][0] - R[key][0]) / R[key][0] < 1e-10, key
+        else:
+            assert relerr(G[key], R[key]) < 1e-6, key
+
+
+@pytest.mark.parametrize("rt", [0, 1, 2])
+def test_oracle_reproduces_reference_3d_keff(rt):
+    """The 3-D problems of tests/test_gpu_fused.py: converged k and every flux DOF (reference numbering)."""
+    p = random_problem(9, 3, (8, 6, 5), ng=2, bc="all")
+    p["NSF"] *= 3.0
+    o = make_oracle(p, rt, rt)
+    o.set_tol(1e-9, 1e-9, 1e-9, 500, 5000)
+    k = o.SolveKeff()
+    assert abs(k - R[f"rows_keff_rt{rt}_k"][0]) / k < 1e-9
+    assert relerr(o.Sol_Phi, R[f"rows_keff_rt{rt}_phi"]) < 1e-7
+
+
+@pytest.mark.parametrize("n,rt", [((16, 9, 5), 1), ((10, 6, 5), 2), ((12, 7, 6), 0)])
+def test_oracle_reproduces_reference_inner_cg(n, rt):
+    """One implicit Schur CG solve (src/solvers.cpp:577-636): the reference's iterate count and solution."""
+    from oracle.neutfem_oracle import CG, SchurSolverOracle
+    p = random_problem(21, 3, n, ng=1, bc="all")
+    o = make_oracle(p, rt, rt)
+    rhs = np.random.default_rng(2).uniform(0.0, 1.0, o.fes.n_Phi)
+    s = SchurSolverOracle()
+    s.solver_type, s.tol, s.max_iter = CG, 1e-10, 3000
+    s.set_matrices(o.A[0], o.B, o.C[0])
+    phi = s.solve_implicit(rhs)
+    key = "rows_cg_%dx%dx%d_rt%d" % (n + (rt,))
+    assert abs(s.last_iterations - int(R[key + "_its"][0])) <= 1
+    assert relerr(phi, R[key + "_phi"]) < 1e-8
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,seed,dim,n,rt,pp,bc", OPERATOR_CASES)
+def test_gpu_reproduces_reference_operators(name, seed, dim, n, rt, pp, bc):
+    p = random_problem(seed, dim, n, ng=2, bc=bc)
+    c = make_gpu(p, rt, pp)
+    x = R[name + "_x"]
+    assert tuple(R[name + "_sizes"]) == (c.n_Phi, c.n_J)
+    assert relerr(c.schur_apply(0, x), R[name + "_Sx_g0"]) < 1e-12
+    assert relerr(c.schur_apply(1, x), R[name + "_Sx_g1"]) < 1e-12
+    assert relerr(c.current_from_flux(0, x), R[name + "_J_g0"]) < 1e-12
+    c.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["cfg1_iaea2d_rt0p0", "cfg2_iaea3d_diag", "cfg3_biblis_rt1p1", "cfg4_koeberg_rt2p2"])
+def test_gpu_reproduces_reference_keff(name):
+    from neutfem_b200 import cabi
+    mk, rt, pp, solver, tol, diag = _cfgs()[name]
+    p = mk()
+    c = cabi.Context(rt, pp, p.ng, p.x_breaks, p.y_breaks, p.z_breaks)
+    c.set_solver(solver_type=solver, tol_keff=tol[0], tol_flux=tol[1], max_outer=tol[2], max_inner=tol[3])
+    for a, t, v in p.bcs:
+        c.set_bc(a, t, v)
+    c.upload_xs(D=p.D, SigR=p.SigR, NSF=p.NSF, Chi=p.Chi, SigS=p.SigS)
+    c.build()
+    k, st = c.solve_keff(diag)
+    k_ref = float(R[name + "_k"][0])
+    assert abs(k - k_ref) / k_ref < 1e-6
+    phi = c.get_flux()
+    assert abs(np.linalg.norm(phi) - R[name + "_phi_norm"][0]) / R[name + "_phi_norm"][0] < 1e-5
+    assert relerr(phi[::37], R[name + "_phi_sample"]) < 1e-5
     c.close()

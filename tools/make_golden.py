@@ -3,9 +3,9 @@
 Generates tests/golden/golden_v1.npz: frozen input/output vectors of the hot path produced by the CPU oracle
 (oracle/neutfem_oracle.py + oracle/fem_ref.c) in this container.
 
-The reference itself cannot produce them: it does not build here (Eigen is absent) and ships no golden
-outputs, so these vectors pin the ORACLE (against drift) and give the -m gpu tests a comparison that needs
-no CPU solve at run time; they do not add pinning against the reference (parity unpinned).
+These vectors guard the ORACLE against drift and give the -m gpu tests a comparison that needs no CPU solve at run time.
+The same cases produced by the REFERENCE'S OWN CODE are in tests/golden/ref_v1.npz (tools/make_golden_ref.py), which is
+what pins the oracle and the CUDA path against the reference.
 
     python tools/make_golden.py        # rewrites tests/golden/golden_v1.npz (a few seconds to a minute of CPU)
 """

@@ -1,0 +1,105 @@
+#!/usr/bin/env python
+"""
+Generates tests/golden/ref_v1.npz: input/output vectors of the hot path produced by the REFERENCE'S OWN CODE -- its
+src/FEM.cpp, src/solvers.cpp and src/NeutFEM.cpp compiled unmodified by oracle/ref_build/build_ref.py (over real Eigen
+where a box has it; in the build container over the Eigen stand-in of oracle/ref_build/eigen_shim, see its header for
+what that does and does not replace).  Same cases and keys as tools/make_golden.py (whose vectors come from the oracle),
+so that
+  * the CPU suite checks the oracle against reference-made vectors even on a box without the reference sources, and
+  * the -m gpu suite checks the CUDA path against reference-made vectors (/root/reference does not exist on the GPU box).
+
+    python tools/make_golden_ref.py      # needs /root/reference (or $NEUTFEM_REFERENCE_DIR); about a minute of CPU
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "oracle", "ref_build"))
+
+import build_ref  # noqa: E402
+from helpers import random_problem  # noqa: E402
+from neutfem_b200 import benchmarks as bm  # noqa: E402
+from make_golden import OPERATOR_CASES  # noqa: E402
+
+SOLVER_NAMES = {6: "BICGSTAB", 4: "CG_DIAG", 3: "CG"}
+
+
+def fill(ref, s, bcs, D, SigR, NSF, Chi, SigS):
+    s.set_verbosity(ref.VerbosityLevel.SILENT)
+    for a, t, v in bcs:
+        s.set_bc(int(a), ref.BCType(int(t)), float(v))
+    for getter, val in ((s.get_D, D), (s.get_SigR, SigR), (s.get_NSF, NSF), (s.get_Chi, Chi), (s.get_SigS, SigS)):
+        getter().reshape(-1)[:] = np.asarray(val).reshape(-1)
+
+
+def main():
+    verdict = build_ref.build()
+    ref = build_ref.load_any()
+    if ref is None:
+        raise SystemExit(f"no reference build: {verdict}")
+    out = {"linear_algebra": np.array(verdict.get("linear_algebra", "eigen"))}
+    for name, seed, dim, n, rt, pp, bc in OPERATOR_CASES:
+        p = random_problem(seed, dim, n, ng=2, bc=bc)
+        s = ref.NeutFEM(rt, pp, 2, p["xb"], p["yb"], p["zb"])
+        fill(ref, s, p["bcs"], p["D"], p["SigR"], p["NSF"], p["Chi"], p["SigS"])
+        s.set_linear_solver(ref.LinearSolverType.BICGSTAB)
+        s.BuildMatrices()
+        x = np.random.default_rng(seed).uniform(0.5, 1.5, s.n_Phi)
+        out[name + "_x"] = x
+        out[name + "_Sx_g0"] = s.schur_product(0, x)
+        out[name + "_Sx_g1"] = s.schur_product(1, x)
+        out[name + "_J_g0"] = s.current_from_flux(0, x)
+        out[name + "_sizes"] = np.array([s.n_Phi, s.n_J], dtype=np.int64)
+        print(f"{name}: n_Phi = {s.n_Phi}, n_J = {s.n_J}")
+    cfgs = [   # the four CPU-sized configurations of BASELINE.json, as in tools/make_golden.py
+        ("cfg1_iaea2d_rt0p0", bm.problem_2d("iaea2d", 2), 0, 0, "BICGSTAB", (1e-9, 1e-9, 800, 5000), False),
+        ("cfg2_iaea3d_diag", bm.problem_iaea3d(2, 1), 0, 0, "BICGSTAB", (1e-10, 1e-10, 1000, 1000), True),
+        ("cfg3_biblis_rt1p1", bm.problem_2d("biblis2d", 2), 1, 1, "CG_DIAG", (1e-9, 1e-9, 800, 5000), False),
+        ("cfg4_koeberg_rt2p2", bm.problem_2d("koeberg2d", 1), 2, 2, "BICGSTAB", (1e-9, 1e-9, 800, 8000), False),
+    ]
+    for name, p, rt, pp, solver, tol, diag in cfgs:
+        s = ref.NeutFEM(rt, pp, p.ng, p.x_breaks, p.y_breaks, p.z_breaks)
+        fill(ref, s, p.bcs, p.D, p.SigR, p.NSF, p.Chi, p.SigS)
+        s.set_linear_solver(getattr(ref.LinearSolverType, solver))
+        s.set_tol(tol[0], tol[1], tol[1], tol[2], tol[3])
+        s.BuildMatrices()
+        k = s.SolveKeff(False, [], diag, False)
+        phi = s.sol_phi()
+        out[name + "_k"] = np.array([k])
+        out[name + "_phi_norm"] = np.array([np.linalg.norm(phi)])
+        out[name + "_phi_sample"] = phi[::37].copy()
+        print(f"{name}: k = {k:.12f}, n = {phi.size}")
+    # the 3-D product path's own test problems (tests/test_gpu_fused.py): converged k and EVERY flux DOF, one inner CG solve
+    for rt in (0, 1, 2):
+        p = random_problem(9, 3, (8, 6, 5), ng=2, bc="all")
+        s = ref.NeutFEM(rt, rt, 2, p["xb"], p["yb"], p["zb"])
+        fill(ref, s, p["bcs"], p["D"], p["SigR"], 3.0 * p["NSF"], p["Chi"], p["SigS"])
+        s.set_linear_solver(ref.LinearSolverType.BICGSTAB)
+        s.set_tol(1e-9, 1e-9, 1e-9, 500, 5000)
+        s.BuildMatrices()
+        out[f"rows_keff_rt{rt}_k"] = np.array([s.SolveKeff()])
+        out[f"rows_keff_rt{rt}_phi"] = s.sol_phi()
+        print(f"rows_keff_rt{rt}: k = {out[f'rows_keff_rt{rt}_k'][0]:.12f}")
+    for n, rt in (((16, 9, 5), 1), ((10, 6, 5), 2), ((12, 7, 6), 0)):
+        p = random_problem(21, 3, n, ng=1, bc="all")
+        s = ref.NeutFEM(rt, rt, 1, p["xb"], p["yb"], p["zb"])
+        fill(ref, s, p["bcs"], p["D"], p["SigR"], p["NSF"], p["Chi"], p["SigS"])
+        s.set_linear_solver(ref.LinearSolverType.CG)
+        s.set_tol(1e-9, 1e-10, 1e-9, 500, 3000)           # inner tolerance = tol_flux (src/NeutFEM.cpp:334)
+        s.BuildMatrices()
+        rhs = np.random.default_rng(2).uniform(0.0, 1.0, s.n_Phi)
+        J, phi, its = s.schur_solve(0, rhs)
+        key = "rows_cg_%dx%dx%d_rt%d" % (n + (rt,))
+        out[key + "_phi"], out[key + "_its"] = phi, np.array([its], dtype=np.int64)
+        print(f"{key}: {its} CG iterations, n_Phi = {s.n_Phi}")
+    path = os.path.join(ROOT, "tests", "golden", "ref_v1.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+    main()
