@@ -139,6 +139,7 @@ def _import(name: str, path: str):
     spec = importlib.util.spec_from_file_location(name, path)
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
+    sys.modules.setdefault(name, mod)      # so that importlib.import_module(type(obj).__module__) finds its enums
     return mod
 
 
