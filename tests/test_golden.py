@@ -5,7 +5,7 @@ Frozen vectors.
     (its src/FEM.cpp, src/solvers.cpp, src/NeutFEM.cpp compiled unmodified by oracle/ref_build/build_ref.py; the npz records
     which linear algebra lay underneath, "eigen" or "eigen_shim").
 CPU: the oracle reproduces both (drift guard + pin against reference-made vectors). GPU: the CUDA path reproduces both
-through the C ABI without any CPU solve at run time. Tolerances: operators 1e-12 relative; k 1e-6, flux 1e-5 (north_star).
+through the C ABI without any CPU solve at run time (golden_v1 here, ref_v1 in tests/test_zy_gpu_reference_vectors.py). Tolerances: operators 1e-12 relative; k 1e-6, flux 1e-5 (north_star).
 """
 import os
 
@@ -164,37 +164,3 @@ def test_oracle_reproduces_reference_inner_cg(n, rt):
     key = "rows_cg_%dx%dx%d_rt%d" % (n + (rt,))
     assert abs(s.last_iterations - int(R[key + "_its"][0])) <= 1
     assert relerr(phi, R[key + "_phi"]) < 1e-8
-
-
-@pytest.mark.gpu
-@pytest.mark.parametrize("name,seed,dim,n,rt,pp,bc", OPERATOR_CASES)
-def test_gpu_reproduces_reference_operators(name, seed, dim, n, rt, pp, bc):
-    p = random_problem(seed, dim, n, ng=2, bc=bc)
-    c = make_gpu(p, rt, pp)
-    x = R[name + "_x"]
-    assert tuple(R[name + "_sizes"]) == (c.n_Phi, c.n_J)
-    assert relerr(c.schur_apply(0, x), R[name + "_Sx_g0"]) < 1e-12
-    assert relerr(c.schur_apply(1, x), R[name + "_Sx_g1"]) < 1e-12
-    assert relerr(c.current_from_flux(0, x), R[name + "_J_g0"]) < 1e-12
-    c.close()
-
-
-@pytest.mark.gpu
-@pytest.mark.parametrize("name", ["cfg1_iaea2d_rt0p0", "cfg2_iaea3d_diag", "cfg3_biblis_rt1p1", "cfg4_koeberg_rt2p2"])
-def test_gpu_reproduces_reference_keff(name):
-    from neutfem_b200 import cabi
-    mk, rt, pp, solver, tol, diag = _cfgs()[name]
-    p = mk()
-    c = cabi.Context(rt, pp, p.ng, p.x_breaks, p.y_breaks, p.z_breaks)
-    c.set_solver(solver_type=solver, tol_keff=tol[0], tol_flux=tol[1], max_outer=tol[2], max_inner=tol[3])
-    for a, t, v in p.bcs:
-        c.set_bc(a, t, v)
-    c.upload_xs(D=p.D, SigR=p.SigR, NSF=p.NSF, Chi=p.Chi, SigS=p.SigS)
-    c.build()
-    k, st = c.solve_keff(diag)
-    k_ref = float(R[name + "_k"][0])
-    assert abs(k - k_ref) / k_ref < 1e-6
-    phi = c.get_flux()
-    assert abs(np.linalg.norm(phi) - R[name + "_phi_norm"][0]) / R[name + "_phi_norm"][0] < 1e-5
-    assert relerr(phi[::37], R[name + "_phi_sample"]) < 1e-5
-    c.close()

@@ -168,41 +168,3 @@ def test_odd_nx_matches_oracle():
         c.close()
     assert abs(k - k_ref) / k_ref < 1e-6
     assert relerr(phi, o.Sol_Phi) < 1e-5
-
-
-# ---- the shipped path against vectors made by the REFERENCE'S OWN CODE (tests/golden/ref_v1.npz, tools/make_golden_ref.py) ----
-
-REF = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_v1.npz"))
-
-
-@pytest.mark.parametrize("n,rt", [((16, 9, 5), 1), ((10, 6, 5), 2), ((12, 7, 6), 0)])
-@pytest.mark.parametrize("mode", [0, 1])
-def test_default_path_inner_cg_matches_reference_vectors(n, rt, mode):
-    """Same problems as test_default_path_inner_cg_matches_oracle; the expected solution and iterate count are the
-    reference's own (src/solvers.cpp:577-636 compiled unmodified)."""
-    p = random_problem(21, 3, n, ng=1, bc="all")
-    key = "rows_cg_%dx%dx%d_rt%d" % (n + (rt,))
-    rhs = np.random.default_rng(2).uniform(0.0, 1.0, REF[key + "_phi"].size)
-    phi, it, res, kt = _solve(p, rt, rt, mode, rhs, None)
-    assert kt["path"] == 3.0, "the default (rows) path was not taken"
-    if mode == 0:
-        assert abs(it - int(REF[key + "_its"][0])) <= 3
-    assert relerr(phi, REF[key + "_phi"]) < 1e-7
-
-
-@pytest.mark.parametrize("rt", [1, 0, 2])
-@pytest.mark.parametrize("mode", [0, 1])
-def test_default_path_keff_matches_reference_vectors(rt, mode):
-    """Same problem as test_default_path_keff_matches_oracle; k and every flux DOF are the reference's own."""
-    p = random_problem(9, 3, (8, 6, 5), ng=2, bc="all")
-    p["NSF"] *= 3.0
-    with path_env(None):
-        c = make_gpu(p, rt, rt)
-        c.set_solver(tol_keff=1e-9, tol_flux=1e-9, max_outer=500, max_inner=5000, mode=mode)
-        k, st = c.solve_keff(False)
-        assert c.time_kernels(0, 1, bool(mode))["path"] == 3.0
-        phi = c.get_flux()
-        c.close()
-    k_ref = float(REF[f"rows_keff_rt{rt}_k"][0])
-    assert abs(k - k_ref) / k_ref < 1e-6
-    assert relerr(phi, REF[f"rows_keff_rt{rt}_phi"]) < 1e-5

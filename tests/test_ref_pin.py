@@ -263,3 +263,30 @@ def test_reference_benchmark_iaea2d_equals_reference():
     k_o, k_r = o.SolveKeff(), s.SolveKeff()
     assert abs(k_o - k_r) / k_r < 1e-8
     assert relerr(np.asarray(o.get_flux()).reshape(-1), np.asarray(s.get_flux()).reshape(-1)) < 1e-6
+
+
+@pytest.mark.parametrize("dim,n,rt", [(3, (3, 3, 2), 1), (2, (4, 3, 1), 0), (3, (3, 2, 2), 2), (1, (5, 1, 1), 1)])
+def test_vtk_restatement_is_byte_identical_to_the_reference_writer(tmp_path, dim, n, rt):
+    """tests/test_gpu_outputs.py checks the product's ExportVTK byte for byte against a python restatement of the reference
+    writer (src/NeutFEM.cpp:2137-2324); here that restatement is checked byte for byte against the reference writer itself."""
+    ref = _need_ref()
+    if not hasattr(ref, "ChebyshevAccel"):
+        pytest.skip("the wrapper build does not expose the raw DOF vectors")
+    from test_gpu_outputs import reference_vtk_text
+    p = random_problem(3, dim, n, ng=2, bc="all")
+    p["NSF"] *= 3.0
+    s = make_ref(ref, p, rt, rt, tol=(1e-8, 1e-8, 1e-8, 500, 5000))
+    s.get_KSF().reshape(-1)[:] = 0.4 * p["NSF"]
+    s.get_SRC().reshape(-1)[:] = np.linspace(0.0, 1.0, 2 * p["ne"])
+    k = s.SolveKeff()
+    phi, J = s.sol_phi(), s.sol_J()
+    nloc = (rt + 1) ** dim
+    nf = 1 if dim == 1 else (rt + 1 if dim == 2 else (rt + 1) ** 2)
+    xs = {"D": p["D"], "SigR": p["SigR"], "NSF": p["NSF"], "Chi": p["Chi"], "KSF": 0.4 * p["NSF"],
+          "SRC": np.linspace(0.0, 1.0, 2 * p["ne"]), "SigS": p["SigS"]}
+    for tag, flags in (("all", (True, True, True)), ("flux", (True, False, False)), ("xs", (False, False, True))):
+        base = str(tmp_path / f"r_{tag}")
+        s.ExportVTK(base, export_flux=flags[0], export_current=flags[1], export_xs=flags[2])
+        want = reference_vtk_text(k, p["xb"], p["yb"], p["zb"], dim, 2, nloc, nf, phi, J, J.size // 2, xs, flags)
+        got = open(base + ".vtk", "rb").read()
+        assert got == want.encode("ascii"), tag

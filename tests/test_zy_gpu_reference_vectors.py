@@ -1,0 +1,84 @@
+"""
+GPU: the CUDA path against vectors produced by the REFERENCE'S OWN CODE (tests/golden/ref_v1.npz, written by
+tools/make_golden_ref.py from the reference's src/FEM.cpp, src/solvers.cpp, src/NeutFEM.cpp compiled unmodified -- see
+oracle/ref_build/build_ref.py; /root/reference does not exist on the GPU box, the vectors travel instead).
+Same cases as tests/test_golden.py (oracle-made vectors) and tests/test_gpu_fused.py (fresh oracle solves); no CPU solve at
+run time. Tolerances: operators 1e-12 relative; k 1e-6, flux 1e-5 (north_star); inner CG iterate count of parity mode +-3.
+(The file name sorts late on purpose: the driver runs pytest -x.)
+"""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import make_gpu, random_problem, relerr
+from test_golden import OPERATOR_CASES, R, _cfgs
+from test_gpu_fused import _solve, path_env
+
+pytestmark = pytest.mark.gpu
+REF = R
+
+
+@pytest.mark.parametrize("name,seed,dim,n,rt,pp,bc", OPERATOR_CASES)
+def test_gpu_reproduces_reference_operators(name, seed, dim, n, rt, pp, bc):
+    p = random_problem(seed, dim, n, ng=2, bc=bc)
+    c = make_gpu(p, rt, pp)
+    x = R[name + "_x"]
+    assert tuple(R[name + "_sizes"]) == (c.n_Phi, c.n_J)
+    assert relerr(c.schur_apply(0, x), R[name + "_Sx_g0"]) < 1e-12
+    assert relerr(c.schur_apply(1, x), R[name + "_Sx_g1"]) < 1e-12
+    assert relerr(c.current_from_flux(0, x), R[name + "_J_g0"]) < 1e-12
+    c.close()
+
+
+@pytest.mark.parametrize("name", ["cfg1_iaea2d_rt0p0", "cfg2_iaea3d_diag", "cfg3_biblis_rt1p1", "cfg4_koeberg_rt2p2"])
+def test_gpu_reproduces_reference_keff(name):
+    from neutfem_b200 import cabi
+    mk, rt, pp, solver, tol, diag = _cfgs()[name]
+    p = mk()
+    c = cabi.Context(rt, pp, p.ng, p.x_breaks, p.y_breaks, p.z_breaks)
+    c.set_solver(solver_type=solver, tol_keff=tol[0], tol_flux=tol[1], max_outer=tol[2], max_inner=tol[3])
+    for a, t, v in p.bcs:
+        c.set_bc(a, t, v)
+    c.upload_xs(D=p.D, SigR=p.SigR, NSF=p.NSF, Chi=p.Chi, SigS=p.SigS)
+    c.build()
+    k, st = c.solve_keff(diag)
+    k_ref = float(R[name + "_k"][0])
+    assert abs(k - k_ref) / k_ref < 1e-6
+    phi = c.get_flux()
+    assert abs(np.linalg.norm(phi) - R[name + "_phi_norm"][0]) / R[name + "_phi_norm"][0] < 1e-5
+    assert relerr(phi[::37], R[name + "_phi_sample"]) < 1e-5
+    c.close()
+
+
+@pytest.mark.parametrize("n,rt", [((16, 9, 5), 1), ((10, 6, 5), 2), ((12, 7, 6), 0)])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_default_path_inner_cg_matches_reference_vectors(n, rt, mode):
+    """Same problems as test_default_path_inner_cg_matches_oracle; the expected solution and iterate count are the
+    reference's own (src/solvers.cpp:577-636 compiled unmodified)."""
+    p = random_problem(21, 3, n, ng=1, bc="all")
+    key = "rows_cg_%dx%dx%d_rt%d" % (n + (rt,))
+    rhs = np.random.default_rng(2).uniform(0.0, 1.0, REF[key + "_phi"].size)
+    phi, it, res, kt = _solve(p, rt, rt, mode, rhs, None)
+    assert kt["path"] == 3.0, "the default (rows) path was not taken"
+    if mode == 0:
+        assert abs(it - int(REF[key + "_its"][0])) <= 3
+    assert relerr(phi, REF[key + "_phi"]) < 1e-7
+
+
+@pytest.mark.parametrize("rt", [1, 0, 2])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_default_path_keff_matches_reference_vectors(rt, mode):
+    """Same problem as test_default_path_keff_matches_oracle; k and every flux DOF are the reference's own."""
+    p = random_problem(9, 3, (8, 6, 5), ng=2, bc="all")
+    p["NSF"] *= 3.0
+    with path_env(None):
+        c = make_gpu(p, rt, rt)
+        c.set_solver(tol_keff=1e-9, tol_flux=1e-9, max_outer=500, max_inner=5000, mode=mode)
+        k, st = c.solve_keff(False)
+        assert c.time_kernels(0, 1, bool(mode))["path"] == 3.0
+        phi = c.get_flux()
+        c.close()
+    k_ref = float(REF[f"rows_keff_rt{rt}_k"][0])
+    assert abs(k - k_ref) / k_ref < 1e-6
+    assert relerr(phi, REF[f"rows_keff_rt{rt}_phi"]) < 1e-5
