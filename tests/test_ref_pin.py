@@ -290,3 +290,38 @@ def test_vtk_restatement_is_byte_identical_to_the_reference_writer(tmp_path, dim
         want = reference_vtk_text(k, p["xb"], p["yb"], p["zb"], dim, 2, nloc, nf, phi, J, J.size // 2, xs, flags)
         got = open(base + ".vtk", "rb").read()
         assert got == want.encode("ascii"), tag
+
+
+def test_reference_cmfd_mode_is_not_a_parity_target():
+    """Record of what SolveKeff(use_cmfd=True) does in the reference's own compiled code (src/NeutFEM.cpp:662-1017, :1748-1761):
+    on its IAEA-2D configuration it stops at k ~ 0.51 -- half the k its own Chebyshev path converges to (1.0290) -- because the
+    x-only D^ correction and the scatter-free coarse source move the fixed point.  The product therefore implements the
+    complete method (oracle/cmfd_oracle.py, nf_cmfd.cuh), whose fixed point IS the unaccelerated eigenpair; this case keeps
+    the evidence executable."""
+    ref = _need_ref()
+    from neutfem_b200 import benchmarks as bm
+    from oracle.neutfem_oracle import OracleNeutFEM, BICGSTAB
+    p = bm.problem_2d("iaea2d", 2)
+    ks = {}
+    for cm in (False, True):
+        s = ref.NeutFEM(0, p.ng, p.x_breaks, p.y_breaks, p.z_breaks)
+        s.set_verbosity(ref.VerbosityLevel.SILENT)
+        s.set_linear_solver(ref.LinearSolverType.BICGSTAB)
+        s.set_tol(1e-7, 1e-6, 1e-6, 500, 5000)
+        for a, t, v in p.bcs:
+            s.set_bc(int(a), ref.BCType(int(t)), float(v))
+        for name, getter in (("D", s.get_D), ("SigR", s.get_SigR), ("NSF", s.get_NSF), ("Chi", s.get_Chi), ("SigS", s.get_SigS)):
+            getter().reshape(-1)[:] = np.asarray(getattr(p, name)).reshape(-1)
+        s.BuildMatrices()
+        if cm:
+            s.initialize_cmfd()
+        ks[cm] = s.SolveKeff(False, [], False, cm)
+    assert abs(ks[False] - 1.02899) < 2e-5
+    assert abs(ks[True] - ks[False]) > 0.1 * ks[False]            # the reference's CMFD path does not reach its own k
+    o = OracleNeutFEM(0, 0, p.ng, p.x_breaks, p.y_breaks, p.z_breaks)
+    o.set_linear_solver(BICGSTAB)
+    o.set_tol(1e-7, 1e-6, 1e-6, 500, 5000)
+    p.apply(o)
+    o.BuildMatrices()
+    k_cmfd = o.SolveKeff(use_cmfd=True)
+    assert abs(k_cmfd - ks[False]) / ks[False] < 5e-6             # the complete method does
