@@ -98,20 +98,22 @@ PYBIND11_MODULE(_neutfem_refshim, m)
 {
     m.doc() = "reference NeutFEM sources (unmodified) over the Eigen stand-in of oracle/ref_build/eigen_shim";
     m.attr("linear_algebra") = "eigen_shim";
+    // every type is module-local: the product's drop-in module (neutfem/_neutfem_eigen) binds classes of the same C++ names,
+    // and pybind11's global type registry is shared by all extension modules of a process
 
-    py::enum_<VerbosityLevel>(m, "VerbosityLevel")
+    py::enum_<VerbosityLevel>(m, "VerbosityLevel", py::module_local())
         .value("SILENT", VerbosityLevel::SILENT)
         .value("LIGHT", VerbosityLevel::LIGHT)
         .value("NORMAL", VerbosityLevel::NORMAL)
         .value("VERBOSE", VerbosityLevel::VERBOSE)
         .value("DEBUG", VerbosityLevel::DEBUG);
-    py::enum_<BCType>(m, "BCType")
+    py::enum_<BCType>(m, "BCType", py::module_local())
         .value("DIRICHLET", BCType::DIRICHLET)
         .value("NEUMANN", BCType::NEUMANN)
         .value("MIRROR", BCType::MIRROR)
         .value("ROBIN", BCType::ROBIN)
         .value("PERIODIC", BCType::PERIODIC);
-    py::enum_<LinearSolverType>(m, "LinearSolverType")
+    py::enum_<LinearSolverType>(m, "LinearSolverType", py::module_local())
         .value("DIRECT_LU", LinearSolverType::DIRECT_LU)
         .value("DIRECT_LDLT", LinearSolverType::DIRECT_LDLT)
         .value("DIRECT_LLT", LinearSolverType::DIRECT_LLT)
@@ -123,7 +125,7 @@ PYBIND11_MODULE(_neutfem_refshim, m)
         .value("BICGSTAB_ILU", LinearSolverType::BICGSTAB_ILU)
         .value("LCG", LinearSolverType::LCG);
 
-    py::class_<NeutFEM>(m, "NeutFEM")
+    py::class_<NeutFEM>(m, "NeutFEM", py::module_local())
         .def(py::init([](int order, int ng, const arr_t &x, const arr_t &y, const arr_t &z) {
             return new NeutFEM(order, ng, to_vec(x), to_vec(y), to_vec(z));
         }))
@@ -211,7 +213,7 @@ PYBIND11_MODULE(_neutfem_refshim, m)
                  return to_np(s.diag_schur_cache_->S_diag_inv[size_t(g)]);
              });
 
-    py::class_<ChebyshevAccel>(m, "ChebyshevAccel")
+    py::class_<ChebyshevAccel>(m, "ChebyshevAccel", py::module_local())
         .def(py::init<int, double>(), py::arg("nmax") = 15, py::arg("sigma") = 0.98)
         .def("reset", &ChebyshevAccel::reset)
         .def("__call__", [](ChebyshevAccel &a, const arr_t &phi) {
@@ -219,7 +221,7 @@ PYBIND11_MODULE(_neutfem_refshim, m)
             a(v);
             return to_np(v);
         });
-    py::class_<AndersonAccel>(m, "AndersonAccel")
+    py::class_<AndersonAccel>(m, "AndersonAccel", py::module_local())
         .def(py::init<int, double>(), py::arg("m") = 5, py::arg("beta") = 1.0)
         .def("reset", &AndersonAccel::reset)
         .def("__call__", [](AndersonAccel &a, const arr_t &phi) {
