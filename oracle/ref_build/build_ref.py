@@ -125,10 +125,11 @@ def build_shim(ref: str) -> dict:
     srcs += [os.path.join(HERE, "ref_stubs.cpp"), os.path.join(HERE, "ref_driver.cpp")]
     cmd = ["g++", "-shared", "-fPIC", "-O3", "-std=c++17", "-ffast-math", "-Wno-deprecated", "-fvisibility=hidden",
            "-finput-charset=UTF-8", "-DNDEBUG", f"-I{sysconfig.get_paths()['include']}", f"-I{pybind11.get_include()}",
-           f"-I{SHIM_DIR}", f"-I{os.path.join(ref, 'include')}", *srcs, "-o", tgt]
+           f"-I{SHIM_DIR}", f"-I{os.path.join(ref, 'include')}", *srcs, "-o", tgt + ".tmp"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         return {"built": False, "path": None, "why": "g++ failed (eigen_shim build): " + r.stderr[-400:], "reference": ref}
+    os.replace(tgt + ".tmp", tgt)          # atomic: a process that has the old file mapped keeps it
     with open(os.path.join(OUT_DIR, "__init__.py"), "w"):
         pass
     return {"built": True, "path": tgt, "reference": ref, "why": "compiled", "linear_algebra": "eigen_shim"}

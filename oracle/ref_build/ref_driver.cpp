@@ -113,6 +113,19 @@ PYBIND11_MODULE(_neutfem_refshim, m)
         .value("MIRROR", BCType::MIRROR)
         .value("ROBIN", BCType::ROBIN)
         .value("PERIODIC", BCType::PERIODIC);
+    py::enum_<BoundaryID>(m, "BoundaryID", py::module_local())
+        .value("LEFT_1D", BoundaryID::LEFT_1D)
+        .value("RIGHT_1D", BoundaryID::RIGHT_1D)
+        .value("LEFT_2D", BoundaryID::LEFT_2D)
+        .value("RIGHT_2D", BoundaryID::RIGHT_2D)
+        .value("TOP_2D", BoundaryID::TOP_2D)
+        .value("BOTTOM_2D", BoundaryID::BOTTOM_2D)
+        .value("FRONT_3D", BoundaryID::FRONT_3D)
+        .value("BACK_3D", BoundaryID::BACK_3D)
+        .value("LEFT_3D", BoundaryID::LEFT_3D)
+        .value("RIGHT_3D", BoundaryID::RIGHT_3D)
+        .value("TOP_3D", BoundaryID::TOP_3D)
+        .value("BOTTOM_3D", BoundaryID::BOTTOM_3D);
     py::enum_<LinearSolverType>(m, "LinearSolverType", py::module_local())
         .value("DIRECT_LU", LinearSolverType::DIRECT_LU)
         .value("DIRECT_LDLT", LinearSolverType::DIRECT_LDLT)

@@ -105,6 +105,44 @@ def test_reference_script_runs_unmodified_on_the_shipped_surface(rel, argv, kref
     assert any(abs(k - kref) < 3e-3 for k in ks), (ks, kref)         # coarse 1x1 mesh: within 300 pcm of the literature value
 
 
+@pytest.mark.parametrize("rel,argv,kref", SCRIPTS)
+def test_reference_script_on_the_reference_build_prints_the_oracle_k(rel, argv, kref, monkeypatch):
+    """The reference end to end -- its own script, unmodified, driving its own compiled code (oracle/_ref, see
+    oracle/ref_build/build_ref.py) -- prints the k-eff the oracle-backed run of the same script prints."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "ref_build"))
+    import build_ref
+    import run_reference_script as rrs
+    build_ref.build()
+    refmod = build_ref.load_any()
+    if refmod is None:
+        pytest.skip("oracle/_ref not built on this box")
+    real = importlib.import_module("neutfem._neutfem_eigen")
+    script = os.path.join(REF, "tests", rel)
+
+    def run(mod):
+        pkg = types.ModuleType("neutfem")
+        pkg._neutfem_eigen = mod
+        monkeypatch.setitem(sys.modules, "neutfem", pkg)
+        monkeypatch.setitem(sys.modules, "neutfem._neutfem_eigen", mod)
+        monkeypatch.setattr(sys, "argv", list(sys.argv))
+        buf = io.StringIO()
+        with redirect_stdout(buf):
+            try:
+                rc = rrs.main(["run_reference_script.py", script] + argv)
+            except SystemExit as e:
+                rc = e.code or 0
+        out = buf.getvalue()
+        assert rc == 0, out[-2000:]
+        return [float(v) for v in re.findall(r"k-?eff[^0-9\n]*([01]\.[0-9]{4,})", out, flags=re.I)]
+
+    k_ref = run(refmod)
+    k_orc = run(_standin(real, set()))
+    assert k_ref and len(k_ref) == len(k_orc), (k_ref, k_orc)
+    for a, b in zip(k_ref, k_orc):
+        assert abs(a - b) < 2e-6, (k_ref, k_orc)                    # printed with 5-6 decimals, script tolerances 1e-5 / 1e-4
+    assert any(abs(k - kref) < 3e-3 for k in k_ref), (k_ref, kref)
+
+
 def test_headless_shims_are_inert():
     import run_reference_script as rrs
     saved = {k: sys.modules.get(k) for k in ("seaborn", "matplotlib", "matplotlib.pyplot")}
