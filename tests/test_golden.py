@@ -125,7 +125,7 @@ def test_oracle_reproduces_reference_operators(name, seed, dim, n, rt, pp, bc):
 def test_oracle_and_reference_vectors_agree_on_every_key():
     """golden_v1 (oracle) against ref_v1 (reference code): operators to rounding, converged k to 1e-10, flux to 1e-6."""
     for key in R.files:
-        if key == "linear_algebra" or key.startswith("rows_"):      # rows_*: checked against a fresh oracle solve below
+        if key == "linear_algebra" or key.startswith("rows_") or key.startswith("cfg4_koeberg34"):   # checked below
             continue
         assert key in G.files, key
         if key.endswith("_sizes") or key.endswith("_x"):
@@ -164,3 +164,12 @@ def test_oracle_reproduces_reference_inner_cg(n, rt):
     key = "rows_cg_%dx%dx%d_rt%d" % (n + (rt,))
     assert abs(s.last_iterations - int(R[key + "_its"][0])) <= 1
     assert relerr(phi, R[key + "_phi"]) < 1e-8
+
+
+def test_oracle_and_reference_agree_on_config4_at_34x34():
+    """BASELINE.json configs[3] at SURVEY's own size (KOEBERG 2-D, 4 groups with up-scatter, blank cells Sigma = 1e8, RT2-P2,
+    n_phi = 10 404 per group, tolerances 1e-7): the committed oracle solve (7 minutes, tools/make_golden_config4.py) against the
+    reference build's (2 minutes, tools/make_golden_ref.py). Measured: k 4e-11, flux 1.3e-8."""
+    g = np.load(os.path.join(HERE, "golden", "config4_koeberg34_rt2p2.npz"))
+    assert abs(float(g["keff"]) - R["cfg4_koeberg34_k"][0]) / R["cfg4_koeberg34_k"][0] < 1e-9
+    assert relerr(g["flux"][::7], R["cfg4_koeberg34_phi_sample"]) < 1e-6

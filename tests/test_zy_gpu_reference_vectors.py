@@ -82,3 +82,22 @@ def test_default_path_keff_matches_reference_vectors(rt, mode):
     k_ref = float(REF[f"rows_keff_rt{rt}_k"][0])
     assert abs(k - k_ref) / k_ref < 1e-6
     assert relerr(phi, REF[f"rows_keff_rt{rt}_phi"]) < 1e-5
+
+
+def test_config4_koeberg_34x34_matches_reference_vectors():
+    """Same solve as tests/test_gpu_keff.py::test_config4_koeberg_34x34_golden; k and the flux sample are the reference build's."""
+    from neutfem_b200 import benchmarks as bm, cabi
+    from oracle.neutfem_oracle import BICGSTAB
+    p = bm.problem_2d("koeberg2d", 2)
+    c = cabi.Context(2, 2, p.ng, p.x_breaks, p.y_breaks, p.z_breaks)
+    c.set_solver(solver_type=BICGSTAB, tol_keff=1e-7, tol_flux=1e-7, max_outer=800, max_inner=8000)
+    for a, t, v in p.bcs:
+        c.set_bc(a, t, v)
+    c.upload_xs(D=p.D, SigR=p.SigR, NSF=p.NSF, Chi=p.Chi, SigS=p.SigS)
+    c.build()
+    k, st = c.solve_keff(False)
+    assert st["converged"] == 1
+    k_ref = float(REF["cfg4_koeberg34_k"][0])
+    assert abs(k - k_ref) / k_ref < 1e-6
+    assert relerr(c.get_flux()[::7], REF["cfg4_koeberg34_phi_sample"]) < 1e-5
+    c.close()

@@ -96,6 +96,21 @@ def main():
         key = "rows_cg_%dx%dx%d_rt%d" % (n + (rt,))
         out[key + "_phi"], out[key + "_its"] = phi, np.array([its], dtype=np.int64)
         print(f"{key}: {its} CG iterations, n_Phi = {s.n_Phi}")
+    # BASELINE.json configs[3] at SURVEY's own size (KOEBERG 2-D, 4 groups, up-scatter, 34x34 cells, RT2-P2, tolerances 1e-7):
+    # about two minutes on the reference build (the oracle-made twin is tests/golden/config4_koeberg34_rt2p2.npz)
+    if "--no-config4" not in sys.argv:
+        p = bm.problem_2d("koeberg2d", 2)
+        s = ref.NeutFEM(2, 2, p.ng, p.x_breaks, p.y_breaks, p.z_breaks)
+        fill(ref, s, p.bcs, p.D, p.SigR, p.NSF, p.Chi, p.SigS)
+        s.set_linear_solver(ref.LinearSolverType.BICGSTAB)
+        s.set_tol(1e-7, 1e-7, 1e-7, 800, 8000)
+        s.BuildMatrices()
+        k = s.SolveKeff()
+        phi = s.sol_phi()
+        out["cfg4_koeberg34_k"] = np.array([k])
+        out["cfg4_koeberg34_phi_norm"] = np.array([np.linalg.norm(phi)])
+        out["cfg4_koeberg34_phi_sample"] = phi[::7].copy()
+        print(f"cfg4_koeberg34: k = {k:.12f}, n = {phi.size}")
     path = os.path.join(ROOT, "tests", "golden", "ref_v1.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")
