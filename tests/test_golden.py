@@ -138,9 +138,11 @@ def test_oracle_and_reference_vectors_agree_on_every_key():
             assert relerr(G[key], R[key]) < 1e-6, key
 
 
-@pytest.mark.parametrize("rt", [0, 1, 2])
+@pytest.mark.parametrize("rt", [0, 1])
 def test_oracle_reproduces_reference_3d_keff(rt):
-    """The 3-D problems of tests/test_gpu_fused.py: converged k and every flux DOF (reference numbering)."""
+    """The 3-D problems of tests/test_gpu_fused.py: converged k and every flux DOF (reference numbering). (RT2: a minute of
+    oracle time, left to tools/make_golden_ref.py's print-out -- measured k 2e-13, flux 2.7e-10 -- and to the RT2 layer and
+    inner-CG cases of tests/test_ref_pin.py.)"""
     p = random_problem(9, 3, (8, 6, 5), ng=2, bc="all")
     p["NSF"] *= 3.0
     o = make_oracle(p, rt, rt)
