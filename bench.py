@@ -265,6 +265,9 @@ def run_reference(args):
         cb["real_reference"] = real
     if not args.no_ladder:
         cb.update({k: v for k, v in cpu_baseline_ladder(args).items()})
+        real3d = real_reference_iaea3d(args, 2)
+        if real3d is not None:
+            cb["real_reference_iaea3d_n2"] = real3d
     cfg = workload_config(args, tuple(args.mesh))
     cfg["inner_solver"] = "reference (unpreconditioned CG from x0 = 0, A factorised per group solve)"
     cfg["parallelism"] = f"{cb['cores']} host threads"
@@ -281,6 +284,44 @@ def run_reference(args):
     }
     print(json.dumps(line), flush=True)
     return 0
+
+
+def real_reference_iaea3d(args, n=2):
+    """The reference's own compiled code (oracle/_ref) on the reference script's own IAEA-3D refinement (n x n cells per
+    assembly, one cell per axial plane; n = 2 -> 38x38x19 cells), RT{rt}-P{p}, script tolerances, ONE outer iteration:
+    BuildMatrices and the outer iteration timed separately. None when oracle/_ref does not exist."""
+    try:
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("build_ref", os.path.join(ROOT, "oracle", "ref_build", "build_ref.py"))
+        br = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(br)
+        ref = br.load_any()
+        if ref is None:
+            return None
+        from neutfem_b200 import benchmarks as bm
+        p = bm.problem_iaea3d(n, 1)
+        s = ref.NeutFEM(args.rt, args.p, p.ng, p.x_breaks, p.y_breaks, p.z_breaks) if args.rt != args.p else ref.NeutFEM(
+            args.rt, p.ng, p.x_breaks, p.y_breaks, p.z_breaks)
+        s.set_verbosity(ref.VerbosityLevel.SILENT)
+        s.set_linear_solver(ref.LinearSolverType.BICGSTAB)
+        p.apply(s)
+        t0 = time.perf_counter()
+        s.BuildMatrices()
+        tb = time.perf_counter() - t0
+        s.set_tol(1e-5, 1e-4, 1e-4, 1, 1000)
+        t0 = time.perf_counter()
+        s.SolveKeff()
+        dt = time.perf_counter() - t0
+        nx, ny, nz = (len(b) - 1 for b in (p.x_breaks, p.y_breaks, p.z_breaks))
+        n_phi = nx * ny * nz * (min(args.rt, args.p) + 1) ** 3
+        full = float(np.prod(args.mesh)) * (min(args.rt, args.p) + 1) ** 3
+        return {"kind": "reference", "linear_algebra": getattr(ref, "linear_algebra", "eigen"), "cores": 1, "mesh": [nx, ny, nz],
+                "n_phi_per_group": n_phi, "seconds_build_matrices": tb, "seconds_per_outer": dt,
+                "EXTRAPOLATED_seconds_per_outer_at_full_mesh": dt / n_phi * full,
+                "note": "reference script's IAEA-3D at n = %d, first outer iteration (flat flux, k = 1), both group solves to tol_flux 1e-4; "
+                        "linear-in-n_phi extrapolation, not a measurement (the reference's 32-bit indices cannot represent the full mesh)" % n}
+    except Exception as e:      # never let the optional arm break the bench line
+        return {"unavailable": f"{type(e).__name__}: {e}"}
 
 
 def cpu_baseline_ladder(args):
