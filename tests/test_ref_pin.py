@@ -355,3 +355,27 @@ def test_reference_ignores_the_solver_enum_on_the_implicit_path():
     for name, (its, phi) in res.items():
         assert its == its0, (name, its, its0)
         assert np.array_equal(phi, phi0), name
+
+
+CF_CASES = [(1, (7, 1, 1), 0, 0), (1, (6, 1, 1), 1, 1), (1, (5, 1, 1), 2, 2), (1, (5, 1, 1), 2, 1), (1, (5, 1, 1), 1, 0),
+            (2, (4, 3, 1), 0, 0), (2, (3, 4, 1), 1, 1), (2, (3, 3, 1), 2, 2), (2, (3, 2, 1), 2, 0), (2, (2, 3, 1), 2, 1),
+            (3, (3, 2, 2), 0, 0), (3, (2, 3, 2), 1, 1), (3, (2, 2, 2), 2, 2), (3, (2, 2, 2), 2, 1), (3, (2, 2, 2), 1, 0)]
+
+
+@pytest.mark.parametrize("dim,n,rt,pp", CF_CASES)
+@pytest.mark.parametrize("bc", ["mixed", "all"])
+def test_kernel_closed_forms_equal_the_reference_schur_product(dim, n, rt, pp, bc):
+    """The matrix-free closed forms the CUDA kernels evaluate (numpy model in tests/closed_form_model.py:
+    per-line condensed tridiagonal systems, mode weights, Dirichlet term) against SchurSolver::SchurProduct of the reference's
+    own compiled code on its quadrature-assembled matrices -- no oracle in between."""
+    ref = _need_ref()
+    if not hasattr(ref, "ChebyshevAccel"):
+        pytest.skip("the wrapper build does not expose the Schur product")
+    from closed_form_model import schur_apply_model
+    p = random_problem(7, dim, n, ng=1, bc=bc)
+    s = make_ref(ref, p, rt, pp)
+    x = np.random.default_rng(3).uniform(0.5, 1.5, s.n_Phi)
+    o = make_oracle(p, rt, pp)                              # only for the mesh widths and the side -> attribute flags
+    f = o.fes
+    y = schur_apply_model(dim, o.rt_order, o.p_order, f.hx, f.hy, f.hz, p["D"], p["SigR"], o._dirichlet_flags(), x)
+    assert relerr(y, s.schur_product(0, x)) < 1e-12
