@@ -3,8 +3,9 @@ GPU: the CMFD acceleration (NF_ACCEL_CMFD, SolveKeff(use_cmfd=True); SURVEY 8(f)
 against oracle/cmfd_oracle.py. tests/test_cmfd.py has already checked the library's CMFD source on the CPU (same functors, run
 in loops); what is left to show here is that the CUDA backend -- functor kernels, the deterministic grid reduction, the device
 line factors of k_factor_lines -- gives the same numbers, one correction at a time and inside the power iteration.
-PARITY UNPINNED at reference level: the reference's own CMFD corrects the x faces only (src/NeutFEM.cpp:866-867), see
-oracle/cmfd_oracle.py. (The file sorts last on purpose: these kernels were added after the last GPU session of the round.)
+Not a parity target at reference level: the reference's own CMFD corrects the x faces only (src/NeutFEM.cpp:866-867) and, run
+from its own compiled code, stops at about half the k of its Chebyshev path (tests/test_ref_pin.py::
+test_reference_cmfd_mode_is_not_a_parity_target); the complete method is specified by oracle/cmfd_oracle.py. (The file sorts last on purpose: these kernels were added after the last GPU session of the round.)
 """
 import numpy as np
 import pytest
