@@ -137,6 +137,27 @@ def single_thread():
         return contextlib.nullcontext()
 
 
+class quiet_fd1:
+    """The reference's constructor prints a banner on the C++ stdout before its verbosity can be set (src/NeutFEM.cpp:236-260);
+    bench.py's stdout carries ONE JSON line, so file descriptor 1 points at /dev/null while the reference's code runs."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        self.null = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(self.null, 1)
+
+    def __exit__(self, *exc):
+        try:
+            import ctypes
+            ctypes.CDLL(None).fflush(None)          # the C++ side buffers its own stdout
+        except Exception:
+            pass
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        os.close(self.null)
+
+
 # ---- CPU side ------------------------------------------------------------------------------------------------------------
 def cpu_lines(args, mesh, max_iter, seconds_cap):
     """All host threads: the reference's inner solve (CG from 0, tol = tol_flux 1e-4, exact A^-1 by per-line Thomas solves)
@@ -206,18 +227,19 @@ def cpu_real_reference(args, mesh, outers, port):
         la = getattr(ref, "linear_algebra", "eigen")
         from neutfem_b200 import benchmarks as bm
         p = bm.problem_iaea3d_synthetic(*mesh)
-        s = ref.NeutFEM(args.rt, args.p, p.ng, p.x_breaks, p.y_breaks, p.z_breaks) if args.rt != args.p else ref.NeutFEM(
-            args.rt, p.ng, p.x_breaks, p.y_breaks, p.z_breaks)
-        s.set_verbosity(ref.VerbosityLevel.SILENT)
-        s.set_linear_solver(ref.LinearSolverType.BICGSTAB)
-        for a, t, v in p.bcs:
-            s.set_bc(int(a), ref.BCType(int(t)), float(v))
-        p.apply(s)
-        s.BuildMatrices()
-        s.set_tol(1e-5, 1e-4, 1e-4, int(outers), 1000)
-        t0 = time.perf_counter()
-        k = s.SolveKeff()
-        dt = time.perf_counter() - t0
+        with quiet_fd1():
+            s = ref.NeutFEM(args.rt, args.p, p.ng, p.x_breaks, p.y_breaks, p.z_breaks) if args.rt != args.p else ref.NeutFEM(
+                args.rt, p.ng, p.x_breaks, p.y_breaks, p.z_breaks)
+            s.set_verbosity(ref.VerbosityLevel.SILENT)
+            s.set_linear_solver(ref.LinearSolverType.BICGSTAB)
+            for a, t, v in p.bcs:
+                s.set_bc(int(a), ref.BCType(int(t)), float(v))
+            p.apply(s)
+            s.BuildMatrices()
+            s.set_tol(1e-5, 1e-4, 1e-4, int(outers), 1000)
+            t0 = time.perf_counter()
+            k = s.SolveKeff()
+            dt = time.perf_counter() - t0
         dof_its = port["cg_iterations"] * port["n_phi_per_group"]
         how = ("Eigen SparseLU + its CG" if la == "eigen" else
                "its own FEM / Schur-CG / outer-iteration code compiled unmodified over our Eigen stand-in (banded LU per group solve)")
@@ -300,18 +322,19 @@ def real_reference_iaea3d(args, n=2):
             return None
         from neutfem_b200 import benchmarks as bm
         p = bm.problem_iaea3d(n, 1)
-        s = ref.NeutFEM(args.rt, args.p, p.ng, p.x_breaks, p.y_breaks, p.z_breaks) if args.rt != args.p else ref.NeutFEM(
-            args.rt, p.ng, p.x_breaks, p.y_breaks, p.z_breaks)
-        s.set_verbosity(ref.VerbosityLevel.SILENT)
-        s.set_linear_solver(ref.LinearSolverType.BICGSTAB)
-        p.apply(s)
-        t0 = time.perf_counter()
-        s.BuildMatrices()
-        tb = time.perf_counter() - t0
-        s.set_tol(1e-5, 1e-4, 1e-4, 1, 1000)
-        t0 = time.perf_counter()
-        s.SolveKeff()
-        dt = time.perf_counter() - t0
+        with quiet_fd1():
+            s = ref.NeutFEM(args.rt, args.p, p.ng, p.x_breaks, p.y_breaks, p.z_breaks) if args.rt != args.p else ref.NeutFEM(
+                args.rt, p.ng, p.x_breaks, p.y_breaks, p.z_breaks)
+            s.set_verbosity(ref.VerbosityLevel.SILENT)
+            s.set_linear_solver(ref.LinearSolverType.BICGSTAB)
+            p.apply(s)
+            t0 = time.perf_counter()
+            s.BuildMatrices()
+            tb = time.perf_counter() - t0
+            s.set_tol(1e-5, 1e-4, 1e-4, 1, 1000)
+            t0 = time.perf_counter()
+            s.SolveKeff()
+            dt = time.perf_counter() - t0
         nx, ny, nz = (len(b) - 1 for b in (p.x_breaks, p.y_breaks, p.z_breaks))
         n_phi = nx * ny * nz * (min(args.rt, args.p) + 1) ** 3
         full = float(np.prod(args.mesh)) * (min(args.rt, args.p) + 1) ** 3
