@@ -165,7 +165,11 @@ PYBIND11_MODULE(_neutfem_refshim, m)
         .def("build_diagonal_cache", &NeutFEM::BuildDiagonalSchurCache)
         .def("initialize_cmfd", &NeutFEM::InitializeCMFD)
         .def("ExportVTK", &NeutFEM::ExportVTK, py::arg("filename"), py::arg("export_flux") = true,
-             py::arg("export_current") = true, py::arg("export_xs") = true, py::arg("export_adjoint") = false)
+             py::arg("export_current") = true, py::arg("export_xs") = false, py::arg("export_adjoint") = false)   // wrapper.cpp:766-771
+        .def("ExportFluxVTK", &NeutFEM::ExportFluxVTK, py::arg("filename"), py::arg("adjoint") = false)
+        .def("ExportXSVTK", &NeutFEM::ExportXSVTK, py::arg("filename"))
+        .def("set_robin_coefficients", &NeutFEM::SetRobinCoefficients)
+        .def("apply_quarter_symmetry", &NeutFEM::ApplyQuarterRotationalSymmetry, py::arg("axis1") = 0, py::arg("axis2") = 1)
         .def("get_D", &NeutFEM::py_get_D)
         .def("get_SRC", &NeutFEM::py_get_SRC)
         .def("get_SigR", &NeutFEM::py_get_SigR)
