@@ -384,3 +384,27 @@ def test_kernel_closed_forms_equal_the_reference_schur_product(dim, n, rt, pp, b
     f = o.fes
     y = schur_apply_model(dim, o.rt_order, o.p_order, f.hx, f.hy, f.hz, p["D"], p["SigR"], o._dirichlet_flags(), x)
     assert relerr(y, s.schur_product(0, x)) < 1e-12
+
+
+@pytest.mark.parametrize("dim,n,rt", [(2, (6, 5, 1), 1), (3, (4, 3, 3), 0)])
+def test_every_bc_type_and_value_is_treated_like_the_reference(dim, n, rt):
+    """NEUMANN / MIRROR / ROBIN / PERIODIC are stored and ignored by the reference (src/NeutFEM.cpp:2128-2131: a side without
+    the Dirichlet term is a zero-flux side of the mixed formulation), and so is the VALUE of a Dirichlet condition; Robin
+    coefficients likewise. Assembled A_g and a converged k with one side of each type and non-zero values."""
+    ref = _need_ref()
+    p = random_problem(18, dim, n, ng=2, bc="none")
+    p["NSF"] *= 3.0
+    nattr = {2: 4, 3: 6}[dim]
+    p["bcs"] = [(a, (a - 1) % 5, 0.3 * a) for a in range(1, nattr + 1)]       # DIRICHLET, NEUMANN, MIRROR, ROBIN, PERIODIC, ...
+    o = make_oracle(p, rt, rt)
+    o.set_tol(1e-10, 1e-10, 1e-10, 2000, 5000)
+    s = make_ref(ref, p, rt, rt)
+    if hasattr(s, "set_robin_coefficients"):
+        s.set_robin_coefficients(4, 0.7, 1.3)
+        s.BuildMatrices()
+    if hasattr(s, "matrix"):
+        for g in range(2):
+            mr, mo = _dense(s.matrix("A", g)), o.A[g].toarray()
+            assert np.abs(mr - mo).max() <= 1e-12 * np.abs(mr).max()
+    k_o, k_r = o.SolveKeff(), s.SolveKeff()
+    assert abs(k_o - k_r) / k_r < 1e-9
