@@ -101,3 +101,21 @@ def test_config4_koeberg_34x34_matches_reference_vectors():
     assert abs(k - k_ref) / k_ref < 1e-6
     assert relerr(c.get_flux()[::7], REF["cfg4_koeberg34_phi_sample"]) < 1e-5
     c.close()
+
+
+@pytest.mark.parametrize("dim,n,rt", [(2, (6, 5, 1), 1), (3, (4, 3, 3), 0)])
+def test_every_bc_type_matches_reference_vectors(dim, n, rt):
+    """One side of each BCType with non-zero values: only DIRICHLET adds a term (src/NeutFEM.cpp:2128-2131), its value is ignored."""
+    from neutfem_b200 import cabi
+    p = random_problem(18, dim, n, ng=2, bc="none")
+    p["NSF"] *= 3.0
+    p["bcs"] = [(a, (a - 1) % 5, 0.3 * a) for a in range(1, {2: 4, 3: 6}[dim] + 1)]
+    c = make_gpu(p, rt, rt)
+    x = np.random.default_rng(18).uniform(0.5, 1.5, c.n_Phi)
+    assert relerr(c.schur_apply(0, x), REF[f"bc5_{dim}d_Sx_g0"]) < 1e-12
+    c.set_solver(tol_keff=1e-10, tol_flux=1e-10, max_outer=2000, max_inner=5000, mode=cabi.MODE_PARITY)
+    k, st = c.solve_keff(False)
+    k_ref = float(REF[f"bc5_{dim}d_k"][0])
+    assert abs(k - k_ref) / k_ref < 1e-6
+    assert relerr(c.get_flux(), REF[f"bc5_{dim}d_phi"]) < 1e-5
+    c.close()

@@ -96,6 +96,20 @@ def main():
         key = "rows_cg_%dx%dx%d_rt%d" % (n + (rt,))
         out[key + "_phi"], out[key + "_its"] = phi, np.array([its], dtype=np.int64)
         print(f"{key}: {its} CG iterations, n_Phi = {s.n_Phi}")
+    # one side of each BCType with non-zero values (stored and ignored except DIRICHLET, src/NeutFEM.cpp:2128-2131)
+    for dim, n, rt in ((2, (6, 5, 1), 1), (3, (4, 3, 3), 0)):
+        p = random_problem(18, dim, n, ng=2, bc="none")
+        bcs = [(a, (a - 1) % 5, 0.3 * a) for a in range(1, {2: 4, 3: 6}[dim] + 1)]
+        s = ref.NeutFEM(rt, rt, 2, p["xb"], p["yb"], p["zb"])
+        fill(ref, s, bcs, p["D"], p["SigR"], 3.0 * p["NSF"], p["Chi"], p["SigS"])
+        s.set_linear_solver(ref.LinearSolverType.BICGSTAB)
+        s.set_tol(1e-10, 1e-10, 1e-10, 2000, 5000)
+        s.BuildMatrices()
+        x = np.random.default_rng(18).uniform(0.5, 1.5, s.n_Phi)
+        out[f"bc5_{dim}d_Sx_g0"] = s.schur_product(0, x)
+        out[f"bc5_{dim}d_k"] = np.array([s.SolveKeff()])
+        out[f"bc5_{dim}d_phi"] = s.sol_phi()
+        print(f"bc5_{dim}d: k = {out[f'bc5_{dim}d_k'][0]:.12f}")
     # BASELINE.json configs[3] at SURVEY's own size (KOEBERG 2-D, 4 groups, up-scatter, 34x34 cells, RT2-P2, tolerances 1e-7):
     # about two minutes on the reference build (the oracle-made twin is tests/golden/config4_koeberg34_rt2p2.npz)
     if "--no-config4" not in sys.argv:
