@@ -5,7 +5,7 @@ Frozen vectors.
     (its src/FEM.cpp, src/solvers.cpp, src/NeutFEM.cpp compiled unmodified by oracle/ref_build/build_ref.py; the npz records
     which linear algebra lay underneath, "eigen" or "eigen_shim").
 CPU: the oracle reproduces both (drift guard + pin against reference-made vectors). GPU: the CUDA path reproduces both
-through the C ABI without any CPU solve at run time (golden_v1 here, ref_v1 in tests/test_zy_gpu_reference_vectors.py). Tolerances: operators 1e-12 relative; k 1e-6, flux 1e-5 (north_star).
+through the C ABI without any CPU solve at run time (golden_v1 here, ref_v1 in tests/test_zzz_gpu_reference_vectors.py). Tolerances: operators 1e-12 relative; k 1e-6, flux 1e-5 (north_star).
 """
 import os
 
