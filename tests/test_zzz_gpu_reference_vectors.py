@@ -119,3 +119,24 @@ def test_every_bc_type_matches_reference_vectors(dim, n, rt):
     assert abs(k - k_ref) / k_ref < 1e-6
     assert relerr(c.get_flux(), REF[f"bc5_{dim}d_phi"]) < 1e-5
     c.close()
+
+
+@pytest.mark.parametrize("use_direct_keff", [True, False])
+def test_adjoint_matches_reference_vectors(use_direct_keff):
+    """Same solve as tests/test_gpu_keff.py::test_adjoint_matches_oracle; k-adjoint and every adjoint flux DOF are the reference's."""
+    from neutfem_b200 import benchmarks as bm, cabi
+    from oracle.neutfem_oracle import BICGSTAB
+    p = bm.problem_2d("iaea2d", 1)
+    c = cabi.Context(1, 1, p.ng, p.x_breaks, p.y_breaks, p.z_breaks)
+    c.set_solver(solver_type=BICGSTAB, tol_keff=1e-8, tol_flux=1e-8, max_outer=600, max_inner=4000)
+    for a, t, v in p.bcs:
+        c.set_bc(a, t, v)
+    c.upload_xs(D=p.D, SigR=p.SigR, NSF=p.NSF, Chi=p.Chi, SigS=p.SigS)
+    c.build()
+    c.solve_keff(False)
+    ka, st = c.solve_adjoint(True, use_direct_keff)
+    tag = "adj_iaea2d_direct%d" % int(use_direct_keff)
+    ka_ref = float(REF[tag + "_k"][0])
+    assert abs(ka - ka_ref) / abs(ka_ref) < 1e-6
+    assert relerr(c.get_flux(adjoint=True), REF[tag + "_phi"]) < 1e-5
+    c.close()

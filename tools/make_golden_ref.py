@@ -110,6 +110,22 @@ def main():
         out[f"bc5_{dim}d_k"] = np.array([s.SolveKeff()])
         out[f"bc5_{dim}d_phi"] = s.sol_phi()
         print(f"bc5_{dim}d: k = {out[f'bc5_{dim}d_k'][0]:.12f}")
+    # adjoint on the reference's IAEA-2D configuration (tests/test_gpu_keff.py::test_adjoint_matches_oracle): both k modes.
+    # Neither mode meets its stopping test within the 600 outer iterations; the iteration is deterministic, so the state after
+    # 600 is still a well-defined vector to compare (with its own k update the adjoint k ends at -0.0547: the reference's
+    # behaviour, reproduced, not endorsed)
+    p = bm.problem_2d("iaea2d", 1)
+    for flag in (True, False):
+        s = ref.NeutFEM(1, p.ng, p.x_breaks, p.y_breaks, p.z_breaks)
+        fill(ref, s, p.bcs, p.D, p.SigR, p.NSF, p.Chi, p.SigS)
+        s.set_linear_solver(ref.LinearSolverType.BICGSTAB)
+        s.set_tol(1e-8, 1e-8, 1e-8, 600, 4000)
+        s.BuildMatrices()
+        s.SolveKeff()
+        tag = "adj_iaea2d_direct%d" % int(flag)
+        out[tag + "_k"] = np.array([s.SolveAdjoint(True, flag)])
+        out[tag + "_phi"] = s.sol_phi_adj()
+        print(f"{tag}: k_adj = {out[tag + '_k'][0]:.12f}")
     # BASELINE.json configs[3] at SURVEY's own size (KOEBERG 2-D, 4 groups, up-scatter, 34x34 cells, RT2-P2, tolerances 1e-7):
     # about two minutes on the reference build (the oracle-made twin is tests/golden/config4_koeberg34_rt2p2.npz)
     if "--no-config4" not in sys.argv:
