@@ -125,7 +125,7 @@ def test_oracle_reproduces_reference_operators(name, seed, dim, n, rt, pp, bc):
 def test_oracle_and_reference_vectors_agree_on_every_key():
     """golden_v1 (oracle) against ref_v1 (reference code): operators to rounding, converged k to 1e-10, flux to 1e-6."""
     for key in R.files:
-        if key == "linear_algebra" or key.startswith(("rows_", "cfg4_koeberg34", "bc5_", "adj_")):   # checked below / in test_ref_pin.py
+        if key == "linear_algebra" or key.startswith(("rows_", "cfg4_koeberg34", "bc5_", "adj_", "coarse_")):   # checked below / in test_ref_pin.py
             continue
         assert key in G.files, key
         if key.endswith("_sizes") or key.endswith("_x"):
@@ -195,3 +195,19 @@ def test_oracle_reproduces_reference_adjoint(use_direct_keff):
     tag = "adj_iaea2d_direct%d" % int(use_direct_keff)
     assert abs(ka - R[tag + "_k"][0]) / abs(R[tag + "_k"][0]) < 1e-9
     assert relerr(o.Sol_Phi_adj, R[tag + "_phi"]) < 1e-8
+
+
+@pytest.mark.parametrize("name,n,rt", [("iaea2d", 2, 0), ("biblis2d", 2, 1)])
+def test_oracle_reproduces_reference_coarse_init(name, n, rt):
+    from neutfem_b200 import benchmarks as bm
+    from oracle.neutfem_oracle import BICGSTAB, OracleNeutFEM
+    p = bm.problem_2d(name, n)
+    o = OracleNeutFEM(rt, rt, p.ng, p.x_breaks, p.y_breaks, p.z_breaks)
+    o.set_linear_solver(BICGSTAB)
+    o.set_tol(1e-9, 1e-9, 1e-9, 600, 5000)
+    p.apply(o)
+    o.BuildMatrices()
+    k = o.SolveKeff(True, [2, 2, 1])
+    tag = f"coarse_{name}_rt{rt}"
+    assert abs(k - R[tag + "_k"][0]) / k < 1e-9
+    assert relerr(np.asarray(o.get_flux()).reshape(-1), R[tag + "_flux"]) < 1e-7

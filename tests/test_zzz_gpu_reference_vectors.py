@@ -140,3 +140,19 @@ def test_adjoint_matches_reference_vectors(use_direct_keff):
     assert abs(ka - ka_ref) / abs(ka_ref) < 1e-6
     assert relerr(c.get_flux(adjoint=True), REF[tag + "_phi"]) < 1e-5
     c.close()
+
+
+@pytest.mark.parametrize("name,n,rt", [("iaea2d", 2, 0), ("biblis2d", 2, 1)])
+def test_dropin_module_coarse_init_matches_reference_vectors(name, n, rt):
+    """The pybind11 drop-in module driven like the reference's scripts (tests/test_gpu_dropin.py), SolveKeff with the coarse-mesh
+    initialisation: k and the cell-mean flux the reference's own SolveCoarse + SolveKeff produce."""
+    from neutfem_b200 import benchmarks as bm
+    from test_gpu_dropin import _script_style_solver
+    p = bm.problem_2d(name, n)
+    s = _script_style_solver(p, rt, rt)
+    s.set_tol(1e-9, 1e-9, 1e-9, 600, 5000)
+    k = s.SolveKeff(use_coarse_init=True, coarse_factors=[2, 2, 1])
+    tag = f"coarse_{name}_rt{rt}"
+    k_ref = float(REF[tag + "_k"][0])
+    assert abs(k - k_ref) / k_ref < 1e-6
+    assert relerr(np.asarray(s.get_flux()).reshape(-1), REF[tag + "_flux"]) < 1e-5

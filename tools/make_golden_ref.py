@@ -126,6 +126,18 @@ def main():
         out[tag + "_k"] = np.array([s.SolveAdjoint(True, flag)])
         out[tag + "_phi"] = s.sol_phi_adj()
         print(f"{tag}: k_adj = {out[tag + '_k'][0]:.12f}")
+    # SolveKeff with the coarse-mesh initialisation, driven like the reference's scripts (tests/test_gpu_dropin.py)
+    for name, n, rt in (("iaea2d", 2, 0), ("biblis2d", 2, 1)):
+        p = bm.problem_2d(name, n)
+        s = ref.NeutFEM(rt, p.ng, p.x_breaks, p.y_breaks, p.z_breaks)
+        fill(ref, s, p.bcs, p.D, p.SigR, p.NSF, p.Chi, p.SigS)
+        s.set_linear_solver(ref.LinearSolverType.BICGSTAB)
+        s.set_tol(1e-9, 1e-9, 1e-9, 600, 5000)
+        s.BuildMatrices()
+        tag = f"coarse_{name}_rt{rt}"
+        out[tag + "_k"] = np.array([s.SolveKeff(True, [2, 2, 1])])
+        out[tag + "_flux"] = np.asarray(s.get_flux()).reshape(-1).copy()          # cell means, (ng, ny, nx)
+        print(f"{tag}: k = {out[tag + '_k'][0]:.12f}")
     # BASELINE.json configs[3] at SURVEY's own size (KOEBERG 2-D, 4 groups, up-scatter, 34x34 cells, RT2-P2, tolerances 1e-7):
     # about two minutes on the reference build (the oracle-made twin is tests/golden/config4_koeberg34_rt2p2.npz)
     if "--no-config4" not in sys.argv:
