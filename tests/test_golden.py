@@ -177,8 +177,8 @@ def test_oracle_and_reference_agree_on_config4_at_34x34():
     assert relerr(g["flux"][::7], R["cfg4_koeberg34_phi_sample"]) < 1e-6
 
 
-@pytest.mark.parametrize("use_direct_keff", [True, False])
-def test_oracle_reproduces_reference_adjoint(use_direct_keff):
+@pytest.mark.parametrize("use_direct_keff", [True, False] if os.environ.get("NEUTFEM_SLOW_TESTS") == "1" else [False])   # 35 s each;
+def test_oracle_reproduces_reference_adjoint(use_direct_keff):          # the direct-k mode is also pinned in tests/test_ref_pin.py
     """Adjoint on the reference's IAEA-2D configuration, both k modes: the oracle walks the reference's trajectory (the
     stopping test is not met within the 600 outer iterations on either side; with its own k update the adjoint k ends at
     -0.0547 -- reproduced, not endorsed)."""
