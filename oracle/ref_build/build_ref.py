@@ -150,6 +150,17 @@ def load():
     return _import("_neutfem_eigen", tgt) if os.path.exists(tgt) else None
 
 
+def load_driver():
+    """The build that has ref_driver.cpp's extra accessors (assembled matrices, raw DOF vectors, one group solve): the Eigen
+    stand-in build, compiled on demand even on a box that also has real Eigen. None without the reference sources."""
+    tgt = shim_target()
+    if not os.path.exists(tgt):
+        ref = find_reference()
+        if ref is None or not build_shim(ref).get("built"):
+            return None
+    return _import("_neutfem_refshim", tgt)
+
+
 def load_any():
     """The real-Eigen build when it exists, else the Eigen-stand-in build, else None."""
     mod = load()

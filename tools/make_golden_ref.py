@@ -38,10 +38,10 @@ def fill(ref, s, bcs, D, SigR, NSF, Chi, SigS):
 
 def main():
     verdict = build_ref.build()
-    ref = build_ref.load_any()
+    ref = build_ref.load_driver()          # the build with ref_driver.cpp's accessors (sol_phi, schur_product, ...)
     if ref is None:
         raise SystemExit(f"no reference build: {verdict}")
-    out = {"linear_algebra": np.array(verdict.get("linear_algebra", "eigen"))}
+    out = {"linear_algebra": np.array(getattr(ref, "linear_algebra", "eigen"))}
     for name, seed, dim, n, rt, pp, bc in OPERATOR_CASES:
         p = random_problem(seed, dim, n, ng=2, bc=bc)
         s = ref.NeutFEM(rt, pp, 2, p["xb"], p["yb"], p["zb"])
