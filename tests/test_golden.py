@@ -125,7 +125,7 @@ def test_oracle_reproduces_reference_operators(name, seed, dim, n, rt, pp, bc):
 def test_oracle_and_reference_vectors_agree_on_every_key():
     """golden_v1 (oracle) against ref_v1 (reference code): operators to rounding, converged k to 1e-10, flux to 1e-6."""
     for key in R.files:
-        if key == "linear_algebra" or key.startswith(("rows_", "cfg4_koeberg34", "bc5_", "adj_", "coarse_")):   # checked below / in test_ref_pin.py
+        if key == "linear_algebra" or key.startswith(("rows_", "cfg4_koeberg34", "bc5_", "adj_", "coarse_", "cfg2_iaea3d_schur")):   # checked below / in test_ref_pin.py
             continue
         assert key in G.files, key
         if key.endswith("_sizes") or key.endswith("_x"):

@@ -156,3 +156,28 @@ def test_dropin_module_coarse_init_matches_reference_vectors(name, n, rt):
     k_ref = float(REF[tag + "_k"][0])
     assert abs(k - k_ref) / k_ref < 1e-6
     assert relerr(np.asarray(s.get_flux()).reshape(-1), REF[tag + "_flux"]) < 1e-5
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_iaea3d_schur_path_matches_reference_vectors(mode):
+    """IAEA-3D 38x38x19 (configs[1]'s mesh, 1e15 void cells) on the NON-diagonal path -- the 3-D Schur CG of a real core, rows path
+    (nx even) -- against the reference's own converged k and flux (tolerances 1e-9 on both sides: at 1e-7 the slowly converging outer iteration
+    leaves the two sides 4e-6 apart in the flux; the reference build needs two minutes for it)."""
+    from neutfem_b200 import benchmarks as bm, cabi
+    from oracle.neutfem_oracle import BICGSTAB
+    p = bm.problem_iaea3d(2, 1)
+    with path_env(None):
+        c = cabi.Context(0, 0, p.ng, p.x_breaks, p.y_breaks, p.z_breaks)
+        c.set_solver(solver_type=BICGSTAB, tol_keff=1e-9, tol_flux=1e-9, max_outer=1000, max_inner=5000, mode=mode)
+        for a, t, v in p.bcs:
+            c.set_bc(a, t, v)
+        c.upload_xs(D=p.D, SigR=p.SigR, NSF=p.NSF, Chi=p.Chi, SigS=p.SigS)
+        c.build()
+        k, st = c.solve_keff(False)
+        assert c.time_kernels(0, 1, bool(mode))["path"] == 3.0
+        phi = c.get_flux()
+        c.close()
+    assert st["converged"] == 1
+    k_ref = float(REF["cfg2_iaea3d_schur_k"][0])
+    assert abs(k - k_ref) / k_ref < 1e-6
+    assert relerr(phi[::11], REF["cfg2_iaea3d_schur_phi_sample"]) < 1e-5

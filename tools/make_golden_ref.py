@@ -138,6 +138,19 @@ def main():
         out[tag + "_k"] = np.array([s.SolveKeff(True, [2, 2, 1])])
         out[tag + "_flux"] = np.asarray(s.get_flux()).reshape(-1).copy()          # cell means, (ng, ny, nx)
         print(f"{tag}: k = {out[tag + '_k'][0]:.12f}")
+    # IAEA-3D 38x38x19 (configs[1]'s mesh, 1e15 void cells) on the NON-diagonal path: the Schur CG of a real 3-D core, tolerances 1e-9 (two minutes)
+    if "--no-config4" not in sys.argv:
+        p = bm.problem_iaea3d(2, 1)
+        s = ref.NeutFEM(0, p.ng, p.x_breaks, p.y_breaks, p.z_breaks)
+        fill(ref, s, p.bcs, p.D, p.SigR, p.NSF, p.Chi, p.SigS)
+        s.set_linear_solver(ref.LinearSolverType.BICGSTAB)
+        s.set_tol(1e-9, 1e-9, 1e-9, 1000, 5000)
+        s.BuildMatrices()
+        k = s.SolveKeff()
+        phi = s.sol_phi()
+        out["cfg2_iaea3d_schur_k"] = np.array([k])
+        out["cfg2_iaea3d_schur_phi_sample"] = phi[::11].copy()
+        print(f"cfg2_iaea3d_schur: k = {k:.12f}, n = {phi.size}")
     # BASELINE.json configs[3] at SURVEY's own size (KOEBERG 2-D, 4 groups, up-scatter, 34x34 cells, RT2-P2, tolerances 1e-7):
     # about two minutes on the reference build (the oracle-made twin is tests/golden/config4_koeberg34_rt2p2.npz)
     if "--no-config4" not in sys.argv:
